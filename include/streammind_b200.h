@@ -1,0 +1,138 @@
+/* streammind_b200 -- C ABI of the B200-native StreamMind hot path.
+ *
+ * The reference (xinding-sys/StreamMind) has NO plugin / operator / FFI interface: its seams are
+ * Python nn.Module method boundaries.  Each entry point below therefore cites
+ * the reference *Python* interface it replaces; the Python host in streammind_b200/ binds these with
+ * ctypes and re-exposes the reference's own method names and argument meaning.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  Unless stated otherwise pointers are
+ *     DEVICE pointers on the handle's device (tensor.data_ptr()); `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream).  Calls are asynchronous on `stream`.
+ *   - every function returns 0 on success, non-zero on error; sm_last_error() gives the message
+ *     (the Python wrapper raises RuntimeError, matching the reference's exception convention).
+ *   - a handle is bound to one device and one video stream's state (Mamba conv/ssm state, KV cache,
+ *     frame count); it is not thread-safe but may be called from any host thread (the reference's
+ *     serving worker calls generate() from a non-main thread: streammind/serve/model_worker.py:271).
+ *   - model dtype: one of fp16 / bf16 for every sub-model of a handle (the reference loads fp16:
+ *     streammind/model/builder.py:54,201; bf16 in eval: eval/inference_video_ego4d_stream_parallel_new.py:160).
+ */
+#ifndef STREAMMIND_B200_H_
+#define STREAMMIND_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sm_handle sm_handle;
+
+enum { SM_DTYPE_F16 = 0, SM_DTYPE_BF16 = 1, SM_DTYPE_F32 = 2 };
+
+typedef struct sm_config {
+    int dtype;              /* SM_DTYPE_F16 | SM_DTYPE_BF16 */
+    int max_frames;         /* frames per sm_vit_encode / sm_frame_step call (chunk size), >= 1 */
+    /* CLIP vision tower (hf CLIPVisionConfig; clip_encoder.py).  vit_layers = 0 disables the tower. */
+    int vit_image, vit_patch, vit_hidden, vit_layers /* layers actually executed = index of
+        hidden_states[select_layer], 23 for CLIP-L with select_layer = -2 */, vit_heads, vit_ffn;
+    float vit_eps;
+    /* projector: PreNet -> Mamba-1 block -> PostNet (multimodal_projector/builder.py:390-414). 0 = off */
+    int proj_d_model, proj_d_state, proj_d_conv, proj_expand;
+    float proj_eps;
+    /* gate: ClsNet = Mistral decoder at L = 1 (multimodal_projector/builder.py:370-385). layers 0 = off */
+    int gate_layers, gate_heads, gate_kv_heads, gate_head_dim, gate_ffn;
+    float gate_eps;
+    /* LLM: MistralForCausalLM (language_model/videollama2_mistral.py:146). layers 0 = off */
+    int llm_hidden, llm_layers, llm_heads, llm_kv_heads, llm_head_dim, llm_ffn, llm_vocab, llm_max_ctx;
+    float llm_eps, llm_rope_theta;
+    int use_graphs;         /* capture the per-frame step and the decode step into CUDA graphs */
+} sm_config;
+
+/* Lifetime.  Replaces model construction in load_pretrained_model (streammind/model/builder.py:30). */
+int sm_create(sm_handle** out, int device, const sm_config* cfg);
+void sm_destroy(sm_handle* h);
+const char* sm_last_error(const sm_handle* h);   /* h may be NULL: error of the last failed sm_create */
+
+/* Weight upload by the reference model's own state_dict key
+ * (e.g. "model.vision_tower.vision_tower.vision_model.encoder.layers.0.self_attn.q_proj.weight",
+ *  "model.mm_projector.mamba_model.ssms.0.mixer.in_proj.weight", "model.layers.3.mlp.up_proj.weight").
+ * Data is copied into the kernel layout (q/k/v and gate/up are packed, the patch conv is re-pitched);
+ * the caller may free `data` afterwards.  Keys that do not influence the path (q_proj/k_proj of the
+ * gate, ViT layers beyond vit_layers, post_layernorm, position_ids, gate embed_tokens) return 0 and
+ * are skipped.  Unknown keys are an error.  dtype must equal cfg.dtype.
+ * Replaces from_pretrained / load_state_dict (streammind/model/builder.py:141-203). */
+int sm_load_weight(sm_handle* h, const char* name, const void* data, int data_on_host, int dtype, int ndim,
+                   const int64_t* shape);
+/* Verifies that every weight the enabled sub-models need was loaded; returns non-zero and lists the
+ * missing keys in sm_last_error otherwise. */
+int sm_finalize_weights(sm_handle* h);
+
+/* Per-stream state: zero the Mamba conv/ssm state, frame count and KV length.  The reference keeps this
+ * state on the model object and never resets it (videollama2_mistral.py:159-165). */
+int sm_stream_reset(sm_handle* h);
+
+/* CLIPVisionTower.forward + feature_select (multimodal_encoder/clip_encoder.py:41-53,31-39).
+ * pixels [B,3,H,W] model dtype, contiguous NCHW -> feats_out [B, P, C] (may be NULL) and
+ * pooled_out [B, C] = mean over patches (multimodal_projector/builder.py:405; may be NULL). */
+int sm_vit_encode(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, void* stream);
+
+/* Mean over the patch axis of externally supplied features (builder.py:405): feats [n, P, C] -> [n, C]. */
+int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, void* stream);
+
+/* One projector step per frame: PreNet -> LayerNorm -> Mamba.step -> +residual -> LayerNorm -> PostNet
+ * (Video_Mamba_seq.forward core, multimodal_projector/builder.py:403-414, evaluated incrementally;
+ * equals row t of the reference's full-sequence call).  pooled [n, C] -> tok_out [n, d_model];
+ * advances the stream's Mamba state by n frames. */
+int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, void* stream);
+
+/* Gate: cls_demo branch (multimodal_projector/builder.py:547-562): tok [d_model] -> logits_out [2] fp32
+ * (index 0 = silence, 1 = respond; videollama2_arch.py:944-948). */
+int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream);
+
+/* Fused per-frame step = sm_vit_encode + sm_projector_step + sm_gate_score for each of the B frames
+ * (encode_images_or_videos_score_cls_inference_allframe_demo, videollama2_arch.py:173-203, in
+ * incremental form).  `pixels` may be a pinned HOST pointer (pixels_on_host = 1; the H2D copy is then
+ * part of the call) or a device pointer.  Outputs (each may be NULL): feats_out [B,P,C],
+ * toks_out [B, d_model], logits_out [B, 2] fp32 (device), and logits_host [B, 2] fp32 (pinned host,
+ * written by an async D2H copy on `stream`; the caller synchronises the stream before reading). */
+int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
+                  float* logits_out, float* logits_host, void* stream);
+
+/* embed_tokens (videollama2_arch.py:967,977): ids [n] int32 device -> out [n, hidden]. */
+int sm_embed_tokens(sm_handle* h, const int32_t* ids, int n, void* out, void* stream);
+
+/* Append P positions to the KV cache (MistralForCausalLM.forward on inputs_embeds with
+ * past_key_values, hf modeling_mistral.py:402-472, as driven by generate(): videollama2_mistral.py:426-431).
+ * embeds [P, hidden].  If last_logits != NULL it receives the fp32 logits [vocab] of the last position. */
+int sm_llm_prefill(sm_handle* h, const void* embeds, int P, float* last_logits, void* stream);
+
+/* Greedy decode loop on the device (GenerationMixin.generate(do_sample=False) + the id rule of
+ * KeywordsStoppingCriteria, mm_utils.py:631-636): must follow sm_llm_prefill.  Produces up to max_new
+ * tokens, stops after emitting any of stop_ids (host array).  ids_out_host [max_new] and n_out_host
+ * are HOST pointers filled on return (the call synchronises `stream`).  The KV cache afterwards holds
+ * every produced token except the last one (which was never fed back), as in HF. */
+int sm_llm_decode(sm_handle* h, int max_new, const int32_t* stop_ids, int n_stop, int32_t* ids_out_host,
+                  int32_t* n_out_host, void* stream);
+
+/* KV length bookkeeping (prefix reuse across fires; the reference re-prefills from scratch:
+ * videollama2_mistral.py:413 past_key_values=None). */
+int sm_kv_len(const sm_handle* h);
+int sm_kv_set_len(sm_handle* h, int len);   /* truncate to a common prefix; len <= current length */
+
+/* Generic building blocks exported for unit tests (tests/test_kernels_gpu.py) */
+int sm_test_gemm(sm_handle* h, const void* x /*[M,K]*/, const void* w /*[N,K]*/, const void* bias /*[N]|NULL*/,
+                 void* out /*[M,N]*/, int M, int N, int K, int epi, int force_swap /*-1 auto*/, int force_bn /*0 auto*/,
+                 void* stream);
+int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out /*[B*S, H*D]*/, int B, int S, int H,
+                      int D, void* stream);
+
+/* Launch accounting: number of this library's kernel launches (graph-replayed kernels included) since
+ * the last call with reset != 0. */
+long long sm_launch_count(sm_handle* h, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMMIND_B200_H_ */

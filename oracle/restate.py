@@ -30,6 +30,46 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# ---------------------------------------------------------------------------------------------
+# Rounding emulation.  On the GPU the reference runs in fp16 / bf16: every tensor an nn.Module
+# returns is materialised in the model dtype (cuBLAS / cuDNN / SDPA accumulate in fp32 and round once
+# on output).  With ``emulate(dtype)`` active the restatement keeps fp32 storage but rounds to ``dtype``
+# at exactly those points, i.e. it computes "the reference's arithmetic with exact accumulation".
+# Feed it weights / inputs that are already representable in ``dtype`` (w.to(dtype).float()).
+# With no emulation (default) everything is plain fp32 -- that mode is pinned by tests/golden/.
+# ---------------------------------------------------------------------------------------------
+_EMULATE: Optional[torch.dtype] = None
+
+
+class emulate:
+    def __init__(self, dtype: Optional[torch.dtype]):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _EMULATE
+        self.prev, _EMULATE = _EMULATE, self.dtype
+        return self
+
+    def __exit__(self, *a):
+        global _EMULATE
+        _EMULATE = self.prev
+
+
+def _r(x: torch.Tensor) -> torch.Tensor:
+    return x if _EMULATE is None else x.to(_EMULATE).to(x.dtype)
+
+
+def _linear(x, w, b=None):
+    return _r(F.linear(x, w, b))
+
+
+def _ln(x, n, w, b, eps):
+    return _r(F.layer_norm(x, (n,), w, b, eps))
+
+
+def _leaky(x):
+    return _r(F.leaky_relu(x))
+
 VIT_PREFIX = "model.vision_tower.vision_tower.vision_model."
 PROJ_PREFIX = "model.mm_projector."
 GATE_PREFIX = "model.mm_projector.cls_net.cls_model."
@@ -111,7 +151,7 @@ class MambaCfg:
 # --------------------------------------------------------------------------------------------
 def quick_gelu(x):
     """hf: activations.py QuickGELUActivation: x * sigmoid(1.702 x)."""
-    return x * torch.sigmoid(1.702 * x)
+    return _r(x * _r(torch.sigmoid(_r(1.702 * x))))
 
 
 def clip_vision_tower(sd: SD, cfg: VitConfig, pixels: torch.Tensor) -> torch.Tensor:
@@ -125,34 +165,32 @@ def clip_vision_tower(sd: SD, cfg: VitConfig, pixels: torch.Tensor) -> torch.Ten
     p = VIT_PREFIX
     B = pixels.shape[0]
     w = sd[p + "embeddings.patch_embedding.weight"]
-    x = F.conv2d(pixels.to(w.dtype), w, bias=None, stride=cfg.patch_size)       # [B,C,gh,gw]
+    x = _r(F.conv2d(pixels.to(w.dtype), w, bias=None, stride=cfg.patch_size))   # [B,C,gh,gw]
     x = x.flatten(2).transpose(1, 2)                                              # [B,N,C]
     cls = sd[p + "embeddings.class_embedding"].expand(B, 1, -1)
-    x = torch.cat([cls, x], dim=1) + sd[p + "embeddings.position_embedding.weight"].unsqueeze(0)
-    x = F.layer_norm(x, (cfg.hidden_size,), sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"],
-                     cfg.layer_norm_eps)
+    x = _r(torch.cat([cls, x], dim=1) + sd[p + "embeddings.position_embedding.weight"].unsqueeze(0))
+    x = _ln(x, cfg.hidden_size, sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"], cfg.layer_norm_eps)
     H, D = cfg.num_heads, cfg.hidden_size // cfg.num_heads
     scale = D ** -0.5
     for i in range(cfg.layers_used):
         lp = f"{p}encoder.layers.{i}."
         r = x
-        h = F.layer_norm(x, (cfg.hidden_size,), sd[lp + "layer_norm1.weight"], sd[lp + "layer_norm1.bias"],
-                         cfg.layer_norm_eps)
-        q = F.linear(h, sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.q_proj.bias"])
-        k = F.linear(h, sd[lp + "self_attn.k_proj.weight"], sd[lp + "self_attn.k_proj.bias"])
-        v = F.linear(h, sd[lp + "self_attn.v_proj.weight"], sd[lp + "self_attn.v_proj.bias"])
+        h = _ln(x, cfg.hidden_size, sd[lp + "layer_norm1.weight"], sd[lp + "layer_norm1.bias"], cfg.layer_norm_eps)
+        q = _linear(h, sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.q_proj.bias"])
+        k = _linear(h, sd[lp + "self_attn.k_proj.weight"], sd[lp + "self_attn.k_proj.bias"])
+        v = _linear(h, sd[lp + "self_attn.v_proj.weight"], sd[lp + "self_attn.v_proj.bias"])
         S = q.shape[1]
         q = q.view(B, S, H, D).transpose(1, 2)
         k = k.view(B, S, H, D).transpose(1, 2)
         v = v.view(B, S, H, D).transpose(1, 2)
-        att = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1, dtype=torch.float32).to(q.dtype)
-        o = (att @ v).transpose(1, 2).reshape(B, S, H * D)
-        x = r + F.linear(o, sd[lp + "self_attn.out_proj.weight"], sd[lp + "self_attn.out_proj.bias"])
+        # fused SDPA: scores and softmax in fp32, probabilities rounded before P@V, fp32 accumulate
+        att = _r(torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1, dtype=torch.float32).to(q.dtype))
+        o = _r((att @ v).transpose(1, 2).reshape(B, S, H * D))
+        x = _r(r + _linear(o, sd[lp + "self_attn.out_proj.weight"], sd[lp + "self_attn.out_proj.bias"]))
         r = x
-        h = F.layer_norm(x, (cfg.hidden_size,), sd[lp + "layer_norm2.weight"], sd[lp + "layer_norm2.bias"],
-                         cfg.layer_norm_eps)
-        h = quick_gelu(F.linear(h, sd[lp + "mlp.fc1.weight"], sd[lp + "mlp.fc1.bias"]))
-        x = r + F.linear(h, sd[lp + "mlp.fc2.weight"], sd[lp + "mlp.fc2.bias"])
+        h = _ln(x, cfg.hidden_size, sd[lp + "layer_norm2.weight"], sd[lp + "layer_norm2.bias"], cfg.layer_norm_eps)
+        h = quick_gelu(_linear(h, sd[lp + "mlp.fc1.weight"], sd[lp + "mlp.fc1.bias"]))
+        x = _r(r + _linear(h, sd[lp + "mlp.fc2.weight"], sd[lp + "mlp.fc2.bias"]))
     return x[:, 1:]
 
 
@@ -175,7 +213,7 @@ class MambaState:
 def pool_patches(feats: torch.Tensor) -> torch.Tensor:
     """``torch.mean(x, dim=2)`` over the patch axis
     (streammind/model/multimodal_projector/builder.py:405).  [..., P, C] -> [..., C]."""
-    return feats.mean(dim=-2)
+    return _r(feats.mean(dim=-2))
 
 
 def projector_sequence(sd: SD, cfg: MambaCfg, feats: torch.Tensor) -> torch.Tensor:
@@ -205,21 +243,21 @@ def projector_step(sd: SD, cfg: MambaCfg, pooled: torch.Tensor, st: MambaState) 
     pooled [C] -> tok [d_model]."""
     p = PROJ_PREFIX
     mp = p + "mamba_model.ssms.0."
-    dt_ = pooled.dtype
-    h0 = F.leaky_relu(F.linear(pooled, sd[p + "pre_net.fc3.weight"], sd[p + "pre_net.fc3.bias"]))
+    h0 = _leaky(_linear(pooled, sd[p + "pre_net.fc3.weight"], sd[p + "pre_net.fc3.bias"]))
     resid = h0
-    hn = F.layer_norm(h0, (cfg.d_model,), sd[mp + "norm.weight"], sd[mp + "norm.bias"], cfg.norm_eps)
-    xz = F.linear(hn, sd[mp + "mixer.in_proj.weight"])
+    hn = _ln(h0, cfg.d_model, sd[mp + "norm.weight"], sd[mp + "norm.bias"], cfg.norm_eps)
+    xz = _linear(hn, sd[mp + "mixer.in_proj.weight"])
     x, z = xz[: cfg.d_inner], xz[cfg.d_inner:]
-    # depth-wise causal conv, rolling window (mamba_simple.py:215-221)
+    # depth-wise causal conv as a rolling window (mamba_simple.py:215-221); rounding follows the
+    # full-sequence path the reference actually runs: act(conv1d(x)) (mamba_simple.py:168-169)
     st.conv.copy_(torch.roll(st.conv, shifts=-1, dims=-1))
     st.conv[:, -1] = x
     cw = sd[mp + "mixer.conv1d.weight"].reshape(cfg.d_inner, cfg.d_conv)
-    x = torch.sum(st.conv * cw, dim=-1) + sd[mp + "mixer.conv1d.bias"]
-    x = F.silu(x).to(dt_)
-    x_db = F.linear(x, sd[mp + "mixer.x_proj.weight"])
+    x = _r(torch.sum(st.conv * cw, dim=-1) + sd[mp + "mixer.conv1d.bias"])
+    x = _r(F.silu(x))
+    x_db = _linear(x, sd[mp + "mixer.x_proj.weight"])
     dt, Bm, Cm = torch.split(x_db, [cfg.dt_rank, cfg.d_state, cfg.d_state], dim=-1)
-    dt = F.linear(dt, sd[mp + "mixer.dt_proj.weight"])
+    dt = _linear(dt, sd[mp + "mixer.dt_proj.weight"])
     A = -torch.exp(sd[mp + "mixer.A_log"].float())
     # selective scan, one step, fp32 internally (selective_scan_interface.py:104-152)
     dtf = F.softplus(dt.float() + sd[mp + "mixer.dt_proj.bias"].float())
@@ -227,11 +265,11 @@ def projector_step(sd: SD, cfg: MambaCfg, pooled: torch.Tensor, st: MambaState) 
     dBx = dtf[:, None] * Bm.float()[None, :] * x.float()[:, None]
     st.ssm.copy_(st.ssm * dA + dBx)
     y = (st.ssm * Cm.float()[None, :]).sum(-1) + sd[mp + "mixer.D"].float() * x.float()
-    y = (y * F.silu(z.float())).to(dt_)
-    out = F.linear(y, sd[mp + "mixer.out_proj.weight"])
-    hid = F.layer_norm(out + resid, (cfg.d_model,), sd[p + "mamba_model.norm_fn.weight"],
-                       sd[p + "mamba_model.norm_fn.bias"], cfg.norm_eps)
-    return F.linear(F.leaky_relu(hid), sd[p + "post_net.fc3.weight"], sd[p + "post_net.fc3.bias"])
+    y = _r((y * F.silu(z.float())).to(pooled.dtype))
+    out = _linear(y, sd[mp + "mixer.out_proj.weight"])
+    hid = _ln(_r(out + resid), cfg.d_model, sd[p + "mamba_model.norm_fn.weight"],
+              sd[p + "mamba_model.norm_fn.bias"], cfg.norm_eps)
+    return _linear(_leaky(hid), sd[p + "post_net.fc3.weight"], sd[p + "post_net.fc3.bias"])
 
 
 # --------------------------------------------------------------------------------------------
@@ -242,7 +280,7 @@ def rms_norm(x, w, eps):
     dt = x.dtype
     xf = x.float()
     xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
-    return w * xf.to(dt)
+    return _r(w * _r(xf.to(dt)))
 
 
 def rope_cos_sin(cfg: MistralCfg, positions: torch.Tensor):
@@ -251,14 +289,14 @@ def rope_cos_sin(cfg: MistralCfg, positions: torch.Tensor):
     inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
     fr = positions.float()[:, None] * inv[None, :]
     emb = torch.cat([fr, fr], dim=-1)
-    return emb.cos(), emb.sin()
+    return _r(emb.cos()), _r(emb.sin())      # cast to the model dtype before use (hf MistralRotaryEmbedding)
 
 
 def apply_rope(x, cos, sin):
     """hf: modeling_mistral.py rotate_half / apply_rotary_pos_emb (:51-81). x [H,L,D]."""
     d = x.shape[-1]
     rot = torch.cat([-x[..., d // 2:], x[..., : d // 2]], dim=-1)
-    return x * cos.to(x.dtype)[None] + rot * sin.to(x.dtype)[None]
+    return _r(_r(x * cos.to(x.dtype)[None]) + _r(rot * sin.to(x.dtype)[None]))
 
 
 @dataclass
@@ -300,9 +338,9 @@ def mistral_forward(sd: SD, prefix: str, cfg: MistralCfg, embeds: torch.Tensor,
     for i in range(cfg.num_layers):
         lp = f"{prefix}model.layers.{i}."
         a = rms_norm(h, sd[lp + "input_layernorm.weight"], cfg.rms_norm_eps)
-        q = F.linear(a, sd[lp + "self_attn.q_proj.weight"]).view(L, Hq, D).transpose(0, 1)
-        k = F.linear(a, sd[lp + "self_attn.k_proj.weight"]).view(L, Hk, D).transpose(0, 1)
-        v = F.linear(a, sd[lp + "self_attn.v_proj.weight"]).view(L, Hk, D).transpose(0, 1)
+        q = _linear(a, sd[lp + "self_attn.q_proj.weight"]).view(L, Hq, D).transpose(0, 1)
+        k = _linear(a, sd[lp + "self_attn.k_proj.weight"]).view(L, Hk, D).transpose(0, 1)
+        v = _linear(a, sd[lp + "self_attn.v_proj.weight"]).view(L, Hk, D).transpose(0, 1)
         q = apply_rope(q, cos, sin)
         k = apply_rope(k, cos, sin)
         if cache.k[i] is not None:
@@ -316,16 +354,16 @@ def mistral_forward(sd: SD, prefix: str, cfg: MistralCfg, embeds: torch.Tensor,
         ctx = kk.shape[1]
         causal = torch.arange(ctx)[None, :] > positions[:, None]
         s = s.masked_fill(causal[None], float("-inf"))
-        pr = torch.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype)
-        o = (pr @ vv).transpose(0, 1).reshape(L, Hq * D)
-        h = h + F.linear(o, sd[lp + "self_attn.o_proj.weight"])
+        pr = _r(torch.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype))
+        o = _r((pr @ vv).transpose(0, 1).reshape(L, Hq * D))
+        h = _r(h + _linear(o, sd[lp + "self_attn.o_proj.weight"]))
         a = rms_norm(h, sd[lp + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-        m = F.silu(F.linear(a, sd[lp + "mlp.gate_proj.weight"])) * F.linear(a, sd[lp + "mlp.up_proj.weight"])
-        h = h + F.linear(m, sd[lp + "mlp.down_proj.weight"])
+        m = _r(_r(F.silu(_linear(a, sd[lp + "mlp.gate_proj.weight"]))) * _linear(a, sd[lp + "mlp.up_proj.weight"]))
+        h = _r(h + _linear(m, sd[lp + "mlp.down_proj.weight"]))
     h = rms_norm(h, sd[prefix + "model.norm.weight"], cfg.rms_norm_eps)
     if not all_logits:
         h = h[-1]
-    return F.linear(h, sd[prefix + "lm_head.weight"]).float()
+    return _linear(h, sd[prefix + "lm_head.weight"]).float()      # logits leave lm_head in model dtype
 
 
 # --------------------------------------------------------------------------------------------
@@ -350,14 +388,14 @@ def gate_logits_degenerate(sd: SD, cfg: MistralCfg, tok: torch.Tensor) -> torch.
     for i in range(cfg.num_layers):
         lp = f"{pfx}model.layers.{i}."
         a = rms_norm(h, sd[lp + "input_layernorm.weight"], cfg.rms_norm_eps)
-        v = F.linear(a, sd[lp + "self_attn.v_proj.weight"]).view(cfg.num_kv_heads, cfg.head_dim)
+        v = _linear(a, sd[lp + "self_attn.v_proj.weight"]).view(cfg.num_kv_heads, cfg.head_dim)
         o = v.repeat_interleave(rep, dim=0).reshape(-1)
-        h = h + F.linear(o, sd[lp + "self_attn.o_proj.weight"])
+        h = _r(h + _linear(o, sd[lp + "self_attn.o_proj.weight"]))
         a = rms_norm(h, sd[lp + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-        m = F.silu(F.linear(a, sd[lp + "mlp.gate_proj.weight"])) * F.linear(a, sd[lp + "mlp.up_proj.weight"])
-        h = h + F.linear(m, sd[lp + "mlp.down_proj.weight"])
+        m = _r(_r(F.silu(_linear(a, sd[lp + "mlp.gate_proj.weight"]))) * _linear(a, sd[lp + "mlp.up_proj.weight"]))
+        h = _r(h + _linear(m, sd[lp + "mlp.down_proj.weight"]))
     h = rms_norm(h, sd[pfx + "model.norm.weight"], cfg.rms_norm_eps)
-    return F.linear(h, sd[pfx + "lm_head.weight"]).float()
+    return _linear(h, sd[pfx + "lm_head.weight"]).float()
 
 
 def gate_decision(logits: torch.Tensor) -> int:

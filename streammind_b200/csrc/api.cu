@@ -1,0 +1,1023 @@
+// C ABI of the B200-native StreamMind hot path (see include/streammind_b200.h for the contract and
+// the reference interfaces each entry point replaces).  This file owns: weight slots (packed kernel
+// layouts), per-stream state, workspaces, TMA tensor maps, launch sequences and CUDA-graph capture.
+#include "../../include/streammind_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "gemm_tc.cuh"
+#include "gemv.cuh"
+#include "misc_kernels.cuh"
+
+using namespace smb;
+
+namespace {
+
+std::string g_create_error;
+
+struct Slot {
+    void* dst = nullptr;       // destination (device)
+    size_t row_bytes = 0;      // bytes per source row
+    size_t rows = 0;           // number of rows
+    size_t dst_pitch = 0;      // destination pitch in bytes (== row_bytes unless re-pitched)
+    size_t numel = 0;
+    bool loaded = false;
+};
+
+struct VitLayer {
+    void *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2;
+};
+struct MistralLayer {
+    void *in_ln, *wqkv /* gate: only the v rows */, *wo, *post_ln, *wgu /* [2F, H]: gate rows then up rows */, *wd;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct sm_handle {
+    sm_config cfg{};
+    int device = 0;
+    int num_sms = 148;
+    int esz = 2;
+    std::string err;
+    std::vector<void*> allocs;
+    std::unordered_map<std::string, Slot> slots;
+    std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
+    PFN_encodeTiled encode = nullptr;
+    long long launches = 0;
+    bool capturing = false;
+    long long captured_launches = 0;
+
+    // ---- ViT
+    int S = 0, P = 0, kpad = 0;
+    void *vit_cls = nullptr, *vit_wpatch = nullptr, *vit_pos = nullptr, *vit_pre_w = nullptr, *vit_pre_b = nullptr;
+    std::vector<VitLayer> vit;
+    void *ws_im = nullptr, *ws_pemb = nullptr, *ws_x = nullptr, *ws_h = nullptr, *ws_qkv = nullptr, *ws_att = nullptr,
+         *ws_mlp = nullptr, *ws_pooled = nullptr, *ws_pixels = nullptr, *ws_feats = nullptr;
+    // ---- projector
+    int d_inner = 0, dt_rank = 0;
+    void *pj_pre_w = nullptr, *pj_pre_b = nullptr, *pj_norm_w = nullptr, *pj_norm_b = nullptr, *pj_in = nullptr,
+         *pj_conv_w = nullptr, *pj_conv_b = nullptr, *pj_xproj = nullptr, *pj_dt_w = nullptr, *pj_dt_b = nullptr,
+         *pj_alog = nullptr, *pj_D = nullptr, *pj_out = nullptr, *pj_nf_w = nullptr, *pj_nf_b = nullptr,
+         *pj_post_w = nullptr, *pj_post_b = nullptr;
+    void *pj_h0 = nullptr, *pj_xc = nullptr, *pj_z = nullptr, *pj_xdb = nullptr, *pj_y = nullptr, *pj_r2 = nullptr,
+         *pj_conv_state = nullptr, *pj_toks = nullptr;
+    float* pj_ssm_state = nullptr;
+    // ---- gate
+    std::vector<MistralLayer> gate;
+    void *gt_norm = nullptr, *gt_head = nullptr, *gt_h = nullptr, *gt_v = nullptr, *gt_m = nullptr;
+    float* gt_logits = nullptr;
+    // ---- llm
+    std::vector<MistralLayer> llm;
+    void *lm_embed = nullptr, *lm_norm = nullptr, *lm_head = nullptr;
+    std::vector<void*> kc, vc;
+    int pmax = 0;
+    void *lw_x = nullptr, *lw_hn = nullptr, *lw_qkv = nullptr, *lw_att = nullptr, *lw_gu = nullptr, *lw_m = nullptr;
+    float *lw_logits = nullptr, *lw_part = nullptr;
+    int *d_pos = nullptr, *d_tok = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_done = nullptr, *d_stop = nullptr;
+    int kv_len = 0;
+    int dec_splits = 16;
+    // ---- graphs
+    std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
+    std::map<int, long long> frame_graph_launches;
+    cudaGraphExec_t decode_graph = nullptr;
+    long long decode_graph_launches = 0;
+};
+
+namespace {
+
+int fail(sm_handle* h, const char* fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CUDA_OK(h, expr)                                                                               \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                            __FILE__, __LINE__);                                       \
+    } while (0)
+
+void* dalloc(sm_handle* h, size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, (bytes + 255) & ~size_t(255)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes);
+    h->allocs.push_back(p);
+    return p;
+}
+
+void add_slot(sm_handle* h, const std::string& name, void* dst, size_t rows, size_t cols, size_t dst_pitch_elems = 0) {
+    Slot s;
+    s.dst = dst;
+    s.rows = rows;
+    s.row_bytes = cols * h->esz;
+    s.dst_pitch = (dst_pitch_elems ? dst_pitch_elems : cols) * h->esz;
+    s.numel = rows * cols;
+    h->slots[name] = s;
+}
+
+inline void count_launch(sm_handle* h) {
+    if (h->capturing) h->captured_launches++; else h->launches++;
+}
+
+// ------------------------------------------------------------------------------------------ tensor maps
+const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int box_rows) {
+    auto key = std::make_tuple(ptr, rows, K, box_rows);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) return &it->second;
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = h->cfg.dtype == SM_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = h->encode(&m, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fail(h, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d K=%d box=%d", (int)r, ptr, rows, K, box_rows);
+        return nullptr;
+    }
+    auto ins = h->tmaps.emplace(key, m);
+    return &ins.first->second;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM
+struct GemmPlan { int swap, bn; };
+
+GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms) {
+    double best = 1e30;
+    GemmPlan bp{0, 128};
+    const double ksteps = std::ceil(K / 16.0);
+    const double bytes_w = 2.0 * feats * K, bytes_x = 2.0 * tokens * K;
+    auto eval = [&](int swap, int bn) {
+        const long ctas = swap ? (long)((feats + 127) / 128) * ((tokens + bn - 1) / bn)
+                               : (long)((tokens + 127) / 128) * ((feats + bn - 1) / bn);
+        const double step = std::max(bn / 2.0, 32.0 + bn / 4.0);           // MMA vs smem-read bound per K=16
+        const double epi = swap ? 40.0 * bn : 14.0 * bn;                    // TMEM drain + stores
+        const double per_cta = ksteps * step + 2500.0 + epi;
+        const double waves = std::ceil((double)ctas / num_sms);
+        const double active = std::min<double>(ctas, num_sms);
+        const double mem = (bytes_w + bytes_x) / (active * 36.0);           // ~36 B/clk/SM of L2->SM bandwidth
+        const double cost = std::max(waves * per_cta, mem + 2500.0);
+        if (cost < best) { best = cost; bp = {swap, bn}; }
+    };
+    if (feats % 16 == 0)
+        for (int bn : {32, 64, 128, 256})
+            if (bn <= feats) eval(0, bn);
+    for (int bn = 16; bn <= 256; bn += 16) {
+        eval(1, bn);
+        if (bn >= tokens) break;
+    }
+    return bp;
+}
+
+template <typename T>
+int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
+                  int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0) {
+    if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
+    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms);
+    if (force_swap >= 0) p.swap = force_swap;
+    if (force_bn > 0) p.bn = force_bn;
+    if (!p.swap && (feats % 16 != 0)) return fail(h, "gemm: non-swapped layout needs features %% 16 == 0");
+    const CUtensorMap *ta, *tb;
+    GemmArgs a{};
+    dim3 grid;
+    if (!p.swap) {
+        ta = get_tmap(h, x, tokens, K, kGemmBM);
+        tb = get_tmap(h, w, feats, K, p.bn);
+        a.Ma = tokens; a.Nb = feats;
+        grid = dim3((tokens + kGemmBM - 1) / kGemmBM, (feats + p.bn - 1) / p.bn);
+    } else {
+        ta = get_tmap(h, w, feats, K, kGemmBM);
+        tb = get_tmap(h, x, tokens, K, p.bn);
+        a.Ma = feats; a.Nb = tokens;
+        grid = dim3((feats + kGemmBM - 1) / kGemmBM, (tokens + p.bn - 1) / p.bn);
+    }
+    if (!ta || !tb) return 1;
+    a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
+    a.nstage = gemm_num_stages(p.bn); a.epi = epi;
+    const int smem = gemm_smem_bytes(p.bn);
+    gemm_tc_kernel<T><<<grid, kGemmThreads, smem, st>>>(*ta, *tb, a);
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
+                int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0) {
+    if (h->cfg.dtype == SM_DTYPE_BF16)
+        return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn);
+    return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn);
+}
+
+// ------------------------------------------------------------------------------------------ GEMV
+template <typename T>
+int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
+    if (a.K % 8 != 0) return fail(h, "gemv: K=%d must be a multiple of 8", a.K);
+    a.seg_len = 1024;
+    int grid = std::min(a.N, 2 * h->num_sms);
+    const int rows_per_cta = (a.N + grid - 1) / grid;
+    grid = (a.N + rows_per_cta - 1) / rows_per_cta;
+    const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
+    const size_t smem = ((a.K * 2 + 15) & ~15) + static_cast<size_t>(nmat) * rows_per_cta * nseg * sizeof(float);
+    if (smem > 100 * 1024) return fail(h, "gemv: K=%d too large for the staging buffer", a.K);
+    if (nmat == 1) gemv_kernel<T, 1><<<grid, kGemvThreads, smem, st>>>(a);
+    else gemv_kernel<T, 2><<<grid, kGemvThreads, smem, st>>>(a);
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+int launch_gemv(sm_handle* h, const GemvArgs& a, int nmat, cudaStream_t st) {
+    if (h->cfg.dtype == SM_DTYPE_BF16) return launch_gemv_t<__nv_bfloat16>(h, a, nmat, st);
+    return launch_gemv_t<__half>(h, a, nmat, st);
+}
+GemvArgs gv(const void* W, int N, int K, int pro, const void* x0, int epi, void* y) {
+    GemvArgs a{};
+    a.W0 = W; a.N = N; a.K = K; a.pro = pro; a.x0 = x0; a.epi = epi; a.y = y;
+    return a;
+}
+
+#define DISPATCH_T(h, T, ...)                          \
+    if ((h)->cfg.dtype == SM_DTYPE_BF16) {             \
+        using T = __nv_bfloat16;                       \
+        __VA_ARGS__                                    \
+    } else {                                           \
+        using T = __half;                              \
+        __VA_ARGS__                                    \
+    }
+
+// ------------------------------------------------------------------------------------------ attention
+template <typename T, int D>
+int launch_attn_t(sm_handle* h, const AttnArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
+    constexpr int smem = attn_smem_bytes<D>();
+    attention_kernel<T, D><<<dim3(q_tiles, heads, batch), kAttnThreads, smem, st>>>(a);
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cudaStream_t st) {
+    const int q_tiles = (a.q_len + kAttnBQ - 1) / kAttnBQ;
+    if (D == 64) { DISPATCH_T(h, T, return launch_attn_t<T, 64>(h, a, q_tiles, heads, batch, st);) }
+    if (D == 128) { DISPATCH_T(h, T, return launch_attn_t<T, 128>(h, a, q_tiles, heads, batch, st);) }
+    return fail(h, "attention: head_dim %d not supported (64 or 128)", D);
+}
+
+template <typename T>
+int init_kernel_attrs_t(sm_handle* h) {
+    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
+    CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ sub-model runners
+int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn;
+    DISPATCH_T(h, T, {
+        const long long n = static_cast<long long>(B) * P * h->kpad;
+        im2col_kernel<T><<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256, 0, st>>>(
+            reinterpret_cast<const T*>(pixels), reinterpret_cast<T*>(h->ws_im), B, c.vit_image, c.vit_patch, h->kpad);
+        count_launch(h);
+    })
+    if (launch_gemm(h, h->ws_im, B * P, h->vit_wpatch, C, h->kpad, nullptr, h->ws_pemb, C, EPI_STORE, st)) return 1;
+    const int warps_per_block = 8;
+    const int ln_blocks = (rows + warps_per_block - 1) / warps_per_block;
+    DISPATCH_T(h, T, {
+        vit_embed_ln_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+            (const T*)h->ws_pemb, (const T*)h->vit_cls, (const T*)h->vit_pos, (const T*)h->vit_pre_w,
+            (const T*)h->vit_pre_b, (const T*)h->vit[0].ln1_w, (const T*)h->vit[0].ln1_b, (T*)h->ws_x, (T*)h->ws_h, rows,
+            S, C, c.vit_eps);
+        count_launch(h);
+    })
+    const int D = C / c.vit_heads;
+    for (int l = 0; l < c.vit_layers; ++l) {
+        const VitLayer& L = h->vit[l];
+        if (l > 0) {
+            DISPATCH_T(h, T, {
+                layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+                    (const T*)h->ws_x, (const T*)L.ln1_w, (const T*)L.ln1_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                count_launch(h);
+            })
+        }
+        if (launch_gemm(h, h->ws_h, rows, L.wqkv, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, st)) return 1;
+        AttnArgs a{};
+        a.q = h->ws_qkv;
+        a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
+        a.v = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(2 * C) * 2;
+        a.o = h->ws_att;
+        a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
+        a.q_ss = a.k_ss = a.v_ss = 3 * C;
+        a.k_hs = a.v_hs = D;
+        a.o_bs = static_cast<long long>(S) * C;
+        a.o_ss = C;
+        a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
+        a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+        if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
+        if (launch_gemm(h, h->ws_att, rows, L.wo, C, C, L.bo, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
+        DISPATCH_T(h, T, {
+            layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+                (const T*)h->ws_x, (const T*)L.ln2_w, (const T*)L.ln2_b, (T*)h->ws_h, rows, C, c.vit_eps);
+            count_launch(h);
+        })
+        if (launch_gemm(h, h->ws_h, rows, L.w1, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, st)) return 1;
+        if (launch_gemm(h, h->ws_mlp, rows, L.w2, C, F, L.b2, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
+    }
+    DISPATCH_T(h, T, {
+        vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
+                                                                         (T*)pooled_out, S, C);
+        count_launch(h);
+    })
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int Dm = c.proj_d_model, Di = h->d_inner, R = h->dt_rank, N = c.proj_d_state, C = c.vit_hidden;
+    GemvArgs a = gv(h->pj_pre_w, Dm, C, PRO_PLAIN, pooled, GEPI_LEAKY, h->pj_h0);
+    a.bias = h->pj_pre_b;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    a = gv(h->pj_in, 2 * Di, Dm, PRO_LAYERNORM, h->pj_h0, GEPI_MAMBA_CONV, h->pj_xc);
+    a.nw = h->pj_norm_w; a.nb = h->pj_norm_b; a.eps = c.proj_eps;
+    a.conv_state = h->pj_conv_state; a.conv_w = h->pj_conv_w; a.conv_b = h->pj_conv_b; a.z_out = h->pj_z;
+    a.d_inner = Di; a.d_conv = c.proj_d_conv;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    a = gv(h->pj_xproj, R + 2 * N, Di, PRO_PLAIN, h->pj_xc, GEPI_STORE, h->pj_xdb);
+    if (launch_gemv(h, a, 1, st)) return 1;
+    ScanArgs s{};
+    s.W_dt = h->pj_dt_w; s.b_dt = h->pj_dt_b; s.A_log = h->pj_alog; s.D = h->pj_D; s.xdb = h->pj_xdb; s.x = h->pj_xc;
+    s.z = h->pj_z; s.state = h->pj_ssm_state; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
+    const int scan_smem = ((R + 2 * N) * 2 + 15) & ~15;
+    DISPATCH_T(h, T, {
+        mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 4 * h->num_sms), 256, scan_smem, st>>>(s);
+        count_launch(h);
+    })
+    a = gv(h->pj_out, Dm, Di, PRO_PLAIN, h->pj_y, GEPI_ADD_TO, h->pj_r2);
+    a.resid = h->pj_h0;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    a = gv(h->pj_post_w, Dm, Dm, PRO_LN_LEAKY, h->pj_r2, GEPI_STORE, tok_out);
+    a.nw = h->pj_nf_w; a.nb = h->pj_nf_b; a.eps = c.proj_eps; a.bias = h->pj_post_b;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    return 0;
+}
+
+int run_gate(sm_handle* h, const void* tok, float* logits_out, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int H = c.proj_d_model, Hq = c.gate_heads, Hk = c.gate_kv_heads, D = c.gate_head_dim, F = c.gate_ffn;
+    CUDA_OK(h, cudaMemcpyAsync(h->gt_h, tok, static_cast<size_t>(H) * h->esz, cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < c.gate_layers; ++l) {
+        const MistralLayer& L = h->gate[l];
+        GemvArgs a = gv(L.wqkv, Hk * D, H, PRO_RMSNORM, h->gt_h, GEPI_STORE, h->gt_v);
+        a.nw = L.in_ln; a.eps = c.gate_eps;
+        if (launch_gemv(h, a, 1, st)) return 1;
+        a = gv(L.wo, H, Hq * D, PRO_GQA_EXPAND, h->gt_v, GEPI_RESID, nullptr);
+        a.resid = h->gt_h; a.gqa_rep = Hq / Hk; a.head_dim = D;
+        if (launch_gemv(h, a, 1, st)) return 1;
+        a = gv(L.wgu, F, H, PRO_RMSNORM, h->gt_h, GEPI_SWIGLU, h->gt_m);
+        a.W1 = reinterpret_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz;
+        a.nw = L.post_ln; a.eps = c.gate_eps;
+        if (launch_gemv(h, a, 2, st)) return 1;
+        a = gv(L.wd, H, F, PRO_PLAIN, h->gt_m, GEPI_RESID, nullptr);
+        a.resid = h->gt_h;
+        if (launch_gemv(h, a, 1, st)) return 1;
+    }
+    GemvArgs a = gv(h->gt_head, 2, H, PRO_RMSNORM, h->gt_h, GEPI_F32, logits_out);
+    a.nw = h->gt_norm; a.eps = c.gate_eps;
+    return launch_gemv(h, a, 1, st);
+}
+
+// one decode step: feeds the token in d_tok at position *d_pos, leaves the next token in d_tok
+int run_decode_step(sm_handle* h, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn;
+    const int QKV = (Hq + 2 * Hk) * D;
+    if (D != 128) return fail(h, "llm decode: head_dim %d not supported (128)", D);
+    DISPATCH_T(h, T, {
+        gather_rows_kernel<T><<<1, 256, 0, st>>>((const T*)h->lm_embed, h->d_tok, (T*)h->lw_x, 1, H);
+        count_launch(h);
+    })
+    const float scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+    for (int l = 0; l < c.llm_layers; ++l) {
+        const MistralLayer& L = h->llm[l];
+        GemvArgs a = gv(L.wqkv, QKV, H, PRO_RMSNORM, h->lw_x, GEPI_STORE, h->lw_qkv);
+        a.nw = L.in_ln; a.eps = c.llm_eps;
+        if (launch_gemv(h, a, 1, st)) return 1;
+        DISPATCH_T(h, T, {
+            rope_append_kernel<T><<<8, 256, 0, st>>>((T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], 1, Hq, Hk, D,
+                                                     c.llm_max_ctx, h->d_pos, 0, c.llm_rope_theta);
+            count_launch(h);
+            decode_attn_partial_kernel<T, 128><<<dim3(h->dec_splits, Hk), 128, 0, st>>>(
+                (const T*)h->lw_qkv, (const T*)h->kc[l], (const T*)h->vc[l], h->lw_part, Hq, Hk, c.llm_max_ctx,
+                h->d_pos, 0, scale_log2e);
+            count_launch(h);
+            decode_attn_combine_kernel<T, 128><<<Hq, 128, 0, st>>>(h->lw_part, (T*)h->lw_att, h->dec_splits);
+            count_launch(h);
+        })
+        a = gv(L.wo, H, Hq * D, PRO_PLAIN, h->lw_att, GEPI_RESID, nullptr);
+        a.resid = h->lw_x;
+        if (launch_gemv(h, a, 1, st)) return 1;
+        a = gv(L.wgu, F, H, PRO_RMSNORM, h->lw_x, GEPI_SWIGLU, h->lw_m);
+        a.W1 = reinterpret_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz;
+        a.nw = L.post_ln; a.eps = c.llm_eps;
+        if (launch_gemv(h, a, 2, st)) return 1;
+        a = gv(L.wd, H, F, PRO_PLAIN, h->lw_m, GEPI_RESID, nullptr);
+        a.resid = h->lw_x;
+        if (launch_gemv(h, a, 1, st)) return 1;
+    }
+    GemvArgs a = gv(h->lm_head, c.llm_vocab, H, PRO_RMSNORM, h->lw_x, GEPI_F32, h->lw_logits);
+    a.nw = h->lm_norm; a.eps = c.llm_eps;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    argmax_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, h->d_tok, h->d_out, h->d_nout, h->d_pos, h->d_stop,
+                                      h->d_done);
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn;
+    const int QKV = (Hq + 2 * Hk) * D;
+    CUDA_OK(h, cudaMemcpyAsync(h->lw_x, embeds, static_cast<size_t>(P) * H * h->esz, cudaMemcpyDeviceToDevice, st));
+    const int nb = (P + 7) / 8;
+    for (int l = 0; l < c.llm_layers; ++l) {
+        const MistralLayer& L = h->llm[l];
+        DISPATCH_T(h, T, {
+            rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            count_launch(h);
+        })
+        if (launch_gemm(h, h->lw_hn, P, L.wqkv, QKV, H, nullptr, h->lw_qkv, QKV, EPI_STORE, st)) return 1;
+        DISPATCH_T(h, T, {
+            const long long tot = static_cast<long long>(P) * ((Hq + Hk) * (D / 2) + Hk * D);
+            rope_append_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 2048)), 256, 0, st>>>(
+                (T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], P, Hq, Hk, D, c.llm_max_ctx, nullptr, pos0, c.llm_rope_theta);
+            count_launch(h);
+        })
+        AttnArgs a{};
+        a.q = h->lw_qkv; a.k = h->kc[l]; a.v = h->vc[l]; a.o = h->lw_att;
+        a.q_bs = 0; a.q_ss = QKV;
+        a.k_bs = a.v_bs = 0; a.k_hs = a.v_hs = static_cast<long long>(c.llm_max_ctx) * D; a.k_ss = a.v_ss = D;
+        a.o_bs = 0; a.o_ss = Hq * D;
+        a.q_len = P; a.kv_len = pos0 + P; a.q_pos0 = pos0; a.causal = 1; a.group = Hq / Hk;
+        a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+        if (launch_attn(h, a, D, Hq, 1, st)) return 1;
+        if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
+        DISPATCH_T(h, T, {
+            rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            count_launch(h);
+        })
+        if (launch_gemm(h, h->lw_hn, P, L.wgu, 2 * F, H, nullptr, h->lw_gu, 2 * F, EPI_STORE, st)) return 1;
+        DISPATCH_T(h, T, {
+            const long long tot = static_cast<long long>(P) * F;
+            swiglu_rows_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 4096)), 256, 0, st>>>(
+                (const T*)h->lw_gu, (T*)h->lw_m, P, F);
+            count_launch(h);
+        })
+        if (launch_gemm(h, h->lw_m, P, L.wd, H, F, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
+    }
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* sm_last_error(const sm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int sm_create(sm_handle** out, int device, const sm_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, "sm_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "sm_create: no CUDA device visible (the CUDA path is the only path; there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, "sm_create: device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, "sm_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (cfg->dtype != SM_DTYPE_F16 && cfg->dtype != SM_DTYPE_BF16) return fail(nullptr, "sm_create: dtype must be fp16 or bf16");
+    cudaSetDevice(device);
+    sm_handle* h = new sm_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    const sm_config& c = h->cfg;
+    if (c.max_frames < 1) h->cfg.max_frames = 1;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        delete h;
+        return fail(nullptr, "sm_create: cuTensorMapEncodeTiled not available from the driver");
+    }
+    h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    {
+        int rc = 0;
+        DISPATCH_T(h, T, rc = init_kernel_attrs_t<T>(h);)
+        if (rc) { g_create_error = h->err; delete h; return 1; }
+    }
+    const size_t e = h->esz;
+    const int Bm = h->cfg.max_frames;
+    bool oom = false;
+    auto A = [&](size_t n) { void* p = dalloc(h, n); if (!p) oom = true; return p; };
+
+    if (c.vit_image > 0 && c.vit_patch > 0) {
+        const int gw0 = c.vit_image / c.vit_patch;
+        h->P = gw0 * gw0;
+        h->S = h->P + 1;
+    }
+    // ---------------- ViT
+    if (c.vit_layers > 0) {
+        if (c.vit_hidden % c.vit_heads || c.vit_hidden / c.vit_heads != 64 || c.vit_hidden % 64 || c.vit_ffn % 64 ||
+            c.vit_hidden > 1024) {
+            delete h;
+            return fail(nullptr, "sm_create: ViT needs head_dim 64, hidden %% 64 == 0, hidden <= 1024, ffn %% 64 == 0");
+        }
+        const int C = c.vit_hidden, F = c.vit_ffn, gw = c.vit_image / c.vit_patch;
+        h->P = gw * gw;
+        h->S = h->P + 1;
+        const int kreal = 3 * c.vit_patch * c.vit_patch;
+        h->kpad = (kreal + 63) / 64 * 64;
+        const std::string p = "model.vision_tower.vision_tower.vision_model.";
+        h->vit_cls = A(C * e); add_slot(h, p + "embeddings.class_embedding", h->vit_cls, 1, C);
+        h->vit_wpatch = A(static_cast<size_t>(C) * h->kpad * e);
+        add_slot(h, p + "embeddings.patch_embedding.weight", h->vit_wpatch, C, kreal, h->kpad);
+        h->vit_pos = A(static_cast<size_t>(h->S) * C * e);
+        add_slot(h, p + "embeddings.position_embedding.weight", h->vit_pos, h->S, C);
+        h->vit_pre_w = A(C * e); add_slot(h, p + "pre_layrnorm.weight", h->vit_pre_w, 1, C);
+        h->vit_pre_b = A(C * e); add_slot(h, p + "pre_layrnorm.bias", h->vit_pre_b, 1, C);
+        h->vit.resize(c.vit_layers);
+        for (int l = 0; l < c.vit_layers; ++l) {
+            VitLayer& L = h->vit[l];
+            const std::string lp = p + "encoder.layers." + std::to_string(l) + ".";
+            L.ln1_w = A(C * e); add_slot(h, lp + "layer_norm1.weight", L.ln1_w, 1, C);
+            L.ln1_b = A(C * e); add_slot(h, lp + "layer_norm1.bias", L.ln1_b, 1, C);
+            L.ln2_w = A(C * e); add_slot(h, lp + "layer_norm2.weight", L.ln2_w, 1, C);
+            L.ln2_b = A(C * e); add_slot(h, lp + "layer_norm2.bias", L.ln2_b, 1, C);
+            L.wqkv = A(static_cast<size_t>(3) * C * C * e);
+            L.bqkv = A(static_cast<size_t>(3) * C * e);
+            const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+            for (int j = 0; j < 3; ++j) {
+                add_slot(h, lp + "self_attn." + nm[j] + ".weight", (char*)L.wqkv + static_cast<size_t>(j) * C * C * e, C, C);
+                add_slot(h, lp + "self_attn." + nm[j] + ".bias", (char*)L.bqkv + static_cast<size_t>(j) * C * e, 1, C);
+            }
+            L.wo = A(static_cast<size_t>(C) * C * e); add_slot(h, lp + "self_attn.out_proj.weight", L.wo, C, C);
+            L.bo = A(C * e); add_slot(h, lp + "self_attn.out_proj.bias", L.bo, 1, C);
+            L.w1 = A(static_cast<size_t>(F) * C * e); add_slot(h, lp + "mlp.fc1.weight", L.w1, F, C);
+            L.b1 = A(F * e); add_slot(h, lp + "mlp.fc1.bias", L.b1, 1, F);
+            L.w2 = A(static_cast<size_t>(C) * F * e); add_slot(h, lp + "mlp.fc2.weight", L.w2, C, F);
+            L.b2 = A(C * e); add_slot(h, lp + "mlp.fc2.bias", L.b2, 1, C);
+        }
+        const size_t rows = static_cast<size_t>(Bm) * h->S;
+        h->ws_pixels = A(static_cast<size_t>(Bm) * 3 * c.vit_image * c.vit_image * e);
+        h->ws_im = A(static_cast<size_t>(Bm) * h->P * h->kpad * e);
+        h->ws_pemb = A(static_cast<size_t>(Bm) * h->P * C * e);
+        h->ws_x = A(rows * C * e);
+        h->ws_h = A(rows * C * e);
+        h->ws_qkv = A(rows * 3 * C * e);
+        h->ws_att = A(rows * C * e);
+        h->ws_mlp = A(rows * F * e);
+        h->ws_pooled = A(static_cast<size_t>(Bm) * C * e);
+        h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
+    }
+    // ---------------- projector
+    if (c.proj_d_model > 0) {
+        const int Dm = c.proj_d_model, C = c.vit_hidden, N = c.proj_d_state, W = c.proj_d_conv;
+        h->d_inner = c.proj_expand * Dm;
+        h->dt_rank = (Dm + 15) / 16;
+        const int Di = h->d_inner, R = h->dt_rank;
+        if (Dm % 8 || C % 8 || Di % 8 || R % 8) {
+            delete h;
+            return fail(nullptr, "sm_create: projector dims must be multiples of 8 (d_model %d, dt_rank %d)", Dm, R);
+        }
+        const std::string p = "model.mm_projector.", mp = p + "mamba_model.ssms.0.";
+        h->pj_pre_w = A(static_cast<size_t>(Dm) * C * e); add_slot(h, p + "pre_net.fc3.weight", h->pj_pre_w, Dm, C);
+        h->pj_pre_b = A(Dm * e); add_slot(h, p + "pre_net.fc3.bias", h->pj_pre_b, 1, Dm);
+        h->pj_norm_w = A(Dm * e); add_slot(h, mp + "norm.weight", h->pj_norm_w, 1, Dm);
+        h->pj_norm_b = A(Dm * e); add_slot(h, mp + "norm.bias", h->pj_norm_b, 1, Dm);
+        h->pj_in = A(static_cast<size_t>(2) * Di * Dm * e); add_slot(h, mp + "mixer.in_proj.weight", h->pj_in, 2 * Di, Dm);
+        h->pj_conv_w = A(static_cast<size_t>(Di) * W * e); add_slot(h, mp + "mixer.conv1d.weight", h->pj_conv_w, Di, W);
+        h->pj_conv_b = A(Di * e); add_slot(h, mp + "mixer.conv1d.bias", h->pj_conv_b, 1, Di);
+        h->pj_xproj = A(static_cast<size_t>(R + 2 * N) * Di * e); add_slot(h, mp + "mixer.x_proj.weight", h->pj_xproj, R + 2 * N, Di);
+        h->pj_dt_w = A(static_cast<size_t>(Di) * R * e); add_slot(h, mp + "mixer.dt_proj.weight", h->pj_dt_w, Di, R);
+        h->pj_dt_b = A(Di * e); add_slot(h, mp + "mixer.dt_proj.bias", h->pj_dt_b, 1, Di);
+        h->pj_alog = A(static_cast<size_t>(Di) * N * e); add_slot(h, mp + "mixer.A_log", h->pj_alog, Di, N);
+        h->pj_D = A(Di * e); add_slot(h, mp + "mixer.D", h->pj_D, 1, Di);
+        h->pj_out = A(static_cast<size_t>(Dm) * Di * e); add_slot(h, mp + "mixer.out_proj.weight", h->pj_out, Dm, Di);
+        h->pj_nf_w = A(Dm * e); add_slot(h, p + "mamba_model.norm_fn.weight", h->pj_nf_w, 1, Dm);
+        h->pj_nf_b = A(Dm * e); add_slot(h, p + "mamba_model.norm_fn.bias", h->pj_nf_b, 1, Dm);
+        h->pj_post_w = A(static_cast<size_t>(Dm) * Dm * e); add_slot(h, p + "post_net.fc3.weight", h->pj_post_w, Dm, Dm);
+        h->pj_post_b = A(Dm * e); add_slot(h, p + "post_net.fc3.bias", h->pj_post_b, 1, Dm);
+        h->pj_h0 = A(Dm * e); h->pj_xc = A(Di * e); h->pj_z = A(Di * e); h->pj_xdb = A((R + 2 * N) * e + 64);
+        h->pj_y = A(Di * e); h->pj_r2 = A(Dm * e);
+        h->pj_conv_state = A(static_cast<size_t>(Di) * W * e);
+        h->pj_ssm_state = static_cast<float*>(A(static_cast<size_t>(Di) * N * sizeof(float)));
+        h->pj_toks = A(static_cast<size_t>(Bm) * Dm * e);
+    }
+    // ---------------- gate
+    if (c.gate_layers > 0) {
+        const int H = c.proj_d_model, Hq = c.gate_heads, Hk = c.gate_kv_heads, D = c.gate_head_dim, F = c.gate_ffn;
+        if (H % 8 || F % 8 || (Hq * D) % 8 || Hq % Hk) {
+            delete h;
+            return fail(nullptr, "sm_create: gate dims must be multiples of 8 and heads %% kv_heads == 0");
+        }
+        const std::string p = "model.mm_projector.cls_net.cls_model.";
+        h->gate.resize(c.gate_layers);
+        for (int l = 0; l < c.gate_layers; ++l) {
+            MistralLayer& L = h->gate[l];
+            const std::string lp = p + "model.layers." + std::to_string(l) + ".";
+            L.in_ln = A(H * e); add_slot(h, lp + "input_layernorm.weight", L.in_ln, 1, H);
+            L.post_ln = A(H * e); add_slot(h, lp + "post_attention_layernorm.weight", L.post_ln, 1, H);
+            L.wqkv = A(static_cast<size_t>(Hk) * D * H * e); add_slot(h, lp + "self_attn.v_proj.weight", L.wqkv, Hk * D, H);
+            L.wo = A(static_cast<size_t>(H) * Hq * D * e); add_slot(h, lp + "self_attn.o_proj.weight", L.wo, H, Hq * D);
+            L.wgu = A(static_cast<size_t>(2) * F * H * e);
+            add_slot(h, lp + "mlp.gate_proj.weight", L.wgu, F, H);
+            add_slot(h, lp + "mlp.up_proj.weight", (char*)L.wgu + static_cast<size_t>(F) * H * e, F, H);
+            L.wd = A(static_cast<size_t>(H) * F * e); add_slot(h, lp + "mlp.down_proj.weight", L.wd, H, F);
+        }
+        h->gt_norm = A(H * e); add_slot(h, p + "model.norm.weight", h->gt_norm, 1, H);
+        h->gt_head = A(static_cast<size_t>(2) * H * e); add_slot(h, p + "lm_head.weight", h->gt_head, 2, H);
+        h->gt_h = A(H * e); h->gt_v = A(static_cast<size_t>(Hk) * D * e); h->gt_m = A(F * e);
+        h->gt_logits = static_cast<float*>(A(static_cast<size_t>(Bm) * 2 * sizeof(float)));
+    }
+    // ---------------- LLM
+    if (c.llm_layers > 0) {
+        const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn, V = c.llm_vocab;
+        if (D != 128 || H % 64 || F % 64 || Hq % Hk || Hq / Hk > 8) {
+            delete h;
+            return fail(nullptr, "sm_create: LLM needs head_dim 128, hidden/ffn %% 64 == 0, GQA group <= 8");
+        }
+        const int QKV = (Hq + 2 * Hk) * D;
+        h->lm_embed = A(static_cast<size_t>(V) * H * e); add_slot(h, "model.embed_tokens.weight", h->lm_embed, V, H);
+        h->llm.resize(c.llm_layers);
+        h->kc.resize(c.llm_layers);
+        h->vc.resize(c.llm_layers);
+        for (int l = 0; l < c.llm_layers; ++l) {
+            MistralLayer& L = h->llm[l];
+            const std::string lp = "model.layers." + std::to_string(l) + ".";
+            L.in_ln = A(H * e); add_slot(h, lp + "input_layernorm.weight", L.in_ln, 1, H);
+            L.post_ln = A(H * e); add_slot(h, lp + "post_attention_layernorm.weight", L.post_ln, 1, H);
+            L.wqkv = A(static_cast<size_t>(QKV) * H * e);
+            add_slot(h, lp + "self_attn.q_proj.weight", L.wqkv, Hq * D, H);
+            add_slot(h, lp + "self_attn.k_proj.weight", (char*)L.wqkv + static_cast<size_t>(Hq) * D * H * e, Hk * D, H);
+            add_slot(h, lp + "self_attn.v_proj.weight", (char*)L.wqkv + static_cast<size_t>(Hq + Hk) * D * H * e, Hk * D, H);
+            L.wo = A(static_cast<size_t>(H) * Hq * D * e); add_slot(h, lp + "self_attn.o_proj.weight", L.wo, H, Hq * D);
+            L.wgu = A(static_cast<size_t>(2) * F * H * e);
+            add_slot(h, lp + "mlp.gate_proj.weight", L.wgu, F, H);
+            add_slot(h, lp + "mlp.up_proj.weight", (char*)L.wgu + static_cast<size_t>(F) * H * e, F, H);
+            L.wd = A(static_cast<size_t>(H) * F * e); add_slot(h, lp + "mlp.down_proj.weight", L.wd, H, F);
+            h->kc[l] = A(static_cast<size_t>(Hk) * c.llm_max_ctx * D * e);
+            h->vc[l] = A(static_cast<size_t>(Hk) * c.llm_max_ctx * D * e);
+        }
+        h->lm_norm = A(H * e); add_slot(h, "model.norm.weight", h->lm_norm, 1, H);
+        h->lm_head = A(static_cast<size_t>(V) * H * e); add_slot(h, "lm_head.weight", h->lm_head, V, H);
+        h->pmax = 512;
+        const size_t Pm = h->pmax;
+        h->lw_x = A(Pm * H * e); h->lw_hn = A(Pm * H * e); h->lw_qkv = A(Pm * QKV * e); h->lw_att = A(Pm * Hq * D * e);
+        h->lw_gu = A(Pm * 2 * F * e); h->lw_m = A(Pm * F * e);
+        h->lw_logits = static_cast<float*>(A(static_cast<size_t>(V) * sizeof(float)));
+        h->lw_part = static_cast<float*>(A(static_cast<size_t>(Hq) * h->dec_splits * (D + 2) * sizeof(float)));
+        int* ints = static_cast<int*>(A((8 + 4096 + 64) * sizeof(int)));
+        h->d_pos = ints; h->d_tok = ints + 1; h->d_nout = ints + 2; h->d_done = ints + 3; h->d_out = ints + 8;
+        h->d_stop = ints + 8 + 4096;
+    }
+    if (oom) {
+        std::string msg = "sm_create: cudaMalloc failed (out of device memory)";
+        sm_destroy(h);
+        return fail(nullptr, "%s", msg.c_str());
+    }
+    cudaDeviceSynchronize();
+    *out = h;
+    return 0;
+}
+
+void sm_destroy(sm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& g : h->frame_graphs) cudaGraphExecDestroy(g.second);
+    if (h->decode_graph) cudaGraphExecDestroy(h->decode_graph);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+int sm_load_weight(sm_handle* h, const char* name, const void* data, int data_on_host, int dtype, int ndim,
+                   const int64_t* shape) {
+    if (!h || !name || !data) return fail(h, "sm_load_weight: null argument");
+    const std::string n(name);
+    auto it = h->slots.find(n);
+    if (it == h->slots.end()) {
+        // keys that exist in the reference state_dict but do not influence the path
+        auto has = [&](const char* t) { return n.find(t) != std::string::npos; };
+        if (has("post_layernorm") || has("position_ids") || has("rotary_emb") || has("inv_freq")) return 0;
+        if (has("cls_net") && (has("q_proj") || has("k_proj") || has("embed_tokens"))) return 0;
+        const size_t lp = n.find("vision_model.encoder.layers.");
+        if (lp != std::string::npos && atoi(n.c_str() + lp + strlen("vision_model.encoder.layers.")) >= h->cfg.vit_layers)
+            return 0;  // layers after hidden_states[select_layer] (clip_encoder.py:32)
+        return fail(h, "sm_load_weight: unknown key '%s'", name);
+    }
+    if (dtype != h->cfg.dtype) return fail(h, "sm_load_weight: '%s' has dtype %d, handle dtype is %d", name, dtype, h->cfg.dtype);
+    Slot& s = it->second;
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= static_cast<size_t>(shape[i]);
+    if (numel != s.numel) return fail(h, "sm_load_weight: '%s' has %zu elements, expected %zu", name, numel, s.numel);
+    cudaSetDevice(h->device);
+    const cudaMemcpyKind kind = data_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_OK(h, cudaMemcpy2D(s.dst, s.dst_pitch, data, s.row_bytes, s.row_bytes, s.rows, kind));
+    s.loaded = true;
+    return 0;
+}
+
+int sm_finalize_weights(sm_handle* h) {
+    if (!h) return 1;
+    std::string missing;
+    int n = 0;
+    for (auto& kv : h->slots)
+        if (!kv.second.loaded) {
+            if (n < 12) missing += (n ? ", " : "") + kv.first;
+            ++n;
+        }
+    if (n) return fail(h, "sm_finalize_weights: %d weights missing: %s%s", n, missing.c_str(), n > 12 ? ", ..." : "");
+    CUDA_OK(h, cudaDeviceSynchronize());
+    return 0;
+}
+
+int sm_stream_reset(sm_handle* h) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    if (h->pj_conv_state) {
+        CUDA_OK(h, cudaMemset(h->pj_conv_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_conv * h->esz));
+        CUDA_OK(h, cudaMemset(h->pj_ssm_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_state * sizeof(float)));
+    }
+    h->kv_len = 0;
+    if (h->d_pos) CUDA_OK(h, cudaMemset(h->d_pos, 0, 8 * sizeof(int)));
+    return 0;
+}
+
+int sm_vit_encode(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, void* stream) {
+    if (!h || h->cfg.vit_layers <= 0) return fail(h, "sm_vit_encode: vision tower not configured");
+    if (B < 1 || B > h->cfg.max_frames) return fail(h, "sm_vit_encode: B=%d outside [1, max_frames=%d]", B, h->cfg.max_frames);
+    cudaSetDevice(h->device);
+    return run_vit(h, pixels, B, feats_out, pooled_out, static_cast<cudaStream_t>(stream));
+}
+
+int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, void* stream) {
+    if (!h || h->cfg.vit_hidden <= 0) return fail(h, "sm_pool_features: not configured");
+    cudaSetDevice(h->device);
+    const int C = h->cfg.vit_hidden, P = h->P;
+    DISPATCH_T(h, T, {
+        pool_kernel<T><<<dim3((C + 127) / 128, n), 128, 0, static_cast<cudaStream_t>(stream)>>>((const T*)feats, (T*)pooled_out, P, C);
+        count_launch(h);
+    })
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, void* stream) {
+    if (!h || h->cfg.proj_d_model <= 0) return fail(h, "sm_projector_step: projector not configured");
+    cudaSetDevice(h->device);
+    for (int i = 0; i < n; ++i) {
+        const char* src = static_cast<const char*>(pooled) + static_cast<size_t>(i) * h->cfg.vit_hidden * h->esz;
+        char* dst = static_cast<char*>(tok_out) + static_cast<size_t>(i) * h->cfg.proj_d_model * h->esz;
+        if (run_projector(h, src, dst, static_cast<cudaStream_t>(stream))) return 1;
+    }
+    return 0;
+}
+
+int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream) {
+    if (!h || h->cfg.gate_layers <= 0) return fail(h, "sm_gate_score: gate not configured");
+    cudaSetDevice(h->device);
+    return run_gate(h, tok, logits_out, static_cast<cudaStream_t>(stream));
+}
+
+int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
+                  float* logits_out, float* logits_host, void* stream) {
+    if (!h || h->cfg.vit_layers <= 0 || h->cfg.proj_d_model <= 0 || h->cfg.gate_layers <= 0)
+        return fail(h, "sm_frame_step: needs vision tower + projector + gate");
+    if (B < 1 || B > h->cfg.max_frames) return fail(h, "sm_frame_step: B=%d outside [1, max_frames=%d]", B, h->cfg.max_frames);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sm_config& c = h->cfg;
+    const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
+    CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    const bool want_feats = feats_out != nullptr;
+    auto body = [&](cudaStream_t s) -> int {
+        if (run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, h->ws_pooled, s)) return 1;
+        for (int i = 0; i < B; ++i) {
+            char* tok = static_cast<char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
+            if (run_projector(h, static_cast<char*>(h->ws_pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, s)) return 1;
+            if (run_gate(h, tok, h->gt_logits + 2 * i, s)) return 1;
+        }
+        return 0;
+    };
+    if (c.use_graphs) {
+        const int key = B | (want_feats ? 1 << 8 : 0);
+        auto it = h->frame_graphs.find(key);
+        if (it == h->frame_graphs.end()) {
+            // warm run outside capture: fills the tensor-map cache and sets function attributes
+            if (body(st)) return 1;
+            CUDA_OK(h, cudaStreamSynchronize(st));
+            // the warm run advanced the Mamba state; rewind is the caller's job only on the very first
+            // call, so capture must not run the kernels: stream capture records without executing.
+            cudaGraph_t g;
+            h->capturing = true;
+            h->captured_launches = 0;
+            CUDA_OK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = body(st);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            h->capturing = false;
+            if (rc || ce != cudaSuccess) return fail(h, "sm_frame_step: graph capture failed: %s", cudaGetErrorString(ce));
+            cudaGraphExec_t ge;
+            CUDA_OK(h, cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            h->frame_graphs[key] = ge;
+            h->frame_graph_launches[key] = h->captured_launches;
+            // the warm run already produced this call's outputs
+        } else {
+            CUDA_OK(h, cudaGraphLaunch(it->second, st));
+            h->launches += h->frame_graph_launches[key];
+        }
+    } else {
+        if (body(st)) return 1;
+    }
+    if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, st));
+    if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, st));
+    if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int sm_embed_tokens(sm_handle* h, const int32_t* ids, int n, void* out, void* stream) {
+    if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_embed_tokens: LLM not configured");
+    cudaSetDevice(h->device);
+    DISPATCH_T(h, T, {
+        gather_rows_kernel<T><<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>((const T*)h->lm_embed, ids, (T*)out, n, h->cfg.llm_hidden);
+        count_launch(h);
+    })
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
+int sm_llm_prefill(sm_handle* h, const void* embeds, int P, float* last_logits, void* stream) {
+    if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_llm_prefill: LLM not configured");
+    if (P < 1) return fail(h, "sm_llm_prefill: P must be >= 1");
+    if (h->kv_len + P > h->cfg.llm_max_ctx) return fail(h, "sm_llm_prefill: %d + %d exceeds llm_max_ctx %d", h->kv_len, P, h->cfg.llm_max_ctx);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sm_config& c = h->cfg;
+    int done = 0, last_chunk = 0;
+    while (done < P) {
+        const int n = std::min(h->pmax, P - done);
+        const char* src = static_cast<const char*>(embeds) + static_cast<size_t>(done) * c.llm_hidden * h->esz;
+        if (run_prefill_chunk(h, src, n, h->kv_len, st)) return 1;
+        h->kv_len += n;
+        done += n;
+        last_chunk = n;
+    }
+    // final norm + lm_head on the last position only (generate() needs nothing else)
+    const char* xlast = static_cast<const char*>(h->lw_x) + static_cast<size_t>(last_chunk - 1) * c.llm_hidden * h->esz;
+    GemvArgs a = gv(h->lm_head, c.llm_vocab, c.llm_hidden, PRO_RMSNORM, xlast, GEPI_F32, h->lw_logits);
+    a.nw = h->lm_norm; a.eps = c.llm_eps;
+    if (launch_gemv(h, a, 1, st)) return 1;
+    if (last_logits) CUDA_OK(h, cudaMemcpyAsync(last_logits, h->lw_logits, static_cast<size_t>(c.llm_vocab) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const int pos = h->kv_len;
+    CUDA_OK(h, cudaMemcpyAsync(h->d_pos, &pos, sizeof(int), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int sm_llm_decode(sm_handle* h, int max_new, const int32_t* stop_ids, int n_stop, int32_t* ids_out_host,
+                  int32_t* n_out_host, void* stream) {
+    if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_llm_decode: LLM not configured");
+    if (max_new < 1 || max_new > 4096) return fail(h, "sm_llm_decode: max_new must be in [1, 4096]");
+    if (n_stop > 63) return fail(h, "sm_llm_decode: at most 63 stop ids");
+    if (h->kv_len + max_new - 1 > h->cfg.llm_max_ctx) return fail(h, "sm_llm_decode: KV cache would overflow llm_max_ctx %d", h->cfg.llm_max_ctx);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sm_config& c = h->cfg;
+    int zeros[2] = {0, 0};
+    CUDA_OK(h, cudaMemcpyAsync(h->d_nout, zeros, 2 * sizeof(int), cudaMemcpyHostToDevice, st));  // n_out, done
+    int stopbuf[64];
+    stopbuf[0] = n_stop;
+    for (int i = 0; i < n_stop; ++i) stopbuf[1 + i] = stop_ids[i];
+    CUDA_OK(h, cudaMemcpyAsync(h->d_stop, stopbuf, 64 * sizeof(int), cudaMemcpyHostToDevice, st));
+    // first token from the prefill logits (not fed back yet: position counter unchanged)
+    argmax_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, h->d_tok, h->d_out, h->d_nout, nullptr, h->d_stop,
+                                      h->d_done);
+    count_launch(h);
+    int produced = 1;
+    int host_done = 0;
+    const int check_every = n_stop > 0 ? 16 : max_new;
+    while (produced < max_new && !host_done) {
+        const int burst = std::min(check_every, max_new - produced);
+        for (int i = 0; i < burst; ++i) {
+            if (c.use_graphs) {
+                if (!h->decode_graph) {
+                    cudaGraph_t g;
+                    // make sure attributes / first-use state is set outside capture
+                    h->capturing = true;
+                    h->captured_launches = 0;
+                    CUDA_OK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    const int rc = run_decode_step(h, st);
+                    cudaError_t ce = cudaStreamEndCapture(st, &g);
+                    h->capturing = false;
+                    if (rc || ce != cudaSuccess) return fail(h, "sm_llm_decode: graph capture failed: %s", cudaGetErrorString(ce));
+                    CUDA_OK(h, cudaGraphInstantiate(&h->decode_graph, g, 0));
+                    cudaGraphDestroy(g);
+                    h->decode_graph_launches = h->captured_launches;
+                }
+                CUDA_OK(h, cudaGraphLaunch(h->decode_graph, st));
+                h->launches += h->decode_graph_launches;
+            } else {
+                if (run_decode_step(h, st)) return 1;
+            }
+        }
+        produced += burst;
+        if (n_stop > 0) {
+            CUDA_OK(h, cudaMemcpyAsync(&host_done, h->d_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_OK(h, cudaStreamSynchronize(st));
+        }
+    }
+    int nout = 0, pos = 0;
+    CUDA_OK(h, cudaMemcpyAsync(&nout, h->d_nout, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(h, cudaMemcpyAsync(&pos, h->d_pos, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(h, cudaStreamSynchronize(st));
+    nout = std::min(nout, max_new);
+    CUDA_OK(h, cudaMemcpy(ids_out_host, h->d_out, static_cast<size_t>(nout) * sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out_host = nout;
+    h->kv_len = pos;
+    return 0;
+}
+
+int sm_kv_len(const sm_handle* h) { return h ? h->kv_len : -1; }
+
+int sm_kv_set_len(sm_handle* h, int len) {
+    if (!h) return 1;
+    if (len < 0 || len > h->kv_len) return fail(h, "sm_kv_set_len: %d outside [0, %d]", len, h->kv_len);
+    h->kv_len = len;
+    if (h->d_pos) {
+        cudaSetDevice(h->device);
+        CUDA_OK(h, cudaMemcpy(h->d_pos, &len, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int sm_test_gemm(sm_handle* h, const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int epi,
+                 int force_swap, int force_bn, void* stream) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    return launch_gemm(h, x, M, w, N, K, bias, out, N, epi, static_cast<cudaStream_t>(stream), force_swap, force_bn);
+}
+
+int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, int H, int D, void* stream) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    const int C = H * D;
+    AttnArgs a{};
+    a.q = qkv;
+    a.k = reinterpret_cast<const char*>(qkv) + static_cast<size_t>(C) * 2;
+    a.v = reinterpret_cast<const char*>(qkv) + static_cast<size_t>(2 * C) * 2;
+    a.o = out;
+    a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
+    a.q_ss = a.k_ss = a.v_ss = 3 * C;
+    a.k_hs = a.v_hs = D;
+    a.o_bs = static_cast<long long>(S) * C;
+    a.o_ss = C;
+    a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
+    a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+    return launch_attn(h, a, D, H, B, static_cast<cudaStream_t>(stream));
+}
+
+long long sm_launch_count(sm_handle* h, int reset) {
+    if (!h) return 0;
+    const long long v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// Small bandwidth kernels around the tensor-core tiles: patch gather (im2col), embedding assembly +
+// LayerNorms, patch mean-pool, RoPE + KV-cache append, split-KV decode attention, argmax, row gather.
+#pragma once
+#include "ptx.cuh"
+
+namespace smb {
+
+// ------------------------------------------------------------------------------------------
+// ViT patch gather: pixels [B,3,H,W] (NCHW) -> A [B*P, Kpad], column k = c*p*p + i*p + j (the order of
+// Conv2d weight [C_out, 3, p, p] flattened), zero padded to Kpad (TMA needs 16-byte row pitch).
+// hf CLIPVisionEmbeddings.patch_embedding (modeling_clip.py:148-154,209-210)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ px, T* __restrict__ out, int B, int img, int patch, int kpad) {
+    const int gw = img / patch, P = gw * gw, kreal = 3 * patch * patch;
+    const long long total = static_cast<long long>(B) * P * kpad;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % kpad);
+        const long long row = i / kpad;
+        T v = Cvt<T>::from_f(0.f);
+        if (k < kreal) {
+            const int b = static_cast<int>(row / P), p = static_cast<int>(row % P);
+            const int py = p / gw, pxx = p % gw;
+            const int c = k / (patch * patch), rem = k % (patch * patch);
+            const int ii = rem / patch, jj = rem % patch;
+            v = px[((static_cast<long long>(b) * 3 + c) * img + (py * patch + ii)) * img + pxx * patch + jj];
+        }
+        out[i] = v;
+    }
+}
+
+// warp-per-row LayerNorm helper: C <= 32*VPL elements, fp32 statistics, returns normalised values in v[]
+template <typename T, int VPL>
+__device__ __forceinline__ void warp_layernorm(float (&v)[VPL], int C, int lane, const T* w, const T* b, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += v[i];
+    s = warp_sum(s);
+    const float mean = s / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        const float d = c < C ? v[i] - mean : 0.f;
+        sq += d * d;
+    }
+    sq = warp_sum(sq);
+    const float r = rsqrtf(sq / C + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) v[i] = rnd<T>((v[i] - mean) * r * Cvt<T>::to_f(w[c]) + Cvt<T>::to_f(b[c]));
+    }
+}
+
+// x[row] = pre_layrnorm( T( (p==0 ? cls : patch_emb[f*P + p-1]) + pos[p] ) );  h[row] = LN1_layer0(x[row])
+// (modeling_clip.py:212-218 cat + position add, :677 pre_layrnorm, :363-366 layer_norm1)
+template <typename T, int VPL>
+__global__ void vit_embed_ln_kernel(const T* __restrict__ patch_emb, const T* __restrict__ cls,
+                                    const T* __restrict__ pos, const T* pre_w, const T* pre_b, const T* ln_w,
+                                    const T* ln_b, T* __restrict__ x, T* __restrict__ h, int rows, int S, int C,
+                                    float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int f = warp / S, p = warp % S;
+    float v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) {
+            const float e = p == 0 ? Cvt<T>::to_f(cls[c])
+                                   : Cvt<T>::to_f(patch_emb[(static_cast<long long>(f) * (S - 1) + p - 1) * C + c]);
+            v[i] = rnd<T>(e + Cvt<T>::to_f(pos[static_cast<long long>(p) * C + c]));
+        } else {
+            v[i] = 0.f;
+        }
+    }
+    warp_layernorm<T, VPL>(v, C, lane, pre_w, pre_b, eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) x[static_cast<long long>(warp) * C + c] = Cvt<T>::from_f(v[i]);
+    }
+    warp_layernorm<T, VPL>(v, C, lane, ln_w, ln_b, eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) h[static_cast<long long>(warp) * C + c] = Cvt<T>::from_f(v[i]);
+    }
+}
+
+template <typename T, int VPL>
+__global__ void layernorm_kernel(const T* __restrict__ x, const T* w, const T* b, T* __restrict__ h, int rows, int C,
+                                 float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        v[i] = c < C ? Cvt<T>::to_f(x[static_cast<long long>(warp) * C + c]) : 0.f;
+    }
+    warp_layernorm<T, VPL>(v, C, lane, w, b, eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) h[static_cast<long long>(warp) * C + c] = Cvt<T>::from_f(v[i]);
+    }
+}
+
+// feature_select('patch') + mean over patches: feats[f, p, :] = x[f*S + 1 + p, :] (CLS dropped,
+// clip_encoder.py:31-35); pooled[f, :] = T(mean_p feats[f, p, :]) (multimodal_projector/builder.py:405)
+template <typename T>
+__global__ void vit_finalize_kernel(const T* __restrict__ x, T* __restrict__ feats, T* __restrict__ pooled, int S,
+                                    int C) {
+    const int f = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int P = S - 1;
+    float s = 0.f;
+    const T* src = x + (static_cast<long long>(f) * S + 1) * C + c;
+    T* dst = feats ? feats + static_cast<long long>(f) * P * C + c : nullptr;
+    for (int p = 0; p < P; ++p) {
+        const T v = src[static_cast<long long>(p) * C];
+        s += Cvt<T>::to_f(v);
+        if (dst) dst[static_cast<long long>(p) * C] = v;
+    }
+    if (pooled) pooled[static_cast<long long>(f) * C + c] = Cvt<T>::from_f(s / P);
+}
+
+// pooled[f, :] = T(mean_p feats[f, p, :]) for externally supplied features (B2 hook: mm_projector(feats))
+template <typename T>
+__global__ void pool_kernel(const T* __restrict__ feats, T* __restrict__ pooled, int P, int C) {
+    const int f = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    const T* src = feats + static_cast<long long>(f) * P * C + c;
+    for (int p = 0; p < P; ++p) s += Cvt<T>::to_f(src[static_cast<long long>(p) * C]);
+    pooled[static_cast<long long>(f) * C + c] = Cvt<T>::from_f(s / P);
+}
+
+// ------------------------------------------------------------------------------------------
+// LLM: RoPE (rotate-half, fp32 cos/sin, hf modeling_mistral.py:51-81) on q in place and on k while
+// appending k, v to the cache.  qkv rows: [q (Hq*D) | k (Hk*D) | v (Hk*D)].
+// cache layout: K/V [Hk][max_ctx][D] per layer.  positions pos0 + row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rope_append_kernel(T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, int rows, int Hq,
+                                   int Hk, int D, int max_ctx, const int* pos0_ptr, int pos0_host, float theta) {
+    const int pos0 = pos0_ptr ? *pos0_ptr : pos0_host;
+    const int half = D / 2;
+    const int per_row = (Hq + Hk) * half + Hk * D;
+    const long long total = static_cast<long long>(rows) * per_row;
+    const int ld = (Hq + 2 * Hk) * D;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int row = static_cast<int>(i / per_row);
+        int j = static_cast<int>(i % per_row);
+        const int pos = pos0 + row;
+        T* base = qkv + static_cast<long long>(row) * ld;
+        if (j < (Hq + Hk) * half) {
+            const int hh = j / half, d = j % half;
+            const float inv = powf(theta, -2.0f * d / D);
+            float sn, cs;
+            sincosf(pos * inv, &sn, &cs);
+            // HF casts cos/sin to the model dtype before the multiply (modeling_mistral.py apply_rotary_pos_emb)
+            cs = rnd<T>(cs);
+            sn = rnd<T>(sn);
+            T* p = base + hh * D;  // q heads then k heads are contiguous
+            const float x1 = Cvt<T>::to_f(p[d]), x2 = Cvt<T>::to_f(p[d + half]);
+            const float y1 = rnd<T>(x1 * cs) + rnd<T>(-x2 * sn);
+            const float y2 = rnd<T>(x2 * cs) + rnd<T>(x1 * sn);
+            if (hh < Hq) {
+                p[d] = Cvt<T>::from_f(y1);
+                p[d + half] = Cvt<T>::from_f(y2);
+            } else {
+                T* dst = kc + (static_cast<long long>(hh - Hq) * max_ctx + pos) * D;
+                dst[d] = Cvt<T>::from_f(y1);
+                dst[d + half] = Cvt<T>::from_f(y2);
+            }
+        } else {
+            j -= (Hq + Hk) * half;
+            const int hh = j / D, d = j % D;
+            vc[(static_cast<long long>(hh) * max_ctx + pos) * D + d] = base[(Hq + Hk) * D + hh * D + d];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode attention (one query token), split over the KV length: grid (splits, Hk).  Each CTA handles
+// the `group` query heads of one kv head over its KV slice (K/V read once per group), writes
+// un-normalised partial (m, l, o[D]) per head; the combine kernel merges splits in fixed order.
+// ------------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(128) decode_attn_partial_kernel(const T* __restrict__ qkv, const T* __restrict__ kc,
+                                                                  const T* __restrict__ vc, float* __restrict__ part,
+                                                                  int Hq, int Hk, int max_ctx, const int* kv_len_ptr,
+                                                                  int kv_len_host, float scale_log2e) {
+    // 4 warps; each warp owns keys kbeg + warp, +4, ...; lane owns D/32 dims.  group <= 8.
+    constexpr int VPL = D / 32;
+    const int kv_len = kv_len_ptr ? (*kv_len_ptr + 1) : kv_len_host;  // device counter holds the position of the new token
+    const int nsplit = gridDim.x, split = blockIdx.x, hk = blockIdx.y;
+    const int group = Hq / Hk;
+    const int per = (kv_len + nsplit - 1) / nsplit;
+    const int kbeg = split * per, kend = min(kv_len, kbeg + per);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float sm_m[4][8], sm_l[4][8];
+    __shared__ float sm_o[4][8][D];
+    float q[8][VPL];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+            q[g][i] = g < group ? Cvt<T>::to_f(qkv[(hk * group + g) * D + lane * VPL + i]) : 0.f;
+    float m[8], l[8], o[8][VPL];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        m[g] = -INFINITY;
+        l[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) o[g][i] = 0.f;
+    }
+    const T* kb = kc + static_cast<long long>(hk) * max_ctx * D;
+    const T* vb = vc + static_cast<long long>(hk) * max_ctx * D;
+    for (int key = kbeg + warp; key < kend; key += 4) {
+        float kv[VPL], vv[VPL];
+        if constexpr (VPL == 4) {
+            const uint2 ku = *reinterpret_cast<const uint2*>(kb + static_cast<long long>(key) * D + lane * 4);
+            const uint2 vu = *reinterpret_cast<const uint2*>(vb + static_cast<long long>(key) * D + lane * 4);
+            float2 a = Cvt<T>::unpack2(ku.x), b = Cvt<T>::unpack2(ku.y);
+            kv[0] = a.x; kv[1] = a.y; kv[2] = b.x; kv[3] = b.y;
+            a = Cvt<T>::unpack2(vu.x); b = Cvt<T>::unpack2(vu.y);
+            vv[0] = a.x; vv[1] = a.y; vv[2] = b.x; vv[3] = b.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                kv[i] = Cvt<T>::to_f(kb[static_cast<long long>(key) * D + lane * VPL + i]);
+                vv[i] = Cvt<T>::to_f(vb[static_cast<long long>(key) * D + lane * VPL + i]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (g < group) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) s = fmaf(q[g][i], kv[i], s);
+                s = warp_sum(s) * scale_log2e;
+                const float mn = fmaxf(m[g], s);
+                const float c = exp2f(m[g] - mn);
+                // P is rounded to T before it multiplies V, as in the fused reference kernels
+                const float p = rnd<T>(exp2f(s - mn));
+                l[g] = l[g] * c + p;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(p, vv[i], o[g][i] * c);
+                m[g] = mn;
+            }
+        }
+    }
+    // merge the 4 warps (fixed order)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (g < group) {
+            if (lane == 0) { sm_m[warp][g] = m[g]; sm_l[warp][g] = l[g]; }
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) sm_o[warp][g][lane * VPL + i] = o[g][i];
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < group * D; idx += blockDim.x) {
+        const int g = idx / D, d = idx % D;
+        float mm = -INFINITY;
+        for (int w = 0; w < 4; ++w) mm = fmaxf(mm, sm_m[w][g]);
+        float ll = 0.f, oo = 0.f;
+        for (int w = 0; w < 4; ++w) {
+            const float c = sm_m[w][g] == -INFINITY ? 0.f : exp2f(sm_m[w][g] - mm);
+            ll += sm_l[w][g] * c;
+            oo += sm_o[w][g][d] * c;
+        }
+        float* dst = part + ((static_cast<long long>(hk * group + g) * nsplit + split) * (D + 2));
+        dst[2 + d] = oo;
+        if (d == 0) { dst[0] = mm; dst[1] = ll; }
+    }
+}
+
+template <typename T, int D>
+__global__ void decode_attn_combine_kernel(const float* __restrict__ part, T* __restrict__ out, int nsplit) {
+    const int h = blockIdx.x, d = threadIdx.x;
+    const float* p = part + static_cast<long long>(h) * nsplit * (D + 2);
+    float mm = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, p[s * (D + 2)]);
+    float ll = 0.f, oo = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float ms = p[s * (D + 2)];
+        const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
+        ll += p[s * (D + 2) + 1] * c;
+        oo += p[s * (D + 2) + 2 + d] * c;
+    }
+    out[h * D + d] = Cvt<T>::from_f(oo / ll);
+}
+
+// argmax over fp32 logits (first index wins ties, like torch.argmax), single CTA; writes the token,
+// appends it to the output list and bumps the device-side position counter used by graph replays.
+__global__ void argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ token_out,
+                              int* __restrict__ out_list, int* __restrict__ n_out, int* __restrict__ pos_counter,
+                              const int* __restrict__ stop /* [0] = count, then ids */, int* __restrict__ done_flag) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = logits[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w)
+            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        const bool already_done = done_flag && *done_flag;
+        if (!already_done) {
+            *token_out = bi;
+            if (out_list && n_out) { out_list[*n_out] = bi; *n_out += 1; }
+            if (pos_counter) *pos_counter += 1;
+            const int n_stop = stop ? stop[0] : 0;
+            for (int s = 0; s < n_stop; ++s)
+                if (stop[1 + s] == bi && done_flag) *done_flag = 1;
+        }
+    }
+}
+
+// rows[i, :] = table[ids[i], :]   (embed_tokens); ids may come from the device (decode loop)
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,
+                                   int n, int C) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const T* src = table + static_cast<long long>(ids[r]) * C;
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8)
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(r) * C + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// RMSNorm rows (prefill path): h = nw * T(x * rsqrt(mean(x^2) + eps))   warp per row
+template <typename T>
+__global__ void rmsnorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ nw, T* __restrict__ h, int rows,
+                                    int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const T* xr = x + static_cast<long long>(warp) * C;
+    float s = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = Cvt<T>::unpack2(w[i]);
+            s += f.x * f.x + f.y * f.y;
+        }
+    }
+    s = warp_sum(s);
+    const float r = rsqrtf(s / C + eps);
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        const uint4 g = *reinterpret_cast<const uint4*>(nw + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = Cvt<T>::unpack2(w[i]), gg = Cvt<T>::unpack2(gw[i]);
+            o[i] = Cvt<T>::pack2(gg.x * rnd<T>(f.x * r), gg.y * rnd<T>(f.y * r));
+        }
+        *reinterpret_cast<uint4*>(h + static_cast<long long>(warp) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// SwiGLU rows (prefill path): m[r, j] = T(T(silu(gu[r, j])) * gu[r, F + j])
+template <typename T>
+__global__ void swiglu_rows_kernel(const T* __restrict__ gu, T* __restrict__ m, int rows, int F) {
+    const long long total = static_cast<long long>(rows) * F;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / F;
+        const int j = static_cast<int>(i % F);
+        const float g = Cvt<T>::to_f(gu[r * 2 * F + j]), u = Cvt<T>::to_f(gu[r * 2 * F + F + j]);
+        const float sg = g / (1.0f + __expf(-g));
+        m[i] = Cvt<T>::from_f(rnd<T>(sg) * u);
+    }
+}
+
+}  // namespace smb
