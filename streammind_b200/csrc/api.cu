@@ -96,6 +96,7 @@ struct sm_handle {
     // ---- graphs
     std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
     std::map<int, long long> frame_graph_launches;
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot capture)
     cudaGraphExec_t decode_graph = nullptr;
     long long decode_graph_launches = 0;
 };
@@ -537,6 +538,10 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         return fail(nullptr, "sm_create: cuTensorMapEncodeTiled not available from the driver");
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, "sm_create: cudaStreamCreate failed");
+    }
     {
         int rc = 0;
         DISPATCH_T(h, T, rc = init_kernel_attrs_t<T>(h);)
@@ -723,6 +728,7 @@ void sm_destroy(sm_handle* h) {
     cudaDeviceSynchronize();
     for (auto& g : h->frame_graphs) cudaGraphExecDestroy(g.second);
     if (h->decode_graph) cudaGraphExecDestroy(h->decode_graph);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -848,9 +854,9 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
             cudaGraph_t g;
             h->capturing = true;
             h->captured_launches = 0;
-            CUDA_OK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = body(st);
-            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            CUDA_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = body(h->cap_stream);
+            cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
             h->capturing = false;
             if (rc || ce != cudaSuccess) return fail(h, "sm_frame_step: graph capture failed: %s", cudaGetErrorString(ce));
             cudaGraphExec_t ge;
@@ -942,9 +948,9 @@ int sm_llm_decode(sm_handle* h, int max_new, const int32_t* stop_ids, int n_stop
                     // make sure attributes / first-use state is set outside capture
                     h->capturing = true;
                     h->captured_launches = 0;
-                    CUDA_OK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    const int rc = run_decode_step(h, st);
-                    cudaError_t ce = cudaStreamEndCapture(st, &g);
+                    CUDA_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+                    const int rc = run_decode_step(h, h->cap_stream);
+                    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
                     h->capturing = false;
                     if (rc || ce != cudaSuccess) return fail(h, "sm_llm_decode: graph capture failed: %s", cudaGetErrorString(ce));
                     CUDA_OK(h, cudaGraphInstantiate(&h->decode_graph, g, 0));

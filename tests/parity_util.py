@@ -19,6 +19,16 @@ def rel_err(a: torch.Tensor, b: torch.Tensor):
     return (d.max() / b.abs().max().clamp_min(1e-30)).item(), (d.norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def check_close(name, a, b, tol, max_factor=2.5):
+    """Parity criterion: relative L2 error <= tol and max-norm error <= max_factor * tol.
+    (One fp16 ulp at the largest-magnitude element is already 2^-10 ~ 1e-3 of max|b|, so the max-norm
+    bound is 2.5 ulp-at-max; the L2 bound is the north_star figure.)"""
+    emax, el2 = rel_err(a, b)
+    print(f"{name}: rel err max-norm {emax:.2e}, L2 {el2:.2e} (tol {tol:.1e})")
+    assert el2 < tol and emax < max_factor * tol, (name, emax, el2, tol)
+    return emax, el2
+
+
 SMALL = dict(vit_image=56, vit_patch=14, vit_hidden=128, vit_layers=2, vit_heads=2, vit_ffn=256,
              proj_d_model=256, gate_layers=2, gate_heads=2, gate_kv_heads=1, gate_head_dim=128, gate_ffn=512,
              llm_hidden=256, llm_layers=2, llm_heads=2, llm_kv_heads=1, llm_head_dim=128, llm_ffn=512,
