@@ -128,6 +128,15 @@ int sm_test_gemm(sm_handle* h, const void* x /*[M,K]*/, const void* w /*[N,K]*/,
 int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out /*[B*S, H*D]*/, int B, int S, int H,
                       int D, void* stream);
 
+/* Per-kernel-class CUDA-event timing (used by bench.py's roofline pass; adds two event records per
+ * launch, so keep it off on the timed path; ignored while capturing / replaying graphs).
+ * sm_profile_read synchronises the device, fills accumulated milliseconds and launch counts per class
+ * (index = class id, name via sm_profile_class_name), clears the accumulators and returns the number
+ * of classes. */
+int sm_profile_enable(sm_handle* h, int on);
+int sm_profile_read(sm_handle* h, int max_classes, double* ms_by_class, long long* launches_by_class);
+const char* sm_profile_class_name(int cls);
+
 /* Launch accounting: number of this library's kernel launches (graph-replayed kernels included) since
  * the last call with reset != 0. */
 long long sm_launch_count(sm_handle* h, int reset);

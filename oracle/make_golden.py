@@ -267,13 +267,67 @@ def make_full(seed: int = 1234):
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+class CharTokenizer:
+    """Deterministic toy tokenizer for the host-logic fixture: BOS + one id per whitespace-separated
+    word (hash-free: ids assigned in order of first appearance from a fixed vocabulary list)."""
+    pad_token_id, bos_token_id, eos_token_id = 0, 1, 2
+
+    def __init__(self):
+        self.vocab = {"</s>": 2}
+
+    def __call__(self, text):
+        ids = [self.bos_token_id]
+        for w in text.replace("\n", " \n ").split(" "):
+            if w == "":
+                continue
+            ids.append(self.vocab.setdefault(w, len(self.vocab) + 3))
+        return type("Enc", (), {"input_ids": ids})()
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        inv = {v: k for k, v in self.vocab.items()}
+        return [" ".join(inv.get(int(t), "?") for t in row if not (skip_special_tokens and int(t) in (0, 1, 2)))
+                for row in ids]
+
+
+def make_host_logic():
+    """Prompt template + tokenizer_MMODAL_token + KeywordsStoppingCriteria run through the REFERENCE's
+    own code (conversation.py:78-98,383-393; mm_utils.py:567-647) on a toy tokenizer."""
+    import json
+    from oracle import shims
+    shims.install()
+    from videollama2.conversation import conv_templates
+    from videollama2.mm_utils import tokenizer_MMODAL_token, KeywordsStoppingCriteria
+    conv = conv_templates["mistral_instruct"].copy()
+    conv.append_message(conv.roles[0], "<video>\n")
+    conv.append_message(conv.roles[1], None)
+    prompt0 = conv.get_prompt()
+    tok = CharTokenizer()
+    prompts = [prompt0]
+    for out in ("a man opens the door", "he sits down"):
+        prompts.append(prompts[-1] + " " + out + " </s>[INST] <video>\n [/INST]")
+    ids = [tokenizer_MMODAL_token(p, tok, -201) for p in prompts]
+    inp = torch.tensor([ids[0]])
+    sc = KeywordsStoppingCriteria(["</s>"], tok, inp)
+    stop_cases = []
+    for tail in ([5, 6, 2], [5, 6, 7], [2]):
+        o = torch.tensor([ids[0] + tail])
+        stop_cases.append({"tail": tail, "stop": bool(sc(o, None))})
+    path = os.path.join(GOLDEN_DIR, "host_logic.json")
+    json.dump({"prompts": prompts, "ids": ids, "vocab": tok.vocab, "stop_cases": stop_cases,
+               "keyword_ids": [k.tolist() for k in sc.keyword_ids]}, open(path, "w"), indent=1)
+    print("  wrote", path)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--host", action="store_true")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    if a.tiny or not a.full:
+    if a.host:
+        make_host_logic()
+    if a.tiny or not (a.full or a.host):
         make_tiny("tiny_model_gate", seed=11, n_frames=8, force=None, max_new=6)
         make_tiny("tiny_forced_gate", seed=23, n_frames=10, force=[0, 1, 0, 0, 1, 1, 0, 1, 0, 1], max_new=5)
     if a.full:

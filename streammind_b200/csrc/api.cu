@@ -61,6 +61,9 @@ struct sm_handle {
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
     bool capturing = false;
     long long captured_launches = 0;
 
@@ -143,6 +146,25 @@ inline void count_launch(sm_handle* h) {
     if (h->capturing) h->captured_launches++; else h->launches++;
 }
 
+// per-kernel-class CUDA-event timing (bench.py's roofline pass; off on the timed path)
+enum KClass { KC_GEMM = 0, KC_GEMV, KC_ATTN, KC_LAYERNORM, KC_IM2COL, KC_VIT_FINALIZE, KC_MAMBA_SCAN, KC_ROPE_APPEND,
+              KC_DECODE_ATTN, KC_ARGMAX, KC_GATHER, KC_RMSNORM_ROWS, KC_SWIGLU_ROWS, KC_COUNT };
+const char* kKClassNames[KC_COUNT] = {"gemm_tc_kernel", "gemv_kernel", "attention_kernel", "layernorm_kernel",
+                                      "im2col_kernel", "vit_finalize_kernel", "mamba_scan_step_kernel",
+                                      "rope_append_kernel", "decode_attn_kernels", "argmax_kernel",
+                                      "gather_rows_kernel", "rmsnorm_rows_kernel", "swiglu_rows_kernel"};
+struct ProfScope {
+    sm_handle* h; cudaStream_t st; cudaEvent_t b = nullptr;
+    ProfScope(sm_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->profiling || h->capturing) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        h->prof.push_back({cls, a, b});
+    }
+    ~ProfScope() { if (b) cudaEventRecord(b, st); }
+};
+
 // ------------------------------------------------------------------------------------------ tensor maps
 const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int box_rows) {
     auto key = std::make_tuple(ptr, rows, K, box_rows);
@@ -221,7 +243,10 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.nstage = gemm_num_stages(p.bn); a.epi = epi;
     const int smem = gemm_smem_bytes(p.bn);
-    gemm_tc_kernel<T><<<grid, kGemmThreads, smem, st>>>(*ta, *tb, a);
+    {
+        ProfScope ps(h, KC_GEMM, st);
+        gemm_tc_kernel<T><<<grid, kGemmThreads, smem, st>>>(*ta, *tb, a);
+    }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
     return 0;
@@ -245,8 +270,11 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
     const size_t smem = ((a.K * 2 + 15) & ~15) + static_cast<size_t>(nmat) * rows_per_cta * nseg * sizeof(float);
     if (smem > 100 * 1024) return fail(h, "gemv: K=%d too large for the staging buffer", a.K);
-    if (nmat == 1) gemv_kernel<T, 1><<<grid, kGemvThreads, smem, st>>>(a);
-    else gemv_kernel<T, 2><<<grid, kGemvThreads, smem, st>>>(a);
+    {
+        ProfScope ps(h, KC_GEMV, st);
+        if (nmat == 1) gemv_kernel<T, 1><<<grid, kGemvThreads, smem, st>>>(a);
+        else gemv_kernel<T, 2><<<grid, kGemvThreads, smem, st>>>(a);
+    }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
     return 0;
@@ -274,7 +302,10 @@ GemvArgs gv(const void* W, int N, int K, int pro, const void* x0, int epi, void*
 template <typename T, int D>
 int launch_attn_t(sm_handle* h, const AttnArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
     constexpr int smem = attn_smem_bytes<D>();
-    attention_kernel<T, D><<<dim3(q_tiles, heads, batch), kAttnThreads, smem, st>>>(a);
+    {
+        ProfScope ps(h, KC_ATTN, st);
+        attention_kernel<T, D><<<dim3(q_tiles, heads, batch), kAttnThreads, smem, st>>>(a);
+    }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
     return 0;
@@ -302,6 +333,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn;
     DISPATCH_T(h, T, {
         const long long n = static_cast<long long>(B) * P * h->kpad;
+        ProfScope ps_kc_im2col(h, KC_IM2COL, st);
         im2col_kernel<T><<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256, 0, st>>>(
             reinterpret_cast<const T*>(pixels), reinterpret_cast<T*>(h->ws_im), B, c.vit_image, c.vit_patch, h->kpad);
         count_launch(h);
@@ -310,6 +342,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     const int warps_per_block = 8;
     const int ln_blocks = (rows + warps_per_block - 1) / warps_per_block;
     DISPATCH_T(h, T, {
+        ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
         vit_embed_ln_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
             (const T*)h->ws_pemb, (const T*)h->vit_cls, (const T*)h->vit_pos, (const T*)h->vit_pre_w,
             (const T*)h->vit_pre_b, (const T*)h->vit[0].ln1_w, (const T*)h->vit[0].ln1_b, (T*)h->ws_x, (T*)h->ws_h, rows,
@@ -321,6 +354,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         const VitLayer& L = h->vit[l];
         if (l > 0) {
             DISPATCH_T(h, T, {
+                ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
                 layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
                     (const T*)h->ws_x, (const T*)L.ln1_w, (const T*)L.ln1_b, (T*)h->ws_h, rows, C, c.vit_eps);
                 count_launch(h);
@@ -342,6 +376,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
         if (launch_gemm(h, h->ws_att, rows, L.wo, C, C, L.bo, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
+            ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
             layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
                 (const T*)h->ws_x, (const T*)L.ln2_w, (const T*)L.ln2_b, (T*)h->ws_h, rows, C, c.vit_eps);
             count_launch(h);
@@ -350,6 +385,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         if (launch_gemm(h, h->ws_mlp, rows, L.w2, C, F, L.b2, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
     }
     DISPATCH_T(h, T, {
+        ProfScope ps_kc_vit_finalize(h, KC_VIT_FINALIZE, st);
         vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
                                                                          (T*)pooled_out, S, C);
         count_launch(h);
@@ -376,6 +412,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t 
     s.z = h->pj_z; s.state = h->pj_ssm_state; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
     const int scan_smem = ((R + 2 * N) * 2 + 15) & ~15;
     DISPATCH_T(h, T, {
+        ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
         mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 4 * h->num_sms), 256, scan_smem, st>>>(s);
         count_launch(h);
     })
@@ -470,6 +507,7 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     for (int l = 0; l < c.llm_layers; ++l) {
         const MistralLayer& L = h->llm[l];
         DISPATCH_T(h, T, {
+            ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
             count_launch(h);
         })
@@ -490,12 +528,14 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         if (launch_attn(h, a, D, Hq, 1, st)) return 1;
         if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
+            ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
             count_launch(h);
         })
         if (launch_gemm(h, h->lw_hn, P, L.wgu, 2 * F, H, nullptr, h->lw_gu, 2 * F, EPI_STORE, st)) return 1;
         DISPATCH_T(h, T, {
             const long long tot = static_cast<long long>(P) * F;
+            ProfScope ps_kc_swiglu_rows(h, KC_SWIGLU_ROWS, st);
             swiglu_rows_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 4096)), 256, 0, st>>>(
                 (const T*)h->lw_gu, (T*)h->lw_m, P, F);
             count_launch(h);
@@ -1018,6 +1058,32 @@ int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, in
     a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
     return launch_attn(h, a, D, H, B, static_cast<cudaStream_t>(stream));
 }
+
+int sm_profile_enable(sm_handle* h, int on) {
+    if (!h) return 1;
+    h->profiling = on != 0;
+    return 0;
+}
+
+int sm_profile_read(sm_handle* h, int max_classes, double* ms_by_class, long long* launches_by_class) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < max_classes; ++i) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls < max_classes) {
+            ms_by_class[r.cls] += ms;
+            launches_by_class[r.cls] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+    return KC_COUNT;
+}
+
+const char* sm_profile_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kKClassNames[cls] : ""; }
 
 long long sm_launch_count(sm_handle* h, int reset) {
     if (!h) return 0;

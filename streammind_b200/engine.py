@@ -218,6 +218,17 @@ class Engine:
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.sm_launch_count(self._h, 1 if reset else 0))
 
+    def profile(self, on: bool):
+        self._check(self.lib.sm_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel class: (accumulated ms, launches)} since the last read (synchronises the device)."""
+        n = 16
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        k = self.lib.sm_profile_read(self._h, n, ms, cnt)
+        return {self.lib.sm_profile_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k) if cnt[i]}
+
     # ------------------------------------------------------------------ unit-test hooks
     def test_gemm(self, x, w, bias, epi: int, out: Optional[torch.Tensor] = None, force_swap=-1, force_bn=0):
         M, K = x.shape

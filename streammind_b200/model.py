@@ -1,0 +1,341 @@
+"""Host-side mirror of the reference's model API for the per-frame path (hooks
+B1 and B2): same class roles, method names, argument meaning and error behaviour as
+
+  * ``CLIPVisionTower``                      /root/reference/streammind/model/multimodal_encoder/clip_encoder.py:7-84
+  * ``Video_Mamba_seq`` (``mm_projector``)   /root/reference/streammind/model/multimodal_projector/builder.py:390-564
+  * ``Videollama2MistralForCausalLM``        /root/reference/streammind/model/language_model/videollama2_mistral.py:146-449
+  * ``infer`` of the streaming demo          /root/reference/streammind/eval/video_score_stream_demo.py:66-125
+
+but every tensor op runs in the CUDA library behind ``Engine`` (no PyTorch arithmetic on the path).
+What differs by design (DESIGN.md "incremental state"): the projector advances a persistent Mamba
+state by the NEW frames only, and the LLM keeps ONE KV cache across fires, re-using the longest common
+prefix of the dialogue (the reference re-runs the projector over all T frames and re-prefills the
+whole dialogue with past_key_values=None on every fire: videollama2_arch.py:190-198,
+videollama2_mistral.py:413,426-431).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .constants import MMODAL_TOKEN_INDEX
+from .engine import Engine, EngineConfig
+
+VIDEO_TOKEN_INDEX = MMODAL_TOKEN_INDEX["VIDEO"]
+Item = Tuple[str, int]        # ('t', token id) | ('f', frame index)
+
+
+# --------------------------------------------------------------------------------------------------
+# pure host logic (unit-tested on CPU)
+# --------------------------------------------------------------------------------------------------
+def expand_dialogue(input_ids: Sequence[int], interval_id_list: Sequence[int]) -> List[Item]:
+    """The sequence the LLM sees for a prompt with ``<video>`` sentinels: the i-th sentinel stands for
+    frame tokens [interval_id_list[i-1], interval_id_list[i]) (0 for i = 0); videollama2_arch.py:949-981."""
+    n_sent = sum(1 for t in input_ids if t == VIDEO_TOKEN_INDEX)
+    if n_sent > len(interval_id_list):
+        raise ValueError(f"prompt has {n_sent} <video> sentinels but only {len(interval_id_list)} intervals were recorded")
+    starts = [0] + list(interval_id_list[:-1])
+    seq: List[Item] = []
+    vi = 0
+    for tid in input_ids:
+        if tid == VIDEO_TOKEN_INDEX:
+            seq.extend(("f", j) for j in range(starts[vi], interval_id_list[vi]))
+            vi += 1
+        else:
+            seq.append(("t", int(tid)))
+    return seq
+
+
+class DialogueCache:
+    """Which items the device KV cache currently holds, and how much of a new dialogue can be re-used."""
+
+    def __init__(self):
+        self.items: List[Item] = []
+
+    def reset(self):
+        self.items = []
+
+    def plan(self, new_items: Sequence[Item]) -> int:
+        """Length of the longest common prefix (always leaves at least one item to prefill, because the
+        logits of the last position are needed to start decoding)."""
+        n = 0
+        lim = min(len(new_items), len(self.items))
+        while n < lim and new_items[n] == self.items[n]:
+            n += 1
+        return min(n, len(new_items) - 1)
+
+    def commit(self, new_items: Sequence[Item], generated: Sequence[int]):
+        """After prefill + greedy decode: the cache holds the dialogue and every generated token except
+        the last one (never fed back, as in HF generate)."""
+        self.items = list(new_items) + [("t", int(t)) for t in generated[:-1]]
+
+
+# --------------------------------------------------------------------------------------------------
+# B2: component API
+# --------------------------------------------------------------------------------------------------
+class CLIPVisionTower:
+    """``forward(images[B,3,H,W] | list) -> [B, num_patches, hidden]`` (patch features of
+    hidden_states[select_layer], CLS dropped), output cast back to the input dtype."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.is_loaded = True
+        self.select_layer = -2
+        self.select_feature = "patch"
+
+    @torch.no_grad()
+    def forward(self, images):
+        if isinstance(images, list):
+            return [self.forward(im.unsqueeze(0)) for im in images]
+        e = self.engine
+        x = images.to(device=e.device, dtype=e.cfg.dtype)
+        outs = []
+        for i in range(0, x.shape[0], e.cfg.max_frames):
+            outs.append(e.vit_encode(x[i:i + e.cfg.max_frames])[0])
+        return torch.cat(outs, 0).to(images.dtype)
+
+    __call__ = forward
+
+    @property
+    def dtype(self):
+        return self.engine.cfg.dtype
+
+    @property
+    def device(self):
+        return self.engine.device
+
+    @property
+    def hidden_size(self):
+        return self.engine.cfg.vit_hidden
+
+    @property
+    def num_patches(self):
+        return self.engine.cfg.num_patches
+
+    @property
+    def num_patches_per_side(self):
+        return self.engine.cfg.vit_image // self.engine.cfg.vit_patch
+
+    @property
+    def dummy_feature(self):
+        return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
+
+
+class VideoMambaSeq:
+    """``mm_projector(frames_features[1,T,P,C], cls_demo=True, frames_features_shape=...) ->
+    (x[1,T,d_model], logits[2])`` and ``-> x`` when no flag is set (builder.py:403,562,564).
+
+    The reference passes ALL T frames' features on every call; this object remembers how many it has
+    already consumed and advances the Mamba state by the remainder only."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.tokens: Optional[torch.Tensor] = None      # [T, d_model] on device
+        self.frames_seen = 0
+
+    def reset(self):
+        self.tokens, self.frames_seen = None, 0
+
+    @torch.no_grad()
+    def forward(self, x, cls_inference=False, cls_training=False, cls_demo=False, frames_features_shape=None,
+                prompt_time_input_ids=None, prompt_time_lable=None):
+        if cls_inference or cls_training:
+            raise NotImplementedError("only the streaming (cls_demo) and plain projector calls are on the hot path")
+        if x.dim() != 4 or x.shape[0] != 1:
+            raise ValueError(f"expected frames_features of shape [1, T, P, C], got {tuple(x.shape)}")
+        T = x.shape[1]
+        if T < self.frames_seen:
+            raise RuntimeError(f"feature history shrank ({T} < {self.frames_seen}); call reset() to start a new stream")
+        e = self.engine
+        if T > self.frames_seen:
+            new = x[0, self.frames_seen:].to(device=e.device, dtype=e.cfg.dtype)
+            toks = e.projector_step(e.pool_features(new))
+            self.tokens = toks if self.tokens is None else torch.cat([self.tokens, toks], 0)
+            self.frames_seen = T
+        out = self.tokens.unsqueeze(0)
+        if cls_demo:
+            return out, e.gate_score(self.tokens[-1])
+        return out
+
+    __call__ = forward
+
+
+# --------------------------------------------------------------------------------------------------
+# B1: model API
+# --------------------------------------------------------------------------------------------------
+class StreamMindB200ForCausalLM:
+    """Drop-in for the calls the streaming demo / serve worker make on ``Videollama2MistralForCausalLM``."""
+
+    def __init__(self, cfg: EngineConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
+                 keep_frame_features: bool = False):
+        self.config = cfg
+        self.engine = Engine(cfg, device=device)
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+        self.vision_tower = CLIPVisionTower(self.engine)
+        self.mm_projector = VideoMambaSeq(self.engine)
+        self.keep_frame_features = keep_frame_features
+        # per-stream state, same attribute names as the reference (videollama2_mistral.py:159-162)
+        self.frame_feature: Optional[torch.Tensor] = None
+        self.interval_id_list: List[int] = []
+        self._tokens: Optional[torch.Tensor] = None          # [T, d_model]
+        self._num_frames = 0
+        self._dialogue = DialogueCache()
+        self.last_prefill_len = 0
+
+    # ---- loading -------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        self.engine.load_state_dict(sd)
+        self.engine.finalize()
+        self.engine.reset_stream()
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+    def get_model(self):
+        return self
+
+    @property
+    def device(self):
+        return self.engine.device
+
+    @property
+    def dtype(self):
+        return self.config.dtype
+
+    def eval(self):
+        return self
+
+    def reset_stream(self):
+        """Start a new video (the reference never resets; one stream per model instance)."""
+        self.engine.reset_stream()
+        self.mm_projector.reset()
+        self.frame_feature, self.interval_id_list = None, []
+        self._tokens, self._num_frames = None, 0
+        self._dialogue.reset()
+
+    # ---- per-frame path ------------------------------------------------------------------------
+    def _encode_frames(self, frames: torch.Tensor):
+        """encode_images_or_videos_score_cls_inference_allframe_demo (videollama2_arch.py:173-203),
+        incremental: returns gate logits [2] fp32 (host) of the last frame."""
+        e = self.engine
+        if frames.dim() != 4:
+            raise ValueError(f"expected frames [t, 3, H, W], got {tuple(frames.shape)}")
+        if frames.dtype != e.cfg.dtype:
+            frames = frames.to(e.cfg.dtype)
+        last = None
+        for i in range(0, frames.shape[0], e.cfg.max_frames):
+            chunk = frames[i:i + e.cfg.max_frames]
+            if not chunk.is_cuda and not chunk.is_pinned():
+                chunk = chunk.to(e.device)
+            feats, toks, _, lg_host = e.frame_step(chunk, want_feats=self.keep_frame_features)
+            self._tokens = toks if self._tokens is None else torch.cat([self._tokens, toks], 0)
+            if self.keep_frame_features:
+                f = feats.unsqueeze(0)
+                self.frame_feature = f if self.frame_feature is None else torch.cat([self.frame_feature, f], 1)
+            torch.cuda.current_stream().synchronize()
+            last = lg_host[chunk.shape[0] - 1].clone()
+        self._num_frames += frames.shape[0]
+        return last
+
+    @torch.no_grad()
+    def stream_generate_demo(self, inputs: Optional[torch.Tensor] = None, images_or_videos: Optional[torch.Tensor] = None,
+                             modal_list=None, **kwargs):
+        """-> (text | None, pred).  Same keyword arguments as the reference (videollama2_mistral.py:385-439)."""
+        kwargs.pop("position_ids", None)
+        kwargs.pop("attention_mask", None)
+        kwargs.pop("score_video", None)
+        tokenizer = kwargs.pop("tokenizer", None)
+        force_pred = kwargs.pop("force_pred", None)         # the authors' "# pred = 1" switch (arch.py:943)
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported")
+        if kwargs.get("do_sample", False):
+            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented on the device")
+        logits = self._encode_frames(images_or_videos)
+        self.last_gate_logits = logits
+        pred = int(torch.softmax(logits, dim=0).argmax(dim=0).item()) if force_pred is None else int(force_pred)
+        if pred == 0:
+            return None, pred
+        self.interval_id_list.append(self._num_frames)
+        ids = inputs[0].tolist() if isinstance(inputs, torch.Tensor) else list(inputs[0])
+        out_ids = self._generate_from_dialogue(ids, kwargs)
+        if tokenizer is None:
+            return out_ids, pred
+        text = tokenizer.batch_decode(torch.tensor([out_ids]), skip_special_tokens=True)[0].strip()
+        return text, pred
+
+    def _stop_ids(self, kwargs) -> List[int]:
+        stops: List[int] = []
+        for sc in kwargs.get("stopping_criteria", None) or []:
+            if getattr(sc, "needs_host_check", False):
+                raise NotImplementedError("multi-token stop keywords need a host-side check; only single-token "
+                                          "keywords (e.g. '</s>') run in the device loop")
+            stops.extend(getattr(sc, "single_token_ids", []))
+        eos = kwargs.get("eos_token_id", kwargs.get("pad_token_id", None))   # the demo passes pad_token_id=eos
+        if eos is not None and eos not in stops:
+            stops.append(int(eos))
+        return stops
+
+    def _generate_from_dialogue(self, ids: Sequence[int], kwargs) -> List[int]:
+        e = self.engine
+        items = expand_dialogue(ids, self.interval_id_list)
+        keep = self._dialogue.plan(items)
+        if keep > e.kv_len:
+            keep = e.kv_len
+        e.kv_set_len(keep)
+        todo = items[keep:]
+        self.last_prefill_len = len(todo)
+        text_pos = [i for i, (k, _) in enumerate(todo) if k == "t"]
+        frame_pos = [i for i, (k, _) in enumerate(todo) if k == "f"]
+        emb = torch.empty(len(todo), e.cfg.llm_hidden, dtype=e.cfg.dtype, device=e.device)
+        if text_pos:
+            tid = torch.tensor([todo[i][1] for i in text_pos], dtype=torch.int32, device=e.device)
+            emb[torch.tensor(text_pos, device=e.device)] = e.embed_tokens(tid)
+        if frame_pos:
+            fidx = torch.tensor([todo[i][1] for i in frame_pos], device=e.device)
+            emb[torch.tensor(frame_pos, device=e.device)] = self._tokens[fidx]
+        e.llm_prefill(emb)
+        out = e.llm_decode(int(kwargs.get("max_new_tokens", 1024)), self._stop_ids(kwargs))
+        self._dialogue.commit(items, out)
+        return out
+
+    @torch.no_grad()
+    def generate(self, inputs: Optional[torch.Tensor] = None, images_or_videos: Optional[torch.Tensor] = None,
+                 modal_list=None, **kwargs) -> torch.Tensor:
+        """Offline call (videollama2_mistral.py:262-315): all frames at once, one ``<video>`` span, greedy
+        decode; returns new token ids [1, n]."""
+        if kwargs.get("do_sample", False):
+            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented on the device")
+        self.reset_stream()
+        if images_or_videos is not None:
+            self._encode_frames(images_or_videos)
+            self.interval_id_list = [self._num_frames]
+        ids = inputs[0].tolist()
+        return torch.tensor([self._generate_from_dialogue(ids, kwargs)], dtype=torch.long)
+
+
+def infer(model: StreamMindB200ForCausalLM, video: torch.Tensor, instruct: str, tokenizer, do_sample=False,
+          version="mistral_instruct", score_video=None, prompt: Optional[str] = None, max_new_tokens: int = 1024):
+    """The demo's per-frame call (eval/video_score_stream_demo.py:66-125): builds / extends the text
+    prompt, tokenizes it with ``<video>`` sentinels, calls ``stream_generate_demo`` and applies the
+    growth rule ``prompt += " " + outputs + " </s>[INST] <video>\\n [/INST]"`` (:123-124)."""
+    from .constants import DEFAULT_MMODAL_TOKEN
+    from .conversation import SeparatorStyle, conv_templates
+    from .mm_utils import KeywordsStoppingCriteria, tokenizer_MMODAL_token
+    conv = conv_templates["mistral_instruct"].copy()
+    if prompt is None:
+        conv.append_message(conv.roles[0], DEFAULT_MMODAL_TOKEN["VIDEO"] + "\n")
+        conv.append_message(conv.roles[1], None)
+        prompt = conv.get_prompt()
+    input_ids = tokenizer_MMODAL_token(prompt, tokenizer, VIDEO_TOKEN_INDEX, return_tensors="pt").unsqueeze(0)
+    stop_str = conv.sep if conv.sep_style in [SeparatorStyle.SINGLE] else conv.sep2
+    stopping = KeywordsStoppingCriteria([stop_str], tokenizer, input_ids)
+    outputs, pred = model.stream_generate_demo(
+        input_ids, attention_mask=input_ids.ne(tokenizer.pad_token_id).long(), images_or_videos=video,
+        modal_list=["video"], do_sample=do_sample, temperature=0.2 if do_sample else 0.0,
+        max_new_tokens=max_new_tokens, use_cache=True, stopping_criteria=[stopping],
+        pad_token_id=tokenizer.eos_token_id, score_video=score_video, tokenizer=tokenizer)
+    if pred == 1:
+        prompt += " " + outputs + " </s>[INST] <video>\n [/INST]"
+    return outputs, prompt

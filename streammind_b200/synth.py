@@ -140,11 +140,13 @@ def make_projector_weights(seed: int, dtype=torch.float16, device="cpu", d_model
 
 def make_projector_gate_weights(seed: int, dtype=torch.float16, device="cpu", d_model=4096,
                                 mm_hidden=1024, gate_ffn=14336, gate_heads=32, gate_kv_heads=8,
-                                gate_head_dim=128, gate_layers=4) -> Dict[str, torch.Tensor]:
+                                gate_head_dim=128, gate_layers=4, gate_with_qk=False) -> Dict[str, torch.Tensor]:
+    """Projector + gate.  The gate's q_proj / k_proj never reach its output at L = 1 (SURVEY.md section
+    8c (i)) and are only generated on request (the CPU reference arm executes them like the reference)."""
     sd = make_projector_weights(seed, dtype, device, d_model, mm_hidden)
     sd.update(make_mistral_weights(seed, GATE_PREFIX, dtype, device, hidden=d_model, ffn=gate_ffn,
                                    layers=gate_layers, heads=gate_heads, kv_heads=gate_kv_heads,
-                                   head_dim=gate_head_dim, vocab=2, with_embed=False, with_qk=False))
+                                   head_dim=gate_head_dim, vocab=2, with_embed=False, with_qk=gate_with_qk))
     return sd
 
 
