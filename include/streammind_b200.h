@@ -125,6 +125,8 @@ int sm_kv_set_len(sm_handle* h, int len);   /* truncate to a common prefix; len 
 int sm_test_gemm(sm_handle* h, const void* x /*[M,K]*/, const void* w /*[N,K]*/, const void* bias /*[N]|NULL*/,
                  void* out /*[M,N]*/, int M, int N, int K, int epi, int force_swap /*-1 auto*/, int force_bn /*0 auto*/,
                  void* stream);
+/* Debug: while device_buf != NULL every GEMM CTA writes 8 phase timestamps (globaltimer, ns). */
+int sm_test_gemm_trace(sm_handle* h, long long* device_buf);
 int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out /*[B*S, H*D]*/, int B, int S, int H,
                       int D, void* stream);
 
@@ -136,6 +138,11 @@ int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out 
 int sm_profile_enable(sm_handle* h, int on);
 int sm_profile_read(sm_handle* h, int max_classes, double* ms_by_class, long long* launches_by_class);
 const char* sm_profile_class_name(int cls);
+
+/* Debug / measurement: launch only the kernel classes whose bit is set (class ids as in
+ * sm_profile_class_name); outputs are then meaningless, timings of the remaining kernels are exact.
+ * bench.py uses it to time one kernel class at a time inside the same captured step. */
+int sm_debug_kernel_filter(sm_handle* h, unsigned mask);
 
 /* Launch accounting: number of this library's kernel launches (graph-replayed kernels included) since
  * the last call with reset != 0. */

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -35,6 +36,10 @@ struct Slot {
     size_t dst_pitch = 0;      // destination pitch in bytes (== row_bytes unless re-pitched)
     size_t numel = 0;
     bool loaded = false;
+    // pre-tiled GEMM weights (ViT): destination matrix base, first row of this block in it, k-blocks per n-tile
+    bool tiled = false;
+    void* tile_base = nullptr;
+    int tile_row0 = 0, tile_kb = 0, cols = 0;
 };
 
 struct VitLayer {
@@ -61,6 +66,10 @@ struct sm_handle {
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
+    bool use_pdl = true;
+    bool vit_tiled = true;            // ViT GEMM weights are stored pre-tiled (gemm_tc.cuh GemmArgs::w_tiled)
+    unsigned kfilter = 0xFFFFFFFFu;   // debug: kernel classes that are actually launched (bench.py per-class timing)
+    long long* gemm_dbg = nullptr;   // device buffer for sm_test_gemm_trace
     bool profiling = false;
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -142,8 +151,33 @@ void add_slot(sm_handle* h, const std::string& name, void* dst, size_t rows, siz
     h->slots[name] = s;
 }
 
+void add_tiled_slot(sm_handle* h, const std::string& name, void* matrix_base, int row0, size_t rows, size_t cols,
+                    int kb_total) {
+    Slot s;
+    s.dst = matrix_base; s.rows = rows; s.row_bytes = cols * h->esz; s.dst_pitch = s.row_bytes; s.numel = rows * cols;
+    s.tiled = true; s.tile_base = matrix_base; s.tile_row0 = row0; s.tile_kb = kb_total; s.cols = static_cast<int>(cols);
+    h->slots[name] = s;
+}
+inline size_t tiled_elems(int n, int k) { return static_cast<size_t>((n + 127) / 128) * ((k + 63) / 64) * 128 * 64; }
+
 inline void count_launch(sm_handle* h) {
     if (h->capturing) h->captured_launches++; else h->launches++;
+}
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its
+// predecessor drains and synchronises itself with griddepcontrol.wait (ptx.cuh pdl_wait).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(sm_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (h->use_pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // per-kernel-class CUDA-event timing (bench.py's roofline pass; off on the timed path)
@@ -153,6 +187,7 @@ const char* kKClassNames[KC_COUNT] = {"gemm_tc_kernel", "gemv_kernel", "attentio
                                       "im2col_kernel", "vit_finalize_kernel", "mamba_scan_step_kernel",
                                       "rope_append_kernel", "decode_attn_kernels", "argmax_kernel",
                                       "gather_rows_kernel", "rmsnorm_rows_kernel", "swiglu_rows_kernel"};
+inline bool kon(const sm_handle* h, int cls) { return (h->kfilter >> cls) & 1u; }
 struct ProfScope {
     sm_handle* h; cudaStream_t st; cudaEvent_t b = nullptr;
     ProfScope(sm_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
@@ -191,20 +226,24 @@ const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int 
 struct GemmPlan { int swap, bn; };
 
 GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms) {
+    // Cost model in nanoseconds, calibrated on B200 with in-kernel timestamps (profiles/r01_gemm_phases.md):
+    //   * one SM ingests ~117 B/ns from L2 through TMA, so a K=64 slab costs (16 KiB + 128*bn B)/117 ns
+    //     unless the MMA (bn/2 clocks per K=16 at 1.9 GHz) is slower;
+    //   * epilogue ~0.58 us per 32 accumulator columns (token-major), ~3 us when transposed (swap);
+    //   * ~0.6 us of setup / drain per CTA, CTAs run in waves of num_sms.
     double best = 1e30;
     GemmPlan bp{0, 128};
-    const double ksteps = std::ceil(K / 16.0);
-    const double bytes_w = 2.0 * feats * K, bytes_x = 2.0 * tokens * K;
+    const double kblocks = std::ceil(K / 64.0);
     auto eval = [&](int swap, int bn) {
         const long ctas = swap ? (long)((feats + 127) / 128) * ((tokens + bn - 1) / bn)
                                : (long)((tokens + 127) / 128) * ((feats + bn - 1) / bn);
-        const double step = std::max(bn / 2.0, 32.0 + bn / 4.0);           // MMA vs smem-read bound per K=16
-        const double epi = swap ? 40.0 * bn : 14.0 * bn;                    // TMEM drain + stores
-        const double per_cta = ksteps * step + 2500.0 + epi;
+        const double step = std::max((16384.0 + 128.0 * bn) / 117.0, 1.05 * bn);
+        const double epi = std::ceil(bn / 32.0) * (swap ? 3000.0 : 580.0);
+        const double per_cta = 600.0 + kblocks * step + epi;
         const double waves = std::ceil((double)ctas / num_sms);
-        const double active = std::min<double>(ctas, num_sms);
-        const double mem = (bytes_w + bytes_x) / (active * 36.0);           // ~36 B/clk/SM of L2->SM bandwidth
-        const double cost = std::max(waves * per_cta, mem + 2500.0);
+        // chip-wide L2 -> SM bandwidth (~12 B/ns per SM-equivalent of 100 SMs) bounds many small tiles
+        const double l2 = (double)ctas * kblocks * (16384.0 + 128.0 * bn) / 12000.0;
+        const double cost = std::max(waves * per_cta, l2 + 600.0 + epi);
         if (cost < best) { best = cost; bp = {swap, bn}; }
     };
     if (feats % 16 == 0)
@@ -219,8 +258,9 @@ GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms) {
 
 template <typename T>
 int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
-                  int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0) {
+                  int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false) {
     if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
+    if (!kon(h, KC_GEMM)) return 0;
     GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms);
     if (force_swap >= 0) p.swap = force_swap;
     if (force_bn > 0) p.bn = force_bn;
@@ -228,13 +268,17 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     const CUtensorMap *ta, *tb;
     GemmArgs a{};
     dim3 grid;
+    const int w_kb = (K + kGemmBK - 1) / kGemmBK;
+    const int w_rows_tiled = ((feats + 127) / 128) * w_kb * 128;
+    a.w_tiled = w_tiled ? 1 : 0;
+    a.w_kb = w_kb;
     if (!p.swap) {
         ta = get_tmap(h, x, tokens, K, kGemmBM);
-        tb = get_tmap(h, w, feats, K, p.bn);
+        tb = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, std::min(p.bn, kGemmBM)) : get_tmap(h, w, feats, K, p.bn);
         a.Ma = tokens; a.Nb = feats;
         grid = dim3((tokens + kGemmBM - 1) / kGemmBM, (feats + p.bn - 1) / p.bn);
     } else {
-        ta = get_tmap(h, w, feats, K, kGemmBM);
+        ta = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, kGemmBM) : get_tmap(h, w, feats, K, kGemmBM);
         tb = get_tmap(h, x, tokens, K, p.bn);
         a.Ma = feats; a.Nb = tokens;
         grid = dim3((feats + kGemmBM - 1) / kGemmBM, (tokens + p.bn - 1) / p.bn);
@@ -242,10 +286,22 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.nstage = gemm_num_stages(p.bn); a.epi = epi;
+    a.dbg = h->gemm_dbg;
+    if (h->gemm_dbg) h->gemm_dbg += 8;   // one 8-slot record per launch
+    const CUtensorMap* tc = ta;  // placeholder when unused
+    a.tma_store = (!p.swap && epi != EPI_STORE_F32 && p.bn % 64 == 0 && ldo == feats && getenv("SMB_NO_TMA_STORE") == nullptr) ? 1 : 0;
+    if (a.tma_store) {
+        tc = get_tmap(h, out, tokens, feats, kGemmBM);
+        if (!tc) return 1;
+    }
+    {
+        static const int dbg_stages = getenv("SMB_GEMM_STAGES") ? atoi(getenv("SMB_GEMM_STAGES")) : 0;   // tuning knob
+        if (dbg_stages > 0 && dbg_stages < a.nstage) a.nstage = dbg_stages;
+    }
     const int smem = gemm_smem_bytes(p.bn);
     {
         ProfScope ps(h, KC_GEMM, st);
-        gemm_tc_kernel<T><<<grid, kGemmThreads, smem, st>>>(*ta, *tb, a);
+        CUDA_OK(h, launch_pdl(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads), smem, st, *ta, *tb, *tc, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -253,16 +309,17 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
 }
 
 int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
-                int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0) {
+                int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false) {
     if (h->cfg.dtype == SM_DTYPE_BF16)
-        return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn);
-    return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn);
+        return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled);
+    return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled);
 }
 
 // ------------------------------------------------------------------------------------------ GEMV
 template <typename T>
 int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (a.K % 8 != 0) return fail(h, "gemv: K=%d must be a multiple of 8", a.K);
+    if (!kon(h, KC_GEMV)) return 0;
     a.seg_len = 1024;
     int grid = std::min(a.N, 2 * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;
@@ -272,8 +329,8 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (smem > 100 * 1024) return fail(h, "gemv: K=%d too large for the staging buffer", a.K);
     {
         ProfScope ps(h, KC_GEMV, st);
-        if (nmat == 1) gemv_kernel<T, 1><<<grid, kGemvThreads, smem, st>>>(a);
-        else gemv_kernel<T, 2><<<grid, kGemvThreads, smem, st>>>(a);
+        if (nmat == 1) CUDA_OK(h, launch_pdl(h, gemv_kernel<T, 1>, dim3(grid), dim3(kGemvThreads), smem, st, a));
+        else CUDA_OK(h, launch_pdl(h, gemv_kernel<T, 2>, dim3(grid), dim3(kGemvThreads), smem, st, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -302,6 +359,7 @@ GemvArgs gv(const void* W, int N, int K, int pro, const void* x0, int epi, void*
 template <typename T, int D>
 int launch_attn_t(sm_handle* h, const AttnArgs& a, int q_tiles, int heads, int batch, cudaStream_t st) {
     constexpr int smem = attn_smem_bytes<D>();
+    if (!kon(h, KC_ATTN)) return 0;
     {
         ProfScope ps(h, KC_ATTN, st);
         attention_kernel<T, D><<<dim3(q_tiles, heads, batch), kAttnThreads, smem, st>>>(a);
@@ -334,19 +392,23 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     DISPATCH_T(h, T, {
         const long long n = static_cast<long long>(B) * P * h->kpad;
         ProfScope ps_kc_im2col(h, KC_IM2COL, st);
+        if (kon(h, KC_IM2COL)) {
         im2col_kernel<T><<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256, 0, st>>>(
             reinterpret_cast<const T*>(pixels), reinterpret_cast<T*>(h->ws_im), B, c.vit_image, c.vit_patch, h->kpad);
+        }
         count_launch(h);
     })
-    if (launch_gemm(h, h->ws_im, B * P, h->vit_wpatch, C, h->kpad, nullptr, h->ws_pemb, C, EPI_STORE, st)) return 1;
+    if (launch_gemm(h, h->ws_im, B * P, h->vit_wpatch, C, h->kpad, nullptr, h->ws_pemb, C, EPI_STORE, st, -1, 0, h->vit_tiled)) return 1;
     const int warps_per_block = 8;
     const int ln_blocks = (rows + warps_per_block - 1) / warps_per_block;
     DISPATCH_T(h, T, {
         ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
+        if (kon(h, KC_LAYERNORM)) {
         vit_embed_ln_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
             (const T*)h->ws_pemb, (const T*)h->vit_cls, (const T*)h->vit_pos, (const T*)h->vit_pre_w,
             (const T*)h->vit_pre_b, (const T*)h->vit[0].ln1_w, (const T*)h->vit[0].ln1_b, (T*)h->ws_x, (T*)h->ws_h, rows,
             S, C, c.vit_eps);
+        }
         count_launch(h);
     })
     const int D = C / c.vit_heads;
@@ -355,12 +417,14 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         if (l > 0) {
             DISPATCH_T(h, T, {
                 ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
-                layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+                if (kon(h, KC_LAYERNORM)) {
+                layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
                     (const T*)h->ws_x, (const T*)L.ln1_w, (const T*)L.ln1_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                }
                 count_launch(h);
             })
         }
-        if (launch_gemm(h, h->ws_h, rows, L.wqkv, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, st)) return 1;
+        if (launch_gemm(h, h->ws_h, rows, L.wqkv, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, st, -1, 0, h->vit_tiled)) return 1;
         AttnArgs a{};
         a.q = h->ws_qkv;
         a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
@@ -374,20 +438,24 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
         a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
         if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
-        if (launch_gemm(h, h->ws_att, rows, L.wo, C, C, L.bo, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
+        if (launch_gemm(h, h->ws_att, rows, L.wo, C, C, L.bo, h->ws_x, C, EPI_RESIDUAL, st, -1, 0, h->vit_tiled)) return 1;
         DISPATCH_T(h, T, {
             ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
-            layernorm_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+            if (kon(h, KC_LAYERNORM)) {
+            layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
                 (const T*)h->ws_x, (const T*)L.ln2_w, (const T*)L.ln2_b, (T*)h->ws_h, rows, C, c.vit_eps);
+            }
             count_launch(h);
         })
-        if (launch_gemm(h, h->ws_h, rows, L.w1, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, st)) return 1;
-        if (launch_gemm(h, h->ws_mlp, rows, L.w2, C, F, L.b2, h->ws_x, C, EPI_RESIDUAL, st)) return 1;
+        if (launch_gemm(h, h->ws_h, rows, L.w1, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, st, -1, 0, h->vit_tiled)) return 1;
+        if (launch_gemm(h, h->ws_mlp, rows, L.w2, C, F, L.b2, h->ws_x, C, EPI_RESIDUAL, st, -1, 0, h->vit_tiled)) return 1;
     }
     DISPATCH_T(h, T, {
         ProfScope ps_kc_vit_finalize(h, KC_VIT_FINALIZE, st);
+        if (kon(h, KC_VIT_FINALIZE)) {
         vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
                                                                          (T*)pooled_out, S, C);
+        }
         count_launch(h);
     })
     CUDA_OK(h, cudaGetLastError());
@@ -413,7 +481,9 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t 
     const int scan_smem = ((R + 2 * N) * 2 + 15) & ~15;
     DISPATCH_T(h, T, {
         ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
+        if (kon(h, KC_MAMBA_SCAN)) {
         mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 4 * h->num_sms), 256, scan_smem, st>>>(s);
+        }
         count_launch(h);
     })
     a = gv(h->pj_out, Dm, Di, PRO_PLAIN, h->pj_y, GEPI_ADD_TO, h->pj_r2);
@@ -508,7 +578,9 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         const MistralLayer& L = h->llm[l];
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
+            if (kon(h, KC_RMSNORM_ROWS)) {
             rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            }
             count_launch(h);
         })
         if (launch_gemm(h, h->lw_hn, P, L.wqkv, QKV, H, nullptr, h->lw_qkv, QKV, EPI_STORE, st)) return 1;
@@ -529,15 +601,19 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
+            if (kon(h, KC_RMSNORM_ROWS)) {
             rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            }
             count_launch(h);
         })
         if (launch_gemm(h, h->lw_hn, P, L.wgu, 2 * F, H, nullptr, h->lw_gu, 2 * F, EPI_STORE, st)) return 1;
         DISPATCH_T(h, T, {
             const long long tot = static_cast<long long>(P) * F;
             ProfScope ps_kc_swiglu_rows(h, KC_SWIGLU_ROWS, st);
+            if (kon(h, KC_SWIGLU_ROWS)) {
             swiglu_rows_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 4096)), 256, 0, st>>>(
                 (const T*)h->lw_gu, (T*)h->lw_m, P, F);
+            }
             count_launch(h);
         })
         if (launch_gemm(h, h->lw_m, P, L.wd, H, F, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
@@ -578,6 +654,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         return fail(nullptr, "sm_create: cuTensorMapEncodeTiled not available from the driver");
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
     if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(nullptr, "sm_create: cudaStreamCreate failed");
@@ -611,8 +688,15 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->kpad = (kreal + 63) / 64 * 64;
         const std::string p = "model.vision_tower.vision_tower.vision_model.";
         h->vit_cls = A(C * e); add_slot(h, p + "embeddings.class_embedding", h->vit_cls, 1, C);
-        h->vit_wpatch = A(static_cast<size_t>(C) * h->kpad * e);
-        add_slot(h, p + "embeddings.patch_embedding.weight", h->vit_wpatch, C, kreal, h->kpad);
+        h->vit_tiled = getenv("SMB_NO_TILED_WEIGHTS") == nullptr && C % 128 == 0 && F % 128 == 0;
+        const int kbC = (C + 63) / 64, kbF = (F + 63) / 64;
+        if (h->vit_tiled) {
+            h->vit_wpatch = A(tiled_elems(C, h->kpad) * e);
+            add_tiled_slot(h, p + "embeddings.patch_embedding.weight", h->vit_wpatch, 0, C, kreal, h->kpad / 64);
+        } else {
+            h->vit_wpatch = A(static_cast<size_t>(C) * h->kpad * e);
+            add_slot(h, p + "embeddings.patch_embedding.weight", h->vit_wpatch, C, kreal, h->kpad);
+        }
         h->vit_pos = A(static_cast<size_t>(h->S) * C * e);
         add_slot(h, p + "embeddings.position_embedding.weight", h->vit_pos, h->S, C);
         h->vit_pre_w = A(C * e); add_slot(h, p + "pre_layrnorm.weight", h->vit_pre_w, 1, C);
@@ -625,18 +709,25 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
             L.ln1_b = A(C * e); add_slot(h, lp + "layer_norm1.bias", L.ln1_b, 1, C);
             L.ln2_w = A(C * e); add_slot(h, lp + "layer_norm2.weight", L.ln2_w, 1, C);
             L.ln2_b = A(C * e); add_slot(h, lp + "layer_norm2.bias", L.ln2_b, 1, C);
-            L.wqkv = A(static_cast<size_t>(3) * C * C * e);
+            L.wqkv = A(tiled_elems(3 * C, C) * e);
             L.bqkv = A(static_cast<size_t>(3) * C * e);
             const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
             for (int j = 0; j < 3; ++j) {
-                add_slot(h, lp + "self_attn." + nm[j] + ".weight", (char*)L.wqkv + static_cast<size_t>(j) * C * C * e, C, C);
+                if (h->vit_tiled) add_tiled_slot(h, lp + "self_attn." + nm[j] + ".weight", L.wqkv, j * C, C, C, kbC);
+                else add_slot(h, lp + "self_attn." + nm[j] + ".weight", (char*)L.wqkv + static_cast<size_t>(j) * C * C * e, C, C);
                 add_slot(h, lp + "self_attn." + nm[j] + ".bias", (char*)L.bqkv + static_cast<size_t>(j) * C * e, 1, C);
             }
-            L.wo = A(static_cast<size_t>(C) * C * e); add_slot(h, lp + "self_attn.out_proj.weight", L.wo, C, C);
+            L.wo = A(tiled_elems(C, C) * e);
+            if (h->vit_tiled) add_tiled_slot(h, lp + "self_attn.out_proj.weight", L.wo, 0, C, C, kbC);
+            else add_slot(h, lp + "self_attn.out_proj.weight", L.wo, C, C);
             L.bo = A(C * e); add_slot(h, lp + "self_attn.out_proj.bias", L.bo, 1, C);
-            L.w1 = A(static_cast<size_t>(F) * C * e); add_slot(h, lp + "mlp.fc1.weight", L.w1, F, C);
+            L.w1 = A(tiled_elems(F, C) * e);
+            if (h->vit_tiled) add_tiled_slot(h, lp + "mlp.fc1.weight", L.w1, 0, F, C, kbC);
+            else add_slot(h, lp + "mlp.fc1.weight", L.w1, F, C);
             L.b1 = A(F * e); add_slot(h, lp + "mlp.fc1.bias", L.b1, 1, F);
-            L.w2 = A(static_cast<size_t>(C) * F * e); add_slot(h, lp + "mlp.fc2.weight", L.w2, C, F);
+            L.w2 = A(tiled_elems(C, F) * e);
+            if (h->vit_tiled) add_tiled_slot(h, lp + "mlp.fc2.weight", L.w2, 0, C, F, kbF);
+            else add_slot(h, lp + "mlp.fc2.weight", L.w2, C, F);
             L.b2 = A(C * e); add_slot(h, lp + "mlp.fc2.bias", L.b2, 1, C);
         }
         const size_t rows = static_cast<size_t>(Bm) * h->S;
@@ -795,6 +886,24 @@ int sm_load_weight(sm_handle* h, const char* name, const void* data, int data_on
     if (numel != s.numel) return fail(h, "sm_load_weight: '%s' has %zu elements, expected %zu", name, numel, s.numel);
     cudaSetDevice(h->device);
     const cudaMemcpyKind kind = data_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (s.tiled) {
+        const void* src = data;
+        void* tmp = nullptr;
+        if (data_on_host) {
+            CUDA_OK(h, cudaMalloc(&tmp, numel * h->esz));
+            CUDA_OK(h, cudaMemcpy(tmp, data, numel * h->esz, cudaMemcpyHostToDevice));
+            src = tmp;
+        }
+        const int blocks = static_cast<int>(std::min<size_t>((numel + 255) / 256, 8192));
+        DISPATCH_T(h, T, {
+            retile_weight_kernel<T><<<blocks, 256>>>((const T*)src, (T*)s.tile_base, static_cast<int>(s.rows), s.cols,
+                                                     s.tile_row0, s.tile_kb);
+        })
+        CUDA_OK(h, cudaDeviceSynchronize());
+        if (tmp) cudaFree(tmp);
+        s.loaded = true;
+        return 0;
+    }
     CUDA_OK(h, cudaMemcpy2D(s.dst, s.dst_pitch, data, s.row_bytes, s.row_bytes, s.rows, kind));
     s.loaded = true;
     return 0;
@@ -883,7 +992,7 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
         return 0;
     };
     if (c.use_graphs) {
-        const int key = B | (want_feats ? 1 << 8 : 0);
+        const int key = B | (want_feats ? 1 << 8 : 0) | static_cast<int>((h->kfilter & 0xFFFFu) << 9);
         auto it = h->frame_graphs.find(key);
         if (it == h->frame_graphs.end()) {
             // warm run outside capture: fills the tensor-map cache and sets function attributes
@@ -1057,6 +1166,18 @@ int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, in
     a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
     a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
     return launch_attn(h, a, D, H, B, static_cast<cudaStream_t>(stream));
+}
+
+int sm_test_gemm_trace(sm_handle* h, long long* device_buf) {
+    if (!h) return 1;
+    h->gemm_dbg = device_buf;
+    return 0;
+}
+
+int sm_debug_kernel_filter(sm_handle* h, unsigned mask) {
+    if (!h) return 1;
+    h->kfilter = mask;
+    return 0;
 }
 
 int sm_profile_enable(sm_handle* h, int on) {

@@ -62,12 +62,14 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uin
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kAttnBQ = 64;   // query rows per CTA (4 warps x 16)
+constexpr int kAttnBQ = 64;   // query rows per CTA (4 warps x 16 per key group)
 constexpr int kAttnBK = 64;   // keys per pipeline stage
-constexpr int kAttnThreads = 128;
+constexpr int kAttnGroups = 2;  // key groups per CTA: group g walks key tiles g, g+2, ... (halves the serial chain)
+constexpr int kAttnGroupThreads = 128;
+constexpr int kAttnThreads = kAttnGroups * kAttnGroupThreads;
 
 template <int D> __host__ __device__ constexpr int attn_smem_bytes() {
-    return (kAttnBQ + 4 * kAttnBK) * D * 2;
+    return (kAttnBQ + kAttnGroups * 4 * kAttnBK) * D * 2;
 }
 // byte offset of element (row, col) in a [rows][D] tile with 16-byte chunks XOR-swizzled by row
 template <int D> __device__ __forceinline__ uint32_t swz(int row, int col) {
@@ -75,12 +77,12 @@ template <int D> __device__ __forceinline__ uint32_t swz(int row, int col) {
     return static_cast<uint32_t>(row * (D * 2) + ((((chunk & 7) ^ (row & 7)) | (chunk & ~7)) << 4) + ((col & 7) << 1));
 }
 
-template <typename T, int D>
+template <typename T, int D, int NT>
 __device__ __forceinline__ void attn_load_tile(uint8_t* smem_tile, const T* base, long long row_stride, int row0,
                                                int nrows_valid_total, int tid) {
-    // tile = kAttnBK (== kAttnBQ) rows x D; rows >= nrows_valid_total are zero-filled
+    // tile = kAttnBK (== kAttnBQ) rows x D; rows >= nrows_valid_total are zero-filled; NT cooperating threads
     constexpr int CHUNKS = D / 8;
-    for (int i = tid; i < kAttnBK * CHUNKS; i += kAttnThreads) {
+    for (int i = tid; i < kAttnBK * CHUNKS; i += NT) {
         const int r = i / CHUNKS, c = i % CHUNKS;
         const bool ok = (row0 + r) < nrows_valid_total;
         const T* src = base + static_cast<long long>(ok ? row0 + r : 0) * row_stride + c * 8;
@@ -91,10 +93,12 @@ __device__ __forceinline__ void attn_load_tile(uint8_t* smem_tile, const T* base
 template <typename T, int D>
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs a) {
     extern __shared__ __align__(128) uint8_t attn_smem[];
+    constexpr int TILE = kAttnBK * D * 2;
+    const int tid = threadIdx.x, grp = tid / kAttnGroupThreads, gtid = tid % kAttnGroupThreads;
+    const int warp = gtid >> 5, lane = tid & 31;
     uint8_t* sQ = attn_smem;
-    uint8_t* sK = sQ + kAttnBQ * D * 2;        // 2 stages
-    uint8_t* sV = sK + 2 * kAttnBK * D * 2;    // 2 stages
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* sK = sQ + kAttnBQ * D * 2 + grp * 4 * TILE;   // 2 stages
+    uint8_t* sV = sK + 2 * TILE;                            // 2 stages
     const int q0 = blockIdx.x * kAttnBQ;
     const int h = blockIdx.y, b = blockIdx.z;
     const int hk = h / a.group;
@@ -107,10 +111,14 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
     if (a.causal) kv_end = min(kv_end, a.q_pos0 + min(q0 + kAttnBQ, a.q_len));
     const int ntiles = (kv_end + kAttnBK - 1) / kAttnBK;
 
-    attn_load_tile<T, D>(sQ, qp, a.q_ss, q0, a.q_len, tid);
-    attn_load_tile<T, D>(sK, kp, a.k_ss, 0, kv_end, tid);
-    attn_load_tile<T, D>(sV, vp, a.v_ss, 0, kv_end, tid);
+    attn_load_tile<T, D, kAttnThreads>(sQ, qp, a.q_ss, q0, a.q_len, tid);
+    if (grp < ntiles) {
+        attn_load_tile<T, D, kAttnGroupThreads>(sK, kp, a.k_ss, grp * kAttnBK, kv_end, gtid);
+        attn_load_tile<T, D, kAttnGroupThreads>(sV, vp, a.v_ss, grp * kAttnBK, kv_end, gtid);
+    }
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 
     constexpr int KD = D / 16;   // k-steps over the head dim for QK^T
     constexpr int NB = kAttnBK / 8;  // 8-wide key blocks per stage
@@ -122,28 +130,22 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
     uint32_t qf[KD][4];
     const int g = lane >> 2, t = lane & 3;
     const int qrow_a = q0 + warp * 16 + g;  // rows owned: qrow_a and qrow_a + 8
-
-    for (int it = 0; it < ntiles; ++it) {
-        const int st = it & 1;
-        if (it + 1 < ntiles) {
-            attn_load_tile<T, D>(sK + (st ^ 1) * kAttnBK * D * 2, kp, a.k_ss, (it + 1) * kAttnBK, kv_end, tid);
-            attn_load_tile<T, D>(sV + (st ^ 1) * kAttnBK * D * 2, vp, a.v_ss, (it + 1) * kAttnBK, kv_end, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (it == 0) {
 #pragma unroll
-            for (int kk = 0; kk < KD; ++kk) {
-                const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int col = kk * 16 + (lane >> 4) * 8;
-                ldmatrix_x4(qf[kk], smem_u32(sQ + swz<D>(row, col)));
-            }
+    for (int kk = 0; kk < KD; ++kk) {
+        const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = kk * 16 + (lane >> 4) * 8;
+        ldmatrix_x4(qf[kk], smem_u32(sQ + swz<D>(row, col)));
+    }
+
+    int st = 0;
+    for (int it = grp; it < ntiles; it += kAttnGroups) {
+        if (it + kAttnGroups < ntiles) {
+            attn_load_tile<T, D, kAttnGroupThreads>(sK + (st ^ 1) * TILE, kp, a.k_ss, (it + kAttnGroups) * kAttnBK, kv_end, gtid);
+            attn_load_tile<T, D, kAttnGroupThreads>(sV + (st ^ 1) * TILE, vp, a.v_ss, (it + kAttnGroups) * kAttnBK, kv_end, gtid);
         }
-        const uint8_t* tK = sK + st * kAttnBK * D * 2;
-        const uint8_t* tV = sV + st * kAttnBK * D * 2;
+        cp_async_commit();
+        const uint8_t* tK = sK + st * TILE;
+        const uint8_t* tV = sV + st * TILE;
         // ---- S = Q K^T  (16 x 64 per warp)
         float s[NB][4];
 #pragma unroll
@@ -220,13 +222,37 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
                 mma16816<T>(o_acc[2 * nb2 + 1], pf[kk], bf[2], bf[3]);
             }
         }
-        __syncthreads();  // stage st is refilled next iteration
+        cp_async_wait<0>();                       // next tile landed (issued before this tile's math)
+        named_bar_sync(1 + grp, kAttnGroupThreads);   // group-local: everyone is done with stage st
+        st ^= 1;
     }
-    // ---- normalise and store
+    // ---- quad-reduce the row sums, then merge the key groups (group 1 -> smem -> group 0)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    __syncthreads();                                // all key tiles consumed: stage memory is free
+    float* mb = reinterpret_cast<float*>(attn_smem + kAttnBQ * D * 2) + gtid * (OD * 4 + 4);
+    if (grp == 1) {
+#pragma unroll
+        for (int i = 0; i < OD; ++i) {
+            mb[i * 4 + 0] = o_acc[i][0]; mb[i * 4 + 1] = o_acc[i][1];
+            mb[i * 4 + 2] = o_acc[i][2]; mb[i * 4 + 3] = o_acc[i][3];
+        }
+        mb[OD * 4 + 0] = m_run[0]; mb[OD * 4 + 1] = m_run[1];
+        mb[OD * 4 + 2] = l_run[0]; mb[OD * 4 + 3] = l_run[1];
+    }
+    __syncthreads();
+    if (grp != 0) return;
+    float sc0[2], sc1[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float m1 = mb[OD * 4 + r], l1 = mb[OD * 4 + 2 + r];
+        const float mm = fmaxf(m_run[r], m1);
+        sc0[r] = m_run[r] == -INFINITY ? 0.f : exp2f(m_run[r] - mm);
+        sc1[r] = m1 == -INFINITY ? 0.f : exp2f(m1 - mm);
+        l_run[r] = l_run[r] * sc0[r] + l1 * sc1[r];
     }
     T* op = reinterpret_cast<T*>(a.o) + b * a.o_bs + h * D;
 #pragma unroll
@@ -236,8 +262,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
             const float inv = l_run[r] > 0.f ? 1.0f / l_run[r] : 0.f;
 #pragma unroll
             for (int i = 0; i < OD; ++i) {
-                const uint32_t pk = Cvt<T>::pack2(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv);
-                *reinterpret_cast<uint32_t*>(op + qrow * a.o_ss + i * 8 + 2 * t) = pk;
+                const float v0 = o_acc[i][2 * r] * sc0[r] + mb[i * 4 + 2 * r] * sc1[r];
+                const float v1 = o_acc[i][2 * r + 1] * sc0[r] + mb[i * 4 + 2 * r + 1] * sc1[r];
+                *reinterpret_cast<uint32_t*>(op + qrow * a.o_ss + i * 8 + 2 * t) = Cvt<T>::pack2(v0 * inv, v1 * inv);
             }
         }
     }

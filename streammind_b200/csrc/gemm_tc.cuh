@@ -8,8 +8,9 @@
 //   swap = 1 : A = weights (features),  B = activations (tokens) -> out[token][feature]  (small-token
 //              GEMMs: the 128-wide MMA M dimension is filled by weight rows, tokens ride on N >= 16)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global; warp w may only touch TMEM lanes 32*(w%4)..+31).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> smem/global; warp w may only touch TMEM lanes 32*(w%4)..+31, so
+// warps w and w+4 share a lane quarter and take alternate 32-column chunks).
 // Operand tiles are 64-element (128-byte) K slabs in SWIZZLE_128B layout, NSTAGE-deep mbarrier ring.
 #pragma once
 #include "ptx.cuh"
@@ -32,11 +33,23 @@ struct GemmArgs {
     int bn;      // tile width on the B side (multiple of 16, 16..256); TMA box of tmap_b has bn rows
     int nstage;  // smem ring depth
     int epi;     // EpiMode
+    int tma_store;  // non-swapped T outputs with bn % 64 == 0: stage the tile in smem, write it with TMA
+    int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
+                    // 16 KiB operand tile contiguous (full-rate DRAM bursts instead of 128-byte strided reads)
+    int w_kb;       // k-blocks per n_tile in that layout
+    long long* dbg; // optional: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
 };
+
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kGemmEpiThreads = 256;
 constexpr int kGemmMaxStages = 8;
 constexpr int kGemmSmemBudget = 200 * 1024;
 
@@ -45,19 +58,21 @@ inline int gemm_num_stages(int bn) {
     int s = kGemmSmemBudget / gemm_stage_bytes(bn);
     return s > kGemmMaxStages ? kGemmMaxStages : s;
 }
-inline int gemm_smem_bytes(int bn) { return gemm_num_stages(bn) * gemm_stage_bytes(bn) + 1024 + 256; }
+inline int gemm_smem_bytes(int bn) { return gemm_num_stages(bn) * gemm_stage_bytes(bn) + 1024 + 256 + 1024; }
 
 template <typename T> __device__ __forceinline__ float quick_gelu_t(float h) {
     // every intermediate is materialised in T by the reference: 1.702*x, sigmoid(.), x*(.)
-    float a = rnd<T>(1.702f * h);
-    float s = rnd<T>(1.0f / (1.0f + __expf(-a)));
+    // sigmoid through MUFU.EX2 + MUFU.RCP (approximation error << one T ulp; an IEEE division here made
+    // this epilogue 8x slower than the mainloop)
+    const float a = rnd<T>(1.702f * h);
+    const float s = rnd<T>(__fdividef(1.0f, 1.0f + __expf(-a)));
     return h * s;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmArgs args) {
+               const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
     const int BN = args.bn;
     const int NSTAGE = args.nstage;
     constexpr int A_BYTES = kGemmBM * kGemmBK * 2;
@@ -75,6 +90,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long* dbg = args.dbg;   // per-launch record: [0] = min CTA start, [i] = max over CTAs of phase i end
+    if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(dbg), static_cast<unsigned long long>(gtimer()));
     const int a0 = blockIdx.x * kGemmBM;  // first A row of this tile
     const int b0 = blockIdx.y * BN;       // first B row of this tile
     const int num_kb = (args.K + kGemmBK - 1) / kGemmBK;
@@ -82,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (args.tma_store) tma_prefetch_desc(&tmap_c);
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -93,36 +111,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here
+    if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 1), static_cast<unsigned long long>(gtimer()));
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer
-            // weights are streamed once; activations are re-read by every CTA column -> keep them in L2
-            const uint64_t pol_a = args.swap ? kEvictFirst : kEvictLast;
-            const uint64_t pol_b = args.swap ? kEvictLast : kEvictNormal;
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ---------------- TMA producer: the whole warp walks the ring, one elected lane issues
+        // weights are streamed once; activations are re-read by every CTA column -> keep them in L2
+        const uint64_t pol_a = args.swap ? kEvictFirst : kEvictLast;
+        const uint64_t pol_b = args.swap ? kEvictLast : kEvictNormal;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * kGemmBK, a0, pol_a);
-                tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (!args.w_tiled) {
+                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * kGemmBK, a0, pol_a);
+                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
+                } else if (args.swap) {   // A = tiled weights
+                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], 0,
+                                (blockIdx.x * args.w_kb + kb) * kGemmBM, pol_a);
+                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
+                } else {                  // B = tiled weights, BN rows = BN/128 whole tiles or a slice of one
+                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * kGemmBK, a0, pol_a);
+                    const int nld = BN > kGemmBM ? BN / kGemmBM : 1;
+                    for (int j = 0; j < nld; ++j)
+                        tma_load_2d(smem_b + stage * B_BYTES + j * (kGemmBM * 128), &tmap_b, &full_bar[stage], 0,
+                                    ((b0 / kGemmBM + j) * args.w_kb + kb) * kGemmBM + (b0 % kGemmBM), pol_b);
+                }
             }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer (one thread)
-            const uint32_t idesc = umma_idesc_f16(kGemmBM, BN, Cvt<T>::kBf16);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
+        // ---------------- MMA issuer: whole warp waits, one elected lane issues tcgen05.mma / commit
+        const uint32_t idesc = umma_idesc_f16(kGemmBM, BN, Cvt<T>::kBf16);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
                 const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * A_BYTES));
                 const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * B_BYTES));
 #pragma unroll
@@ -131,112 +165,167 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (kb == num_kb - 1) umma_commit(accum_bar);  // accumulator complete
             }
-            umma_commit(accum_bar);  // accumulator complete
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else {
-        // ---------------- epilogue warps 2..5
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        // ---------------- epilogue warps 2..9
         const int lane_base = (warp & 3) * 32;
+        const int chalf = (warp - 2) >> 2;   // 0: even 32-column chunks, 1: odd chunks
         const int a_row = a0 + lane_base + lane;  // A row owned by this thread
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
         T* out_t = reinterpret_cast<T*>(args.out);
         float* out_f = reinterpret_cast<float*>(args.out);
         const T* bias = reinterpret_cast<const T*>(args.bias);
         const int epi = args.epi;
         const bool a_ok = a_row < args.Ma;
+        // While the mainloop runs: stage the bias of this tile's columns in smem (non-swapped layout)
+        float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [256] floats after the barriers
         if (!args.swap) {
-            // thread = token row; columns = features; 16 contiguous features per step
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                __syncwarp();
-                tmem_ld_x16(taddr + c, r);
-                tmem_wait_ld();
+            const int et = threadIdx.x - 64;  // 0..255
+            for (int c = et; c < BN; c += kGemmEpiThreads) {
                 const int col = b0 + c;
-                if (a_ok && col < args.Nb) {
-                    float v[16];
+                bias_s[c] = (bias != nullptr && col < args.Nb) ? Cvt<T>::to_f(bias[col]) : 0.0f;
+            }
+            named_bar_sync(1, kGemmEpiThreads);
+        }
+        const float bv = (args.swap && bias != nullptr && a_ok) ? Cvt<T>::to_f(bias[a_row]) : 0.0f;
+        if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 2), static_cast<unsigned long long>(gtimer()));
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 3), static_cast<unsigned long long>(gtimer()));
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
+        // 32-column chunks, TMEM load of chunk c+1 (and residual read) in flight while chunk c is processed
+        const int nchunk = (BN + 31) / 32;
+        uint32_t rbA[32], rbB[32];
+        uint4 xrA[4], xrB[4];
+        auto prefetch_res = [&](int c, uint4 (&xr)[4]) {
+            if (epi == EPI_RESIDUAL && !args.swap && a_ok) {
+                const int col = b0 + c * 32;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    if (bias != nullptr) {
-                        uint4 q0 = *reinterpret_cast<const uint4*>(bias + col);
-                        uint4 q1 = *reinterpret_cast<const uint4*>(bias + col + 8);
-                        uint32_t bw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                for (int q = 0; q < 4; ++q)
+                    if (col + q * 8 < args.Nb && c * 32 + q * 8 < BN)
+                        xr[q] = *reinterpret_cast<const uint4*>(out_t + static_cast<size_t>(a_row) * args.ldo + col + q * 8);
+            }
+        };
+        auto process = [&](int c, const uint32_t (&rb)[32], const uint4 (&xr)[4]) {
+            const int cbase = c * 32;
+            if (!a_ok) return;
+            if (!args.swap) {
+                // thread = token row; columns = features; 8 contiguous features (16 bytes) per store
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float2 f = Cvt<T>::unpack2(bw[i]);
-                            v[2 * i] += f.x;
-                            v[2 * i + 1] += f.y;
-                        }
-                    }
-                    const size_t off = static_cast<size_t>(a_row) * args.ldo + col;
-                    if (epi == EPI_STORE_F32) {
+                for (int q = 0; q < 4; ++q) {
+                    const int col = b0 + cbase + q * 8;
+                    if (col < args.Nb && cbase + q * 8 < BN) {
+                        float v[8];
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(out_f + off + i) =
-                                make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-                        if (epi == EPI_QUICK_GELU) {
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rb[q * 8 + i]) + bias_s[cbase + q * 8 + i];
+                        const size_t off = static_cast<size_t>(a_row) * args.ldo + col;
+                        if (epi == EPI_STORE_F32) {
+                            *reinterpret_cast<float4*>(out_f + off) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(out_f + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            if (epi == EPI_QUICK_GELU) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = quick_gelu_t<T>(rnd<T>(v[i]));
-                        } else if (epi == EPI_RESIDUAL) {
-                            uint4 x0 = *reinterpret_cast<const uint4*>(out_t + off);
-                            uint4 x1 = *reinterpret_cast<const uint4*>(out_t + off + 8);
-                            uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                                for (int i = 0; i < 8; ++i) v[i] = quick_gelu_t<T>(rnd<T>(v[i]));
+                            } else if (epi == EPI_RESIDUAL) {
+                                const uint4 x0 = xr[q];
+                                const uint32_t xw[4] = {x0.x, x0.y, x0.z, x0.w};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float2 f = Cvt<T>::unpack2(xw[i]);
-                                v[2 * i] = f.x + rnd<T>(v[2 * i]);
-                                v[2 * i + 1] = f.y + rnd<T>(v[2 * i + 1]);
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = Cvt<T>::unpack2(xw[i]);
+                                    v[2 * i] = f.x + rnd<T>(v[2 * i]);
+                                    v[2 * i + 1] = f.y + rnd<T>(v[2 * i + 1]);
+                                }
+                            }
+                            uint4 o;
+                            o.x = Cvt<T>::pack2(v[0], v[1]); o.y = Cvt<T>::pack2(v[2], v[3]);
+                            o.z = Cvt<T>::pack2(v[4], v[5]); o.w = Cvt<T>::pack2(v[6], v[7]);
+                            if (args.tma_store) {
+                                // staging tile: 64-column blocks of [128 rows x 128 B], SWIZZLE_128B
+                                const int ct = cbase + q * 8, r = lane_base + lane;
+                                uint8_t* dst = smem_a + (ct >> 6) * (kGemmBM * 128) + r * 128 +
+                                               ((((ct & 63) >> 3) ^ (r & 7)) << 4);
+                                *reinterpret_cast<uint4*>(dst) = o;
+                            } else {
+                                *reinterpret_cast<uint4*>(out_t + off) = o;
                             }
                         }
-                        uint4 o0, o1;
-                        o0.x = Cvt<T>::pack2(v[0], v[1]);   o0.y = Cvt<T>::pack2(v[2], v[3]);
-                        o0.z = Cvt<T>::pack2(v[4], v[5]);   o0.w = Cvt<T>::pack2(v[6], v[7]);
-                        o1.x = Cvt<T>::pack2(v[8], v[9]);   o1.y = Cvt<T>::pack2(v[10], v[11]);
-                        o1.z = Cvt<T>::pack2(v[12], v[13]); o1.w = Cvt<T>::pack2(v[14], v[15]);
-                        *reinterpret_cast<uint4*>(out_t + off) = o0;
-                        *reinterpret_cast<uint4*>(out_t + off + 8) = o1;
+                    }
+                }
+            } else {
+                // thread = feature; columns = tokens; a warp writes 32 consecutive features of one token
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int tok = b0 + cbase + i;
+                    if (tok < args.Nb && cbase + i < BN) {
+                        float v = __uint_as_float(rb[i]) + bv;
+                        const size_t off = static_cast<size_t>(tok) * args.ldo + a_row;
+                        if (epi == EPI_STORE_F32) {
+                            out_f[off] = v;
+                        } else {
+                            if (epi == EPI_QUICK_GELU) v = quick_gelu_t<T>(rnd<T>(v));
+                            if (epi == EPI_RESIDUAL) v = Cvt<T>::to_f(out_t[off]) + rnd<T>(v);
+                            out_t[off] = Cvt<T>::from_f(v);
+                        }
                     }
                 }
             }
-        } else {
-            // thread = feature; columns = tokens; a warp writes 32 consecutive features of one token
-            const float bv = (bias != nullptr && a_ok) ? Cvt<T>::to_f(bias[a_row]) : 0.0f;
+        };
+        // BN is a multiple of 16: the last chunk may be half valid; x32 loads stay inside the TMEM
+        // allocation because it is a power of two >= 32.  Chunk c+1 (TMEM load + residual read) is in
+        // flight while chunk c is processed; ping-pong on two statically indexed register sets.
+        // this warp's chunks: chalf, chalf + 2, ...
+        const int nmine = nchunk > chalf ? (nchunk - chalf + 1) / 2 : 0;
+        auto chunk_of = [&](int k) { return chalf + 2 * k; };
+        if (nmine > 0) {
+            prefetch_res(chunk_of(0), xrA);
+            __syncwarp();
+            tmem_ld_x32(taddr + chunk_of(0) * 32, rbA);
+            tmem_wait_ld();
+        }
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
+        for (int k = 0; k < nmine; k += 2) {
+            const bool has1 = k + 1 < nmine, has2 = k + 2 < nmine;
+            if (has1) {
+                prefetch_res(chunk_of(k + 1), xrB);
                 __syncwarp();
-                tmem_ld_x16(taddr + c, r);
+                tmem_ld_x32(taddr + chunk_of(k + 1) * 32, rbB);
+            }
+            process(chunk_of(k), rbA, xrA);
+            if (has1) {
                 tmem_wait_ld();
-                if (a_ok) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int tok = b0 + c + i;
-                        if (tok < args.Nb) {
-                            float v = __uint_as_float(r[i]) + bv;
-                            const size_t off = static_cast<size_t>(tok) * args.ldo + a_row;
-                            if (epi == EPI_STORE_F32) {
-                                out_f[off] = v;
-                            } else {
-                                if (epi == EPI_QUICK_GELU) v = quick_gelu_t<T>(rnd<T>(v));
-                                if (epi == EPI_RESIDUAL) v = Cvt<T>::to_f(out_t[off]) + rnd<T>(v);
-                                out_t[off] = Cvt<T>::from_f(v);
-                            }
-                        }
-                    }
+                if (has2) {
+                    prefetch_res(chunk_of(k + 2), xrA);
+                    __syncwarp();
+                    tmem_ld_x32(taddr + chunk_of(k + 2) * 32, rbA);
                 }
+                process(chunk_of(k + 1), rbB, xrB);
+                if (has2) tmem_wait_ld();
+            }
+        }
+        if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 4), static_cast<unsigned long long>(gtimer()));
+        if (args.tma_store) {
+            // the mainloop is over (accum_bar): the operand ring is free and doubles as the staging tile
+            fence_proxy_async_smem();
+            named_bar_sync(1, kGemmEpiThreads);
+            if (warp == 2 && elect_one_sync()) {
+                for (int cb = 0; cb < BN / 64; ++cb)
+                    if (b0 + cb * 64 < args.Nb) tma_store_2d(&tmap_c, smem_a + cb * (kGemmBM * 128), b0 + cb * 64, a0);
+                tma_store_commit();
+                tma_store_wait_all();
             }
         }
         tc_fence_before();
     }
+    if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 5), static_cast<unsigned long long>(gtimer()));
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (dbg && threadIdx.x == 32) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 6), static_cast<unsigned long long>(gtimer()));
 }
 
 }  // namespace smb

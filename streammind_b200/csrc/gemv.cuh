@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
             }
         }
     };
-    if (item < nitems) issue(item, 0);
+    pdl_trigger();
+    if (item < nitems) issue(item, 0);   // weights never depend on the previous kernel
+    pdl_wait();
 
     // ---- stage pro(x) in shared memory
     {

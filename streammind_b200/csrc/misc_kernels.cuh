@@ -30,6 +30,20 @@ __global__ void im2col_kernel(const T* __restrict__ px, T* __restrict__ out, int
     }
 }
 
+// Re-tile a row-major weight block [rows, cols] into the GEMM's HBM operand layout
+// dst[((r / 128) * KB + c / 64) * 128 + r % 128][c % 64]  (r counted from row0 of the packed matrix).
+template <typename T>
+__global__ void retile_weight_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols, int row0,
+                                     int kb_total) {
+    const long long total = static_cast<long long>(rows) * cols;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / cols) + row0, c = static_cast<int>(i % cols);
+        const long long tile = static_cast<long long>(r / 128) * kb_total + c / 64;
+        dst[(tile * 128 + r % 128) * 64 + c % 64] = src[i];
+    }
+}
+
 // warp-per-row LayerNorm helper: C <= 32*VPL elements, fp32 statistics, returns normalised values in v[]
 template <typename T, int VPL>
 __device__ __forceinline__ void warp_layernorm(float (&v)[VPL], int C, int lane, const T* w, const T* b, float eps) {
@@ -90,22 +104,68 @@ __global__ void vit_embed_ln_kernel(const T* __restrict__ patch_emb, const T* __
     }
 }
 
-template <typename T, int VPL>
-__global__ void layernorm_kernel(const T* __restrict__ x, const T* w, const T* b, T* __restrict__ h, int rows, int C,
-                                 float eps) {
+// LayerNorm rows: one warp per row, fp32 two-pass statistics held in registers.  Fast path: C a multiple of
+// 256 up to 1024 -> each lane owns C/256 chunks of 8 contiguous elements (16-byte loads / stores).
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
+                                 T* __restrict__ h, int rows, int C, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    float v[VPL];
+    const T* xr = x + static_cast<long long>(warp) * C;
+    T* hr = h + static_cast<long long>(warp) * C;
+    if ((C & 255) == 0 && C <= 1024) {
+        float v[4][8];
+        const int nch = C >> 8;
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = lane + i * 32;
-        v[i] = c < C ? Cvt<T>::to_f(x[static_cast<long long>(warp) * C + c]) : 0.f;
-    }
-    warp_layernorm<T, VPL>(v, C, lane, w, b, eps);
+        for (int j = 0; j < 4; ++j) {
+            if (j < nch) {
+                const uint4 u = *reinterpret_cast<const uint4*>(xr + j * 256 + lane * 8);
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = lane + i * 32;
-        if (c < C) h[static_cast<long long>(warp) * C + c] = Cvt<T>::from_f(v[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = Cvt<T>::unpack2(uw[i]);
+                    v[j][2 * i] = f.x; v[j][2 * i + 1] = f.y;
+                    s += f.x + f.y;
+                }
+            }
+        }
+        s = warp_sum(s);
+        const float mean = s / C;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nch)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; sq += d * d; }
+        sq = warp_sum(sq);
+        const float r = rsqrtf(sq / C + eps);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nch) {
+                const uint4 wu = *reinterpret_cast<const uint4*>(w + j * 256 + lane * 8);
+                const uint4 bu = *reinterpret_cast<const uint4*>(b + j * 256 + lane * 8);
+                const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 wf = Cvt<T>::unpack2(ww[i]), bf = Cvt<T>::unpack2(bw[i]);
+                    o[i] = Cvt<T>::pack2((v[j][2 * i] - mean) * r * wf.x + bf.x, (v[j][2 * i + 1] - mean) * r * wf.y + bf.y);
+                }
+                *reinterpret_cast<uint4*>(hr + j * 256 + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += Cvt<T>::to_f(xr[c]);
+        s = warp_sum(s);
+        const float mean = s / C;
+        float sq = 0.f;
+        for (int c = lane; c < C; c += 32) { const float d = Cvt<T>::to_f(xr[c]) - mean; sq += d * d; }
+        sq = warp_sum(sq);
+        const float r = rsqrtf(sq / C + eps);
+        for (int c = lane; c < C; c += 32)
+            hr[c] = Cvt<T>::from_f((Cvt<T>::to_f(xr[c]) - mean) * r * Cvt<T>::to_f(w[c]) + Cvt<T>::to_f(b[c]));
     }
 }
 

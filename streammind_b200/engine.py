@@ -218,6 +218,20 @@ class Engine:
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.sm_launch_count(self._h, 1 if reset else 0))
 
+    KERNEL_CLASSES = ["gemm_tc_kernel", "gemv_kernel", "attention_kernel", "layernorm_kernel", "im2col_kernel",
+                      "vit_finalize_kernel", "mamba_scan_step_kernel"]
+
+    def kernel_filter(self, classes=None):
+        """Launch only the named kernel classes (None = all).  Measurement aid, see sm_debug_kernel_filter."""
+        if classes is None:
+            mask = 0xFFFFFFFF
+        else:
+            mask = 0
+            for i in range(16):
+                if self.lib.sm_profile_class_name(i).decode() in classes:
+                    mask |= 1 << i
+        self._check(self.lib.sm_debug_kernel_filter(self._h, mask))
+
     def profile(self, on: bool):
         self._check(self.lib.sm_profile_enable(self._h, 1 if on else 0))
 

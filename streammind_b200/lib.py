@@ -50,10 +50,12 @@ SYMBOLS = {
     "sm_kv_len": (_I, [_VP]),
     "sm_kv_set_len": (_I, [_VP, _I]),
     "sm_test_gemm": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "sm_test_gemm_trace": (_I, [_VP, _VP]),
     "sm_test_attention": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "sm_profile_enable": (_I, [_VP, _I]),
     "sm_profile_read": (_I, [_VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sm_profile_class_name": (C.c_char_p, [_I]),
+    "sm_debug_kernel_filter": (_I, [_VP, C.c_uint]),
     "sm_launch_count": (_LL, [_VP, _I]),
 }
 
