@@ -320,12 +320,125 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_decode_workload(args):
+    """BASELINE configs[2] / [4]: ViT encode + gated Mistral-7B greedy decode through the reference-facing API
+    (StreamMindB200ForCausalLM.stream_generate_demo), bf16, persistent KV cache.  Gate policy is overridden
+    (fire schedule below, the authors' own "# pred = 1" switch) while gate logits are still computed."""
+    import torch
+    from streammind_b200 import dist_util, synth
+    from streammind_b200.engine import EngineConfig
+    from streammind_b200.model import StreamMindB200ForCausalLM
+    rank, world, local = dist_util.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_util.init("nccl", dev)
+    dt = torch.bfloat16
+    if args.workload == "gated_decode":
+        n_frames, fire_every, max_new, label = 256, 16, 224, "BASELINE configs[2]: 256-frame stream, fire every 16th frame, 224 greedy tokens per fire, KV -> ~4.1k"
+    else:
+        n_frames, fire_every, max_new, label = 512, 1, 5, "BASELINE configs[4]: gate-off dense mode, 512 frames, every frame fires, 5 greedy tokens, KV -> ~8.3k"
+    if args.frames != 64:
+        n_frames = args.frames
+    cfg = EngineConfig(dtype=dt, max_frames=1, llm_max_ctx=8704, use_graphs=not args.no_graphs)
+    model = StreamMindB200ForCausalLM(cfg, None, device=local)
+    seed = 1234
+    for part in (synth.make_vit_weights(seed, dt, device=dev, layers=cfg.vit_layers),
+                 synth.make_projector_gate_weights(seed, dt, device=dev)):
+        model.engine.load_state_dict(part)
+        del part
+    # the LLM is generated and uploaded layer by layer (14.5 GB)
+    full = synth.make_mistral_weights(seed, "", dt, device=dev, vocab=cfg.llm_vocab)
+    model.engine.load_state_dict(full)
+    del full
+    torch.cuda.empty_cache()
+    model.engine.finalize()
+    prompt0, turn_suffix = synth.make_prompt_ids(vocab=32000)
+    frames_host = synth.make_frames(rank, 0, n_frames, 336, dtype=dt).pin_memory()
+    frames_dev = frames_host.to(dev)
+    stats = {}
+
+    def one_stream(frames):
+        model.reset_stream()
+        prompt = list(prompt0)
+        toks = fires = 0
+        t_dec = 0.0
+        for t in range(n_frames):
+            fire = 1 if (t % fire_every == fire_every - 1) else 0
+            ids = torch.tensor([prompt])
+            t0 = time.perf_counter()
+            out, pred = model.stream_generate_demo(ids, images_or_videos=frames[t:t + 1], modal_list=["video"],
+                                                   do_sample=False, max_new_tokens=max_new, use_cache=True,
+                                                   force_pred=fire)
+            if pred:
+                t_dec += time.perf_counter() - t0
+                toks += len(out); fires += 1
+                prompt = prompt + out + turn_suffix
+        stats.update(tokens=toks, fires=fires, kv_len=model.engine.kv_len, decode_wall_s=t_dec)
+
+    def timed(fn, steps):
+        dist_util.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = dist_util.max_over_ranks(e0.elapsed_time(e1), device=dev)
+        dist_util.barrier()
+        return ms
+    for _ in range(args.warmup):
+        one_stream(frames_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.engine.launch_count(reset=True)
+    ms = timed(lambda: one_stream(frames_dev), args.steps)
+    launches = model.engine.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    dec_tok_s = stats["tokens"] / stats["decode_wall_s"]
+    ms_e2e = timed(lambda: one_stream(frames_host), args.steps)
+    if rank == 0:
+        peaks = _peaks()
+        fps = world * n_frames * args.steps / (ms / 1e3)
+        gbs = DECODE_GB_PER_TOKEN * dec_tok_s            # weights only; KV traffic comes on top
+        # serial roofline of the stream (SURVEY.md section 8d)
+        t_frame = (578.8 + GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) / peaks["hbm"] * 1e-3
+        t_tok = DECODE_GB_PER_TOKEN / peaks["hbm"]
+        roof_s = n_frames * t_frame + stats["tokens"] * t_tok + stats["fires"] * t_tok
+        line = {
+            "metric": "streaming frames/sec (encode+gate+decode) @336px, Mistral-7B", "value": fps, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": label + "; CLIP-ViT-L/14-336 + projector + gate + Mistral-7B (32 layers, vocab 32002), random-init, one frame per call",
+                       "frames_per_step": n_frames, "fires": stats["fires"], "decoded_tokens": stats["tokens"],
+                       "kv_len_end": stats["kv_len"], "cuda_graphs": cfg.use_graphs,
+                       "l2_policy": "inputs larger than L2: 14.2 GB of LLM weights are re-streamed per decoded token",
+                       "parallelism": f"{world} independent stream(s), one per GPU"},
+            "e2e": {"value": world * n_frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": n_frames * 3 * 336 * 336 * 2, "d2h_bytes_per_step": n_frames * 8 + stats["tokens"] * 4,
+                    "note": "pinned-host frames, H2D per frame, gate logits and generated ids read back"},
+            "gpu_launches": launches, "clocks": clocks,
+            "decode": {"tokens_per_s": dec_tok_s, "ms_per_token": 1e3 / dec_tok_s,
+                       "note": "wall time of the fire calls (prefill of the new dialogue suffix + greedy decode) / tokens"},
+            "roofline": {"kernel": "gemv_kernel (LLM decode)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_token": DECODE_GB_PER_TOKEN * 1e9},
+            "stream_roofline": {"seconds_at_peak": roof_s, "frac": roof_s / (ms / args.steps / 1e3)},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    model.engine.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="frames", choices=["frames", "gated_decode", "dense_decode"])
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=1, help="frames per call (1 = streaming, as the reference's demo)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
@@ -336,6 +449,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "frames":
+        run_decode_workload(args)
     else:
         run_ours(args)
 

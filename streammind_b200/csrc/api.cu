@@ -16,6 +16,7 @@
 #include <string>
 #include <tuple>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "attention.cuh"
@@ -167,17 +168,29 @@ inline void count_launch(sm_handle* h) {
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its
 // predecessor drains and synchronises itself with griddepcontrol.wait (ptx.cuh pdl_wait).
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(sm_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                       Args&&... args) {
+cudaError_t launch_ex(sm_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      int cluster_y, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
+    int n = 0;
     if (h->use_pdl) {
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
     }
+    if (cluster_y > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = cluster_y; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(sm_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+    return launch_ex(h, kern, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 // per-kernel-class CUDA-event timing (bench.py's roofline pass; off on the timed path)
@@ -237,13 +250,14 @@ GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms) {
     auto eval = [&](int swap, int bn) {
         const long ctas = swap ? (long)((feats + 127) / 128) * ((tokens + bn - 1) / bn)
                                : (long)((tokens + 127) / 128) * ((feats + bn - 1) / bn);
-        const double step = std::max((16384.0 + 128.0 * bn) / 117.0, 1.05 * bn);
-        const double epi = std::ceil(bn / 32.0) * (swap ? 3000.0 : 580.0);
-        const double per_cta = 600.0 + kblocks * step + epi;
+        const double tile_bytes = 16384.0 + 128.0 * bn;
         const double waves = std::ceil((double)ctas / num_sms);
-        // chip-wide L2 -> SM bandwidth (~12 B/ns per SM-equivalent of 100 SMs) bounds many small tiles
-        const double l2 = (double)ctas * kblocks * (16384.0 + 128.0 * bn) / 12000.0;
-        const double cost = std::max(waves * per_cta, l2 + 600.0 + epi);
+        const double active = std::min<double>((double)ctas, num_sms);
+        // per K=64 slab: one SM ingests <= 117 B/ns, the whole chip's L2 serves <= ~12.3 kB/ns, MMA needs 1.05*bn ns
+        const double step = std::max({tile_bytes / 117.0, active * tile_bytes / 12300.0, 1.05 * bn});
+        const double epi = 500.0 + std::ceil(bn / 64.0) * (swap ? 900.0 : 800.0);   // 8 epilogue warps, 64 columns per pass
+        const double per_cta = 800.0 + kblocks * step + epi;
+        const double cost = waves * per_cta;
         if (cost < best) { best = cost; bp = {swap, bn}; }
     };
     if (feats % 16 == 0)
@@ -283,15 +297,33 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         a.Ma = feats; a.Nb = tokens;
         grid = dim3((feats + kGemmBM - 1) / kGemmBM, (tokens + p.bn - 1) / p.bn);
     }
+    // cluster along grid.y: the CTAs of a cluster share the A tile and multicast 128/CS-row slices of it
+    int CS = 1;
+    {
+        static const int max_cs = getenv("SMB_GEMM_CLUSTER") ? atoi(getenv("SMB_GEMM_CLUSTER")) : 8;
+        for (int c = 8; c > 1; c >>= 1)
+            if (c <= max_cs && grid.y % c == 0) { CS = c; break; }
+    }
+    a.cluster_n = CS;
+    if (CS > 1) {
+        if (!p.swap) ta = get_tmap(h, x, tokens, K, kGemmBM / CS);
+        else ta = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, kGemmBM / CS) : get_tmap(h, w, feats, K, kGemmBM / CS);
+    }
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.nstage = gemm_num_stages(p.bn); a.epi = epi;
+    {
+        static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
+        a.dbg_mode = dm;
+    }
     a.dbg = h->gemm_dbg;
     if (h->gemm_dbg) h->gemm_dbg += 8;   // one 8-slot record per launch
     const CUtensorMap* tc = ta;  // placeholder when unused
-    a.tma_store = (!p.swap && epi != EPI_STORE_F32 && p.bn % 64 == 0 && ldo == feats && getenv("SMB_NO_TMA_STORE") == nullptr) ? 1 : 0;
+    static const bool no_tma_store = getenv("SMB_NO_TMA_STORE") != nullptr;
+    if (!p.swap) a.tma_store = (epi != EPI_STORE_F32 && p.bn % 64 == 0 && ldo == feats && !no_tma_store) ? 1 : 0;
+    else a.tma_store = ((epi == EPI_STORE || epi == EPI_QUICK_GELU) && ldo == feats && feats % 8 == 0 && !no_tma_store) ? 1 : 0;
     if (a.tma_store) {
-        tc = get_tmap(h, out, tokens, feats, kGemmBM);
+        tc = get_tmap(h, out, tokens, feats, p.swap ? p.bn : kGemmBM);
         if (!tc) return 1;
     }
     {
@@ -301,7 +333,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     const int smem = gemm_smem_bytes(p.bn);
     {
         ProfScope ps(h, KC_GEMM, st);
-        CUDA_OK(h, launch_pdl(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads), smem, st, *ta, *tb, *tc, a));
+        CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads), smem, st, CS, *ta, *tb, *tc, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());

@@ -34,9 +34,12 @@ struct GemmArgs {
     int nstage;  // smem ring depth
     int epi;     // EpiMode
     int tma_store;  // non-swapped T outputs with bn % 64 == 0: stage the tile in smem, write it with TMA
+    int cluster_n;  // CTAs per cluster along blockIdx.y (1, 2, 4 or 8): they share the A tile, each CTA loads
+                    // 128/cluster_n of its rows and TMA-multicasts them to the whole cluster (L2 reads of A / cluster_n)
     int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
                     // 16 KiB operand tile contiguous (full-rate DRAM bursts instead of 128-byte strided reads)
     int w_kb;       // k-blocks per n_tile in that layout
+    int dbg_mode;   // microbenchmark aid: 1 = no MMA issue (TMA + barriers only), 2 = no TMA (MMA + barriers only)
     long long* dbg; // optional: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
 };
 
@@ -69,6 +72,97 @@ template <typename T> __device__ __forceinline__ float quick_gelu_t(float h) {
     return h * s;
 }
 
+// One 32-column accumulator chunk of one thread, specialised at compile time so the element loop has no
+// mode branches (the runtime-flag version spent ~150 clocks per element on branch resolution).
+//   SWAP = false: thread owns a token row, the chunk is 32 consecutive features (4 x 16-byte stores)
+//   SWAP = true : thread owns a feature, the chunk is 32 tokens (2-byte stores, coalesced across the warp)
+//   TMAST: write into the swizzled smem staging tile (TMA store afterwards) instead of global memory
+struct EpiCtx {
+    const GemmArgs* args;
+    uint8_t* stage;        // smem staging tile (the free operand ring)
+    const float* bias_s;   // non-swap: bias of this tile's columns in smem
+    float bv;              // swap: bias of this thread's feature
+    int a_row, b0, BN, lane_row;   // lane_row = row inside the 128-row tile
+};
+
+template <typename T, bool SWAP, int EPI, bool TMAST>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& cx, int cbase, const uint32_t (&rb)[32], const uint4 (&xr)[4]) {
+    const GemmArgs& args = *cx.args;
+    T* out_t = reinterpret_cast<T*>(args.out);
+    float* out_f = reinterpret_cast<float*>(args.out);
+    if constexpr (!SWAP) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = cx.b0 + cbase + q * 8;
+            if (col < args.Nb && cbase + q * 8 < cx.BN) {
+                const float4 bA = *reinterpret_cast<const float4*>(cx.bias_s + cbase + q * 8);
+                const float4 bB = *reinterpret_cast<const float4*>(cx.bias_s + cbase + q * 8 + 4);
+                float v[8] = {__uint_as_float(rb[q * 8 + 0]) + bA.x, __uint_as_float(rb[q * 8 + 1]) + bA.y,
+                              __uint_as_float(rb[q * 8 + 2]) + bA.z, __uint_as_float(rb[q * 8 + 3]) + bA.w,
+                              __uint_as_float(rb[q * 8 + 4]) + bB.x, __uint_as_float(rb[q * 8 + 5]) + bB.y,
+                              __uint_as_float(rb[q * 8 + 6]) + bB.z, __uint_as_float(rb[q * 8 + 7]) + bB.w};
+                const size_t off = static_cast<size_t>(cx.a_row) * args.ldo + col;
+                if constexpr (EPI == EPI_STORE_F32) {
+                    *reinterpret_cast<float4*>(out_f + off) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(out_f + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                    if constexpr (EPI == EPI_QUICK_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = quick_gelu_t<T>(rnd<T>(v[i]));
+                    } else if constexpr (EPI == EPI_RESIDUAL) {
+                        const uint4 x0 = xr[q];
+                        const uint32_t xw[4] = {x0.x, x0.y, x0.z, x0.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = Cvt<T>::unpack2(xw[i]);
+                            v[2 * i] = f.x + rnd<T>(v[2 * i]);
+                            v[2 * i + 1] = f.y + rnd<T>(v[2 * i + 1]);
+                        }
+                    }
+                    uint4 o;
+                    o.x = Cvt<T>::pack2(v[0], v[1]); o.y = Cvt<T>::pack2(v[2], v[3]);
+                    o.z = Cvt<T>::pack2(v[4], v[5]); o.w = Cvt<T>::pack2(v[6], v[7]);
+                    if constexpr (TMAST) {
+                        // staging tile: 64-column blocks of [128 rows x 128 B], SWIZZLE_128B
+                        const int ct = cbase + q * 8, r = cx.lane_row;
+                        const uint32_t dst = smem_u32(cx.stage) + (ct >> 6) * (kGemmBM * 128) + r * 128 +
+                                             ((((ct & 63) >> 3) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    } else {
+                        *reinterpret_cast<uint4*>(out_t + off) = o;
+                    }
+                }
+            }
+        }
+    } else {
+        const int fr = cx.lane_row;   // feature within the tile
+        const uint32_t sbase = smem_u32(cx.stage) + (fr >> 6) * (cx.BN * 128) + ((fr & 7) << 1);
+        const int fchunk = (fr & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int row = cbase + i;            // token within the tile
+            const int tok = cx.b0 + row;
+            float v = __uint_as_float(rb[i]) + cx.bv;
+            if constexpr (EPI == EPI_QUICK_GELU) v = quick_gelu_t<T>(rnd<T>(v));
+            if constexpr (TMAST) {
+                if (row < cx.BN) {
+                    const uint32_t dst = sbase + row * 128 + ((fchunk ^ (row & 7)) << 4);
+                    const T hv = Cvt<T>::from_f(v);
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+                }
+            } else if (tok < args.Nb && row < cx.BN) {
+                const size_t off = static_cast<size_t>(tok) * args.ldo + cx.a_row;
+                if constexpr (EPI == EPI_STORE_F32) {
+                    out_f[off] = v;
+                } else {
+                    if constexpr (EPI == EPI_RESIDUAL) v = Cvt<T>::to_f(out_t[off]) + rnd<T>(v);
+                    out_t[off] = Cvt<T>::from_f(v);
+                }
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -77,7 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int NSTAGE = args.nstage;
     constexpr int A_BYTES = kGemmBM * kGemmBK * 2;
     const int B_BYTES = BN * kGemmBK * 2;
-    const uint32_t TMEM_COLS = BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
+    const bool ksplit = args.dbg_mode >= 3 && BN <= 128;   // experiment: one accumulator per K=16 step
+    const uint32_t TMEM_COLS = ksplit ? 512u : BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,6 +190,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int a0 = blockIdx.x * kGemmBM;  // first A row of this tile
     const int b0 = blockIdx.y * BN;       // first B row of this tile
     const int num_kb = (args.K + kGemmBK - 1) / kGemmBK;
+    const int CS = args.cluster_n;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = static_cast<uint16_t>((1u << CS) - 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -102,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (args.tma_store) tma_prefetch_desc(&tmap_c);
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CS);   // one tcgen05.commit arrival from every CTA that reads the shared A slices
         }
         mbar_init(accum_bar, 1);
         fence_mbar_init();
@@ -113,7 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     pdl_trigger();
     tc_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all();   // peers' barriers must be initialised before any multicast / remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here
@@ -128,17 +227,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t phase = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one_sync()) {
+            if (args.dbg_mode == 2 || args.dbg_mode == 3) {
+                if (elect_one_sync()) mbar_arrive(&full_bar[stage]);
+            } else if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                if (!args.w_tiled) {
-                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * kGemmBK, a0, pol_a);
-                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
-                } else if (args.swap) {   // A = tiled weights
-                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], 0,
-                                (blockIdx.x * args.w_kb + kb) * kGemmBM, pol_a);
+                // A tile: whole (CS = 1) or this CTA's 128/CS-row slice multicast to the cluster
+                const int a_slice = kGemmBM / CS;
+                uint8_t* a_dst = smem_a + stage * A_BYTES + crank * a_slice * 128;
+                const bool a_is_tiled_w = args.w_tiled && args.swap;
+                const int ac0 = a_is_tiled_w ? 0 : kb * kGemmBK;
+                const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kb) * kGemmBM : a0) + crank * a_slice;
+                if (CS > 1) tma_load_2d_mc(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, cmask, pol_a);
+                else tma_load_2d(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, pol_a);
+                if (!args.w_tiled || args.swap) {
                     tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
                 } else {                  // B = tiled weights, BN rows = BN/128 whole tiles or a slice of one
-                    tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * kGemmBK, a0, pol_a);
                     const int nld = BN > kGemmBM ? BN / kGemmBM : 1;
                     for (int j = 0; j < nld; ++j)
                         tma_load_2d(smem_b + stage * B_BYTES + j * (kGemmBM * 128), &tmap_b, &full_bar[stage], 0,
@@ -159,12 +262,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (elect_one_sync()) {
                 const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * A_BYTES));
                 const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * B_BYTES));
+                if (ksplit) {
 #pragma unroll
-                for (int k = 0; k < kGemmBK / 16; ++k) {
-                    // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in (addr>>4) units
-                    umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kGemmBK / 16; ++k)
+                        umma_f16(tmem_base + k * BN, adesc + 2 * k, bdesc + 2 * k, idesc, kb != 0 ? 1u : 0u);
+                } else if (args.dbg_mode != 1) {
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k) {
+                        // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in (addr>>4) units
+                        umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                // frees the smem slot once these MMAs have read it -- in every CTA that multicasts into it
+                if (CS > 1) umma_commit_mc(&empty_bar[stage], cmask);
+                else umma_commit(&empty_bar[stage]);
                 if (kb == num_kb - 1) umma_commit(accum_bar);  // accumulator complete
             }
             __syncwarp();
@@ -181,7 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int epi = args.epi;
         const bool a_ok = a_row < args.Ma;
         // While the mainloop runs: stage the bias of this tile's columns in smem (non-swapped layout)
-        float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [256] floats after the barriers
+        float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [256] floats, 16-byte aligned
         if (!args.swap) {
             const int et = threadIdx.x - 64;  // 0..255
             for (int c = et; c < BN; c += kGemmEpiThreads) {
@@ -209,68 +320,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         xr[q] = *reinterpret_cast<const uint4*>(out_t + static_cast<size_t>(a_row) * args.ldo + col + q * 8);
             }
         };
+        EpiCtx cx;
+        cx.args = &args; cx.stage = smem_a; cx.bias_s = bias_s; cx.bv = bv; cx.a_row = a_row; cx.b0 = b0; cx.BN = BN;
+        cx.lane_row = lane_base + lane;
+        const int mode = (args.swap ? 8 : 0) | (args.tma_store ? 4 : 0) | epi;   // uniform: one branch per chunk
         auto process = [&](int c, const uint32_t (&rb)[32], const uint4 (&xr)[4]) {
-            const int cbase = c * 32;
             if (!a_ok) return;
-            if (!args.swap) {
-                // thread = token row; columns = features; 8 contiguous features (16 bytes) per store
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = b0 + cbase + q * 8;
-                    if (col < args.Nb && cbase + q * 8 < BN) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rb[q * 8 + i]) + bias_s[cbase + q * 8 + i];
-                        const size_t off = static_cast<size_t>(a_row) * args.ldo + col;
-                        if (epi == EPI_STORE_F32) {
-                            *reinterpret_cast<float4*>(out_f + off) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(out_f + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
-                            if (epi == EPI_QUICK_GELU) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = quick_gelu_t<T>(rnd<T>(v[i]));
-                            } else if (epi == EPI_RESIDUAL) {
-                                const uint4 x0 = xr[q];
-                                const uint32_t xw[4] = {x0.x, x0.y, x0.z, x0.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = Cvt<T>::unpack2(xw[i]);
-                                    v[2 * i] = f.x + rnd<T>(v[2 * i]);
-                                    v[2 * i + 1] = f.y + rnd<T>(v[2 * i + 1]);
-                                }
-                            }
-                            uint4 o;
-                            o.x = Cvt<T>::pack2(v[0], v[1]); o.y = Cvt<T>::pack2(v[2], v[3]);
-                            o.z = Cvt<T>::pack2(v[4], v[5]); o.w = Cvt<T>::pack2(v[6], v[7]);
-                            if (args.tma_store) {
-                                // staging tile: 64-column blocks of [128 rows x 128 B], SWIZZLE_128B
-                                const int ct = cbase + q * 8, r = lane_base + lane;
-                                uint8_t* dst = smem_a + (ct >> 6) * (kGemmBM * 128) + r * 128 +
-                                               ((((ct & 63) >> 3) ^ (r & 7)) << 4);
-                                *reinterpret_cast<uint4*>(dst) = o;
-                            } else {
-                                *reinterpret_cast<uint4*>(out_t + off) = o;
-                            }
-                        }
-                    }
-                }
-            } else {
-                // thread = feature; columns = tokens; a warp writes 32 consecutive features of one token
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int tok = b0 + cbase + i;
-                    if (tok < args.Nb && cbase + i < BN) {
-                        float v = __uint_as_float(rb[i]) + bv;
-                        const size_t off = static_cast<size_t>(tok) * args.ldo + a_row;
-                        if (epi == EPI_STORE_F32) {
-                            out_f[off] = v;
-                        } else {
-                            if (epi == EPI_QUICK_GELU) v = quick_gelu_t<T>(rnd<T>(v));
-                            if (epi == EPI_RESIDUAL) v = Cvt<T>::to_f(out_t[off]) + rnd<T>(v);
-                            out_t[off] = Cvt<T>::from_f(v);
-                        }
-                    }
-                }
+            const int cbase = c * 32;
+            switch (mode) {
+                case 0: epi_chunk<T, false, EPI_STORE, false>(cx, cbase, rb, xr); break;
+                case 1: epi_chunk<T, false, EPI_QUICK_GELU, false>(cx, cbase, rb, xr); break;
+                case 2: epi_chunk<T, false, EPI_RESIDUAL, false>(cx, cbase, rb, xr); break;
+                case 3: epi_chunk<T, false, EPI_STORE_F32, false>(cx, cbase, rb, xr); break;
+                case 4: epi_chunk<T, false, EPI_STORE, true>(cx, cbase, rb, xr); break;
+                case 5: epi_chunk<T, false, EPI_QUICK_GELU, true>(cx, cbase, rb, xr); break;
+                case 6: epi_chunk<T, false, EPI_RESIDUAL, true>(cx, cbase, rb, xr); break;
+                case 8: epi_chunk<T, true, EPI_STORE, false>(cx, cbase, rb, xr); break;
+                case 9: epi_chunk<T, true, EPI_QUICK_GELU, false>(cx, cbase, rb, xr); break;
+                case 10: epi_chunk<T, true, EPI_RESIDUAL, false>(cx, cbase, rb, xr); break;
+                case 11: epi_chunk<T, true, EPI_STORE_F32, false>(cx, cbase, rb, xr); break;
+                case 12: epi_chunk<T, true, EPI_STORE, true>(cx, cbase, rb, xr); break;
+                case 13: epi_chunk<T, true, EPI_QUICK_GELU, true>(cx, cbase, rb, xr); break;
+                default: break;
             }
         };
         // BN is a multiple of 16: the last chunk may be half valid; x32 loads stay inside the TMEM
@@ -311,8 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             fence_proxy_async_smem();
             named_bar_sync(1, kGemmEpiThreads);
             if (warp == 2 && elect_one_sync()) {
-                for (int cb = 0; cb < BN / 64; ++cb)
-                    if (b0 + cb * 64 < args.Nb) tma_store_2d(&tmap_c, smem_a + cb * (kGemmBM * 128), b0 + cb * 64, a0);
+                if (!args.swap) {
+                    for (int cb = 0; cb < BN / 64; ++cb)
+                        if (b0 + cb * 64 < args.Nb) tma_store_2d(&tmap_c, smem_a + cb * (kGemmBM * 128), b0 + cb * 64, a0);
+                } else {
+                    for (int cb = 0; cb < 2; ++cb)
+                        if (a0 + cb * 64 < args.Ma) tma_store_2d(&tmap_c, smem_a + cb * (BN * 128), a0 + cb * 64, b0);
+                }
                 tma_store_commit();
                 tma_store_wait_all();
             }
@@ -320,7 +396,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_before();
     }
     if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 5), static_cast<unsigned long long>(gtimer()));
-    __syncthreads();
+    if (CS > 1) cluster_sync_all();   // no CTA may exit while peers can still multicast into it / arrive on its barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
