@@ -83,6 +83,7 @@ struct sm_handle {
     std::vector<VitLayer> vit;
     void *ws_im = nullptr, *ws_pemb = nullptr, *ws_x = nullptr, *ws_h = nullptr, *ws_qkv = nullptr, *ws_att = nullptr,
          *ws_mlp = nullptr, *ws_pooled = nullptr, *ws_pixels = nullptr, *ws_feats = nullptr;
+    float* ws_part = nullptr;   // split-K partial sums [4][rows][C] fp32
     // ---- projector
     int d_inner = 0, dt_rank = 0;
     void *pj_pre_w = nullptr, *pj_pre_b = nullptr, *pj_norm_w = nullptr, *pj_norm_b = nullptr, *pj_in = nullptr,
@@ -238,44 +239,28 @@ const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int 
 // ------------------------------------------------------------------------------------------ GEMM
 struct GemmPlan { int swap, bn; };
 
-GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms) {
-    // Cost model in nanoseconds, calibrated on B200 with in-kernel timestamps (profiles/r01_gemm_phases.md):
-    //   * one SM ingests ~117 B/ns from L2 through TMA, so a K=64 slab costs (16 KiB + 128*bn B)/117 ns
-    //     unless the MMA (bn/2 clocks per K=16 at 1.9 GHz) is slower;
-    //   * epilogue ~0.58 us per 32 accumulator columns (token-major), ~3 us when transposed (swap);
-    //   * ~0.6 us of setup / drain per CTA, CTAs run in waves of num_sms.
-    double best = 1e30;
-    GemmPlan bp{0, 128};
-    const double kblocks = std::ceil(K / 64.0);
-    auto eval = [&](int swap, int bn) {
-        const long ctas = swap ? (long)((feats + 127) / 128) * ((tokens + bn - 1) / bn)
-                               : (long)((tokens + 127) / 128) * ((feats + bn - 1) / bn);
-        const double tile_bytes = 16384.0 + 128.0 * bn;
-        const double waves = std::ceil((double)ctas / num_sms);
-        const double active = std::min<double>((double)ctas, num_sms);
-        // per K=64 slab: one SM ingests <= 117 B/ns, the whole chip's L2 serves <= ~12.3 kB/ns, MMA needs 1.05*bn ns
-        const double step = std::max({tile_bytes / 117.0, active * tile_bytes / 12300.0, 1.05 * bn});
-        const double epi = 500.0 + std::ceil(bn / 64.0) * (swap ? 900.0 : 800.0);   // 8 epilogue warps, 64 columns per pass
-        const double per_cta = 800.0 + kblocks * step + epi;
-        const double cost = waves * per_cta;
-        if (cost < best) { best = cost; bp = {swap, bn}; }
-    };
-    if (feats % 16 == 0)
-        for (int bn : {32, 64, 128, 256})
-            if (bn <= feats) eval(0, bn);
-    for (int bn = 16; bn <= 256; bn += 16) {
-        eval(1, bn);
-        if (bn >= tokens) break;
-    }
-    return bp;
+GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi) {
+    // Rule distilled from the graph-timed sweep in profiles/r01_gemm_plan_sweep.md: on B200 one tcgen05.mma
+    // costs >= ~105 clocks whatever its N, so a CTA's mainloop lasts ~250 ns per K=64 slab for any tile width;
+    // the best plan is the widest feature tile that still yields about half a wave of CTAs.  Transposed (swap)
+    // tiles only pay off for a handful of tokens (weight rows fill the 128 MMA lanes, tokens ride on N >= 16).
+    (void)K;
+    const bool residual = epi == EPI_RESIDUAL || epi == EPI_STORE_F32;
+    if (tokens <= 64 && !residual) return {1, std::max(16, (tokens + 15) / 16 * 16)};
+    if (feats % 16 != 0) return {1, std::min(256, std::max(16, (tokens + 15) / 16 * 16))};
+    const int mt = (tokens + 127) / 128;
+    for (int bn : {256, 128, 64, 32})
+        if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / 2) return {0, bn};
+    return {0, std::min(32, feats)};
 }
 
 template <typename T>
 int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
-                  int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false) {
+                  int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false,
+                  int split_k = 1) {
     if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
     if (!kon(h, KC_GEMM)) return 0;
-    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms);
+    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi);
     if (force_swap >= 0) p.swap = force_swap;
     if (force_bn > 0) p.bn = force_bn;
     if (!p.swap && (feats % 16 != 0)) return fail(h, "gemm: non-swapped layout needs features %% 16 == 0");
@@ -300,7 +285,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     // cluster along grid.y: the CTAs of a cluster share the A tile and multicast 128/CS-row slices of it
     int CS = 1;
     {
-        static const int max_cs = getenv("SMB_GEMM_CLUSTER") ? atoi(getenv("SMB_GEMM_CLUSTER")) : 8;
+        static const int max_cs = getenv("SMB_GEMM_CLUSTER") ? atoi(getenv("SMB_GEMM_CLUSTER")) : 1;   // measured: no gain on B200 (the mainloop is MMA-issue bound)
         for (int c = 8; c > 1; c >>= 1)
             if (c <= max_cs && grid.y % c == 0) { CS = c; break; }
     }
@@ -309,6 +294,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         if (!p.swap) ta = get_tmap(h, x, tokens, K, kGemmBM / CS);
         else ta = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, kGemmBM / CS) : get_tmap(h, w, feats, K, kGemmBM / CS);
     }
+    if (split_k > 1) { grid.z = split_k; a.split_k = split_k; a.split_stride = static_cast<long long>(tokens) * feats; }
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.nstage = gemm_num_stages(p.bn); a.epi = epi;
@@ -341,10 +327,23 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
 }
 
 int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
-                int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false) {
+                int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false,
+                int split_k = 1) {
     if (h->cfg.dtype == SM_DTYPE_BF16)
-        return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled);
-    return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled);
+        return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
+    return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
+}
+
+// Split-K factor for a residual GEMM whose 128x128 tiles alone cannot fill the SMs (streaming B = 1):
+// every MMA instruction costs >= ~105 clocks whatever its N (profiles/r01_gemm_phases.md), so a CTA's time is
+// ~ k-blocks x 250 ns and the only way to shorten it is to give each CTA fewer k-blocks.
+int splitk_factor(const sm_handle* h, int tokens, int feats, int K) {
+    static const int max_split = getenv("SMB_SPLITK") ? atoi(getenv("SMB_SPLITK")) : 4;
+    const int tiles = ((tokens + 127) / 128) * ((feats + 127) / 128);
+    const int kb = (K + kGemmBK - 1) / kGemmBK;
+    int s = std::min({max_split, h->num_sms / std::max(1, tiles), kb / 4});
+    while (s > 1 && (s - 1) * ((kb + s - 1) / s) >= kb) --s;   // every split gets at least one k-block
+    return s < 2 ? 1 : s;
 }
 
 // ------------------------------------------------------------------------------------------ GEMV
@@ -444,18 +443,39 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         count_launch(h);
     })
     const int D = C / c.vit_heads;
-    for (int l = 0; l < c.vit_layers; ++l) {
-        const VitLayer& L = h->vit[l];
-        if (l > 0) {
+    // x += W a + bias, then h = LN(x) (ln_w == nullptr: no LN).  Small token counts: split-K GEMM into fp32
+    // partials whose fixed-order sum, the residual add and the LayerNorm run in one row kernel.
+    auto residual_gemm_ln = [&](const void* a_in, const void* W, int K, const void* bias, const void* ln_w,
+                                const void* ln_b) -> int {
+        const int S = ((C & 255) == 0 && C <= 1024) ? splitk_factor(h, rows, C, K) : 1;
+        if (S > 1) {
+            if (launch_gemm(h, a_in, rows, W, C, K, nullptr, h->ws_part, C, EPI_STORE_F32, st, 0, 128, h->vit_tiled, S)) return 1;
             DISPATCH_T(h, T, {
                 ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
                 if (kon(h, KC_LAYERNORM)) {
-                layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
-                    (const T*)h->ws_x, (const T*)L.ln1_w, (const T*)L.ln1_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                splitk_residual_ln_kernel<T><<<rows, C / 8, 0, st>>>(
+                    h->ws_part, S, static_cast<long long>(rows) * C, (const T*)bias, (T*)h->ws_x, (const T*)ln_w,
+                    (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps);
                 }
                 count_launch(h);
             })
+        } else {
+            if (launch_gemm(h, a_in, rows, W, C, K, bias, h->ws_x, C, EPI_RESIDUAL, st, -1, 0, h->vit_tiled)) return 1;
+            if (ln_w != nullptr) {
+                DISPATCH_T(h, T, {
+                    ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
+                    if (kon(h, KC_LAYERNORM)) {
+                    layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+                        (const T*)h->ws_x, (const T*)ln_w, (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                    }
+                    count_launch(h);
+                })
+            }
         }
+        return 0;
+    };
+    for (int l = 0; l < c.vit_layers; ++l) {
+        const VitLayer& L = h->vit[l];
         if (launch_gemm(h, h->ws_h, rows, L.wqkv, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, st, -1, 0, h->vit_tiled)) return 1;
         AttnArgs a{};
         a.q = h->ws_qkv;
@@ -470,17 +490,11 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
         a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
         if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
-        if (launch_gemm(h, h->ws_att, rows, L.wo, C, C, L.bo, h->ws_x, C, EPI_RESIDUAL, st, -1, 0, h->vit_tiled)) return 1;
-        DISPATCH_T(h, T, {
-            ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
-            if (kon(h, KC_LAYERNORM)) {
-            layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
-                (const T*)h->ws_x, (const T*)L.ln2_w, (const T*)L.ln2_b, (T*)h->ws_h, rows, C, c.vit_eps);
-            }
-            count_launch(h);
-        })
+        if (residual_gemm_ln(h->ws_att, L.wo, C, L.bo, L.ln2_w, L.ln2_b)) return 1;
         if (launch_gemm(h, h->ws_h, rows, L.w1, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, st, -1, 0, h->vit_tiled)) return 1;
-        if (launch_gemm(h, h->ws_mlp, rows, L.w2, C, F, L.b2, h->ws_x, C, EPI_RESIDUAL, st, -1, 0, h->vit_tiled)) return 1;
+        const bool last = l + 1 == c.vit_layers;
+        if (residual_gemm_ln(h->ws_mlp, L.w2, F, L.b2, last ? nullptr : h->vit[l + 1].ln1_w,
+                             last ? nullptr : h->vit[l + 1].ln1_b)) return 1;
     }
     DISPATCH_T(h, T, {
         ProfScope ps_kc_vit_finalize(h, KC_VIT_FINALIZE, st);
@@ -773,6 +787,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->ws_mlp = A(rows * F * e);
         h->ws_pooled = A(static_cast<size_t>(Bm) * C * e);
         h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
+        h->ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
     }
     // ---------------- projector
     if (c.proj_d_model > 0) {

@@ -34,6 +34,9 @@ struct GemmArgs {
     int nstage;  // smem ring depth
     int epi;     // EpiMode
     int tma_store;  // non-swapped T outputs with bn % 64 == 0: stage the tile in smem, write it with TMA
+    int split_k;    // > 1: blockIdx.z takes k-blocks [z*kb_per, (z+1)*kb_per) and writes an fp32 partial tile to
+                    // out + z*split_stride (EPI_STORE_F32, no bias); the consumer sums the partials in fixed order
+    long long split_stride;   // elements between partial outputs
     int cluster_n;  // CTAs per cluster along blockIdx.y (1, 2, 4 or 8): they share the A tile, each CTA loads
                     // 128/cluster_n of its rows and TMA-multicasts them to the whole cluster (L2 reads of A / cluster_n)
     int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
@@ -83,13 +86,14 @@ struct EpiCtx {
     const float* bias_s;   // non-swap: bias of this tile's columns in smem
     float bv;              // swap: bias of this thread's feature
     int a_row, b0, BN, lane_row;   // lane_row = row inside the 128-row tile
+    size_t out_off;                // split-K: element offset of this split's partial output
 };
 
 template <typename T, bool SWAP, int EPI, bool TMAST>
 __device__ __forceinline__ void epi_chunk(const EpiCtx& cx, int cbase, const uint32_t (&rb)[32], const uint4 (&xr)[4]) {
     const GemmArgs& args = *cx.args;
     T* out_t = reinterpret_cast<T*>(args.out);
-    float* out_f = reinterpret_cast<float*>(args.out);
+    float* out_f = reinterpret_cast<float*>(args.out) + cx.out_off;
     if constexpr (!SWAP) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -189,7 +193,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(dbg), static_cast<unsigned long long>(gtimer()));
     const int a0 = blockIdx.x * kGemmBM;  // first A row of this tile
     const int b0 = blockIdx.y * BN;       // first B row of this tile
-    const int num_kb = (args.K + kGemmBK - 1) / kGemmBK;
+    const int total_kb = (args.K + kGemmBK - 1) / kGemmBK;
+    const int kb_per = args.split_k > 1 ? (total_kb + args.split_k - 1) / args.split_k : total_kb;
+    const int kb_begin = args.split_k > 1 ? blockIdx.z * kb_per : 0;
+    const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
     const int CS = args.cluster_n;
     const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = static_cast<uint16_t>((1u << CS) - 1u);
@@ -235,17 +242,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int a_slice = kGemmBM / CS;
                 uint8_t* a_dst = smem_a + stage * A_BYTES + crank * a_slice * 128;
                 const bool a_is_tiled_w = args.w_tiled && args.swap;
-                const int ac0 = a_is_tiled_w ? 0 : kb * kGemmBK;
-                const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kb) * kGemmBM : a0) + crank * a_slice;
+                const int kg = kb_begin + kb;   // global k-block index
+                const int ac0 = a_is_tiled_w ? 0 : kg * kGemmBK;
+                const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kg) * kGemmBM : a0) + crank * a_slice;
                 if (CS > 1) tma_load_2d_mc(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, cmask, pol_a);
                 else tma_load_2d(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, pol_a);
                 if (!args.w_tiled || args.swap) {
-                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * kGemmBK, b0, pol_b);
+                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kg * kGemmBK, b0, pol_b);
                 } else {                  // B = tiled weights, BN rows = BN/128 whole tiles or a slice of one
                     const int nld = BN > kGemmBM ? BN / kGemmBM : 1;
                     for (int j = 0; j < nld; ++j)
                         tma_load_2d(smem_b + stage * B_BYTES + j * (kGemmBM * 128), &tmap_b, &full_bar[stage], 0,
-                                    ((b0 / kGemmBM + j) * args.w_kb + kb) * kGemmBM + (b0 % kGemmBM), pol_b);
+                                    ((b0 / kGemmBM + j) * args.w_kb + kg) * kGemmBM + (b0 % kGemmBM), pol_b);
                 }
             }
             __syncwarp();
@@ -323,6 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         EpiCtx cx;
         cx.args = &args; cx.stage = smem_a; cx.bias_s = bias_s; cx.bv = bv; cx.a_row = a_row; cx.b0 = b0; cx.BN = BN;
         cx.lane_row = lane_base + lane;
+        cx.out_off = args.split_k > 1 ? static_cast<size_t>(blockIdx.z) * static_cast<size_t>(args.split_stride) : 0;
         const int mode = (args.swap ? 8 : 0) | (args.tma_store ? 4 : 0) | epi;   // uniform: one branch per chunk
         auto process = [&](int c, const uint32_t (&rb)[32], const uint4 (&xr)[4]) {
             if (!a_ok) return;

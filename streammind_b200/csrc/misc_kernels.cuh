@@ -169,6 +169,78 @@ __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ 
     }
 }
 
+// Consumer of a split-K residual GEMM, fused with the LayerNorm that follows it:
+//   v = T(sum_z part[z][row][:] + bias)   (fixed order -> deterministic);  x[row] = T(x[row] + v);
+//   h[row] = LN(x[row]) * w + b           (skipped when w == nullptr: last layer)
+// One CTA per row, one thread per 8 contiguous elements (blockDim = C/8 <= 128): every thread issues all
+// of its partial-sum loads at once, so the kernel costs about one L2 round trip plus two block reductions.
+template <typename T>
+__global__ void __launch_bounds__(128) splitk_residual_ln_kernel(
+    const float* __restrict__ part, int nsplit, long long split_stride, const T* __restrict__ bias, T* __restrict__ x,
+    const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ h, int rows, int C, float eps) {
+    __shared__ float red[8];
+    const int row = blockIdx.x, c0 = threadIdx.x * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    T* xr = x + static_cast<long long>(row) * C;
+    const float* p = part + static_cast<long long>(row) * C + c0;
+    float4 pa[4], pb[4];
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+        if (z < nsplit) {
+            pa[z] = *reinterpret_cast<const float4*>(p + z * split_stride);
+            pb[z] = *reinterpret_cast<const float4*>(p + z * split_stride + 4);
+        }
+    }
+    const uint4 bu = *reinterpret_cast<const uint4*>(bias + c0);
+    const uint4 xu = *reinterpret_cast<const uint4*>(xr + c0);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+        if (z < nsplit) {
+            acc[0] += pa[z].x; acc[1] += pa[z].y; acc[2] += pa[z].z; acc[3] += pa[z].w;
+            acc[4] += pb[z].x; acc[5] += pb[z].y; acc[6] += pb[z].z; acc[7] += pb[z].w;
+        }
+    }
+    const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w}, xw[4] = {xu.x, xu.y, xu.z, xu.w};
+    float v[8];
+    uint32_t o[4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 bf = Cvt<T>::unpack2(bw[i]), xf = Cvt<T>::unpack2(xw[i]);
+        v[2 * i] = rnd<T>(xf.x + rnd<T>(acc[2 * i] + bf.x));
+        v[2 * i + 1] = rnd<T>(xf.y + rnd<T>(acc[2 * i + 1] + bf.y));
+        s += v[2 * i] + v[2 * i + 1];
+        o[i] = Cvt<T>::pack2(v[2 * i], v[2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(xr + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (w == nullptr) return;
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < nwarp; ++i) tot += red[i];
+    const float mean = tot / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+    sq = warp_sum(sq);
+    if (lane == 0) red[4 + warp] = sq;
+    __syncthreads();
+    float var = 0.f;
+    for (int i = 0; i < nwarp; ++i) var += red[4 + i];
+    const float r = rsqrtf(var / C + eps);
+    const uint4 wu = *reinterpret_cast<const uint4*>(w + c0);
+    const uint4 b2 = *reinterpret_cast<const uint4*>(b + c0);
+    const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, b2w[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 wf = Cvt<T>::unpack2(ww[i]), bf = Cvt<T>::unpack2(b2w[i]);
+        o[i] = Cvt<T>::pack2((v[2 * i] - mean) * r * wf.x + bf.x, (v[2 * i + 1] - mean) * r * wf.y + bf.y);
+    }
+    *reinterpret_cast<uint4*>(h + static_cast<long long>(row) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // feature_select('patch') + mean over patches: feats[f, p, :] = x[f*S + 1 + p, :] (CLS dropped,
 // clip_encoder.py:31-35); pooled[f, :] = T(mean_p feats[f, p, :]) (multimodal_projector/builder.py:405)
 template <typename T>
