@@ -413,6 +413,24 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
+    // One shared-memory carve-out for every kernel of the per-frame chain: an SM has to drain before it can
+    // change its L1/shared split, which serialises back-to-back launches (and defeats PDL overlap) when
+    // neighbouring kernels ask for different splits.
+    if (getenv("SMB_CARVEOUT") != nullptr) {
+        const int co = atoi(getenv("SMB_CARVEOUT")) > 0 ? atoi(getenv("SMB_CARVEOUT")) : cudaSharedmemCarveoutMaxShared;
+        auto set = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, co); };
+        CUDA_OK(h, set((const void*)gemm_tc_kernel<T>));
+        CUDA_OK(h, set((const void*)gemv_kernel<T, 1>));
+        CUDA_OK(h, set((const void*)gemv_kernel<T, 2>));
+        CUDA_OK(h, set((const void*)attention_kernel<T, 64>));
+        CUDA_OK(h, set((const void*)attention_kernel<T, 128>));
+        CUDA_OK(h, set((const void*)layernorm_kernel<T>));
+        CUDA_OK(h, set((const void*)splitk_residual_ln_kernel<T>));
+        CUDA_OK(h, set((const void*)vit_embed_ln_kernel<T, 32>));
+        CUDA_OK(h, set((const void*)im2col_kernel<T>));
+        CUDA_OK(h, set((const void*)vit_finalize_kernel<T>));
+        CUDA_OK(h, set((const void*)mamba_scan_step_kernel<T>));
+    }
     return 0;
 }
 
