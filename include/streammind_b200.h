@@ -100,6 +100,19 @@ int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream
 int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
                   float* logits_out, float* logits_host, void* stream);
 
+/* Pipelined form of sm_frame_step for throughput streams.  The vision tower of the call runs on an internal
+ * high-priority stream; projector + gate run on a second internal low-priority stream, so the gate of frame t
+ * overlaps the tower of frame t+1 (the tower is tensor/latency-bound and leaves HBM mostly idle, the gate is
+ * HBM-bound).  `pixels` must be ready on
+ * `stream` at call time.  Outputs are NOT ordered on `stream`: *ticket identifies the call, and
+ * sm_frame_wait(ticket, stream, block_host) makes `stream` wait for (stream != NULL or block_host == 0) and/or
+ * blocks the host until (block_host != 0) that call's outputs -- including the pinned-host logits -- are
+ * complete.  At most 4 tickets are in flight (the 5th submit blocks the host on the oldest).  Results are
+ * identical to sm_frame_step (same kernels and arithmetic; stream state advances in ticket order). */
+int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
+                    float* logits_out, float* logits_host, void* stream, long long* ticket);
+int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host);
+
 /* embed_tokens (videollama2_arch.py:967,977): ids [n] int32 device -> out [n, hidden]. */
 int sm_embed_tokens(sm_handle* h, const int32_t* ids, int n, void* out, void* stream);
 
@@ -143,6 +156,12 @@ const char* sm_profile_class_name(int cls);
  * sm_profile_class_name); outputs are then meaningless, timings of the remaining kernels are exact.
  * bench.py uses it to time one kernel class at a time inside the same captured step. */
 int sm_debug_kernel_filter(sm_handle* h, unsigned mask);
+
+/* Debug / measurement: per-op trace of the persistent vision-tower kernel (csrc/vit_mega.cuh).  device_buf
+ * (NULL = off) receives 4 int64 slots per op of the plan for chunk size B: max over CTAs of the globaltimer
+ * when the op's grid barrier was passed, when its work was done, and when the CTA arrived.  n_ops / types
+ * (optional) return the op list of that plan (MegaOpType values). */
+int sm_debug_mega_trace(sm_handle* h, long long* device_buf, int B, int* n_ops, int* types, int max_ops);
 
 /* Launch accounting: number of this library's kernel launches (graph-replayed kernels included) since
  * the last call with reset != 0. */

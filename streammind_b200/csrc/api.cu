@@ -22,7 +22,9 @@
 #include "attention.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
+#include "gemv_tma.cuh"
 #include "misc_kernels.cuh"
+#include "vit_mega.cuh"
 
 using namespace smb;
 
@@ -68,6 +70,8 @@ struct sm_handle {
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
     bool use_pdl = true;
+    bool gemv_tma = false;            // weight-streaming GEMVs through the bulk-copy ring (gemv_tma.cuh, experimental)
+    int gemv_grid_cap = 0;            // > 0: GEMVs use at most this many CTAs (background gate)
     bool vit_tiled = true;            // ViT GEMM weights are stored pre-tiled (gemm_tc.cuh GemmArgs::w_tiled)
     unsigned kfilter = 0xFFFFFFFFu;   // debug: kernel classes that are actually launched (bench.py per-class timing)
     long long* gemm_dbg = nullptr;   // device buffer for sm_test_gemm_trace
@@ -84,6 +88,12 @@ struct sm_handle {
     void *ws_im = nullptr, *ws_pemb = nullptr, *ws_x = nullptr, *ws_h = nullptr, *ws_qkv = nullptr, *ws_att = nullptr,
          *ws_mlp = nullptr, *ws_pooled = nullptr, *ws_pixels = nullptr, *ws_feats = nullptr;
     float* ws_part = nullptr;   // split-K partial sums [4][rows][C] fp32
+    // persistent vision-tower kernel (vit_mega.cuh): one op list + tensor-map array per chunk size B
+    struct MegaPlan { MegaOp* d_ops = nullptr; CUtensorMap* d_maps = nullptr; int n_ops = 0; std::vector<int> types; };
+    std::map<int, MegaPlan> mega_plans;
+    unsigned int* mega_sync = nullptr;
+    long long* mega_dbg = nullptr;
+    int mega_mode = 2;   // 0 = one kernel per op (round-1 path), 1 = persistent kernel, attention as separate launches, 2 = one launch
     // ---- projector
     int d_inner = 0, dt_rank = 0;
     void *pj_pre_w = nullptr, *pj_pre_b = nullptr, *pj_norm_w = nullptr, *pj_norm_b = nullptr, *pj_in = nullptr,
@@ -107,6 +117,13 @@ struct sm_handle {
     int *d_pos = nullptr, *d_tok = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_done = nullptr, *d_stop = nullptr;
     int kv_len = 0;
     int dec_splits = 16;
+    // ---- pipelined frame path (sm_frame_submit): tower on vit_stream, projector + gate on gate_stream
+    bool pipe_init = false;
+    cudaStream_t vit_stream = nullptr, gate_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_vit[2] = {nullptr, nullptr}, ev_gate[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long ticket = 0;
+    int bg_grid = 0;                   // > 0: projector/gate GEMVs of the pipelined path on this many CTAs (experiment; measured slower)
+    void* ws_pooled2[2] = {nullptr, nullptr};
     // ---- graphs
     std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
     std::map<int, long long> frame_graph_launches;
@@ -249,6 +266,10 @@ GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi) {
     if (tokens <= 64 && !residual) return {1, std::max(16, (tokens + 15) / 16 * 16)};
     if (feats % 16 != 0) return {1, std::min(256, std::max(16, (tokens + 15) / 16 * 16))};
     const int mt = (tokens + 127) / 128;
+    // measured (profiles/r01_gemm_plan_sweep.md, one streaming frame = 577 tokens): the wide fc1 GEMM is fastest with
+    // weight rows on the MMA lanes and 160 tokens per tile (4 x 32 = 128 CTAs, no 2-byte-strided stores: TMA store)
+    static const int fc1_swap = getenv("SMB_FC1_SWAP") ? atoi(getenv("SMB_FC1_SWAP")) : 1;
+    if (fc1_swap && !residual && mt == 5 && feats >= 4096 && feats % 128 == 0) return {1, 160};
     for (int bn : {256, 128, 64, 32})
         if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / 2) return {0, bn};
     return {0, std::min(32, feats)};
@@ -347,12 +368,35 @@ int splitk_factor(const sm_handle* h, int tokens, int feats, int K) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMV
+// bulk-copy ring + tensor-pipe kernel (gemv_tma.cuh)
+template <typename T>
+int launch_gemv_tma_t(sm_handle* h, const GemvArgs& a, int nmat, cudaStream_t st) {
+    const int G = h->gemv_grid_cap > 0 ? std::min(h->gemv_grid_cap, h->num_sms) : h->num_sms;
+    const int R = kGtTileRows;
+    const int per_cta = (a.N + G * kGtMaxBlockRows - 1) / (G * kGtMaxBlockRows);          // row blocks per CTA
+    int rpb = ((a.N + G * per_cta - 1) / (G * per_cta) + R - 1) / R * R;
+    rpb = std::max(R, std::min(rpb, kGtMaxBlockRows));
+    const int nblocks = (a.N + rpb - 1) / rpb;
+    const int grid = std::min(nblocks, G);
+    const int smem = gemv_tma_smem_bytes(a.K, nmat);
+    {
+        ProfScope ps(h, KC_GEMV, st);
+        if (nmat == 2) CUDA_OK(h, launch_pdl(h, gemv_tma_kernel<T, 2>, dim3(grid), dim3(kGtThreads), smem, st, a, rpb, nblocks));
+        else CUDA_OK(h, launch_pdl(h, gemv_tma_kernel<T, 1>, dim3(grid), dim3(kGtThreads), smem, st, a, rpb, nblocks));
+    }
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
 template <typename T>
 int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (a.K % 8 != 0) return fail(h, "gemv: K=%d must be a multiple of 8", a.K);
     if (!kon(h, KC_GEMV)) return 0;
+    if (h->gemv_tma && gemv_tma_supported(a.K)) return launch_gemv_tma_t<T>(h, a, nmat, st);
     a.seg_len = 1024;
-    int grid = std::min(a.N, 2 * h->num_sms);
+    static const int grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;   // experiment: background-sized grids
+    int grid = std::min(a.N, grid_cap > 0 ? grid_cap : 2 * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;
     grid = (a.N + rows_per_cta - 1) / rows_per_cta;
     const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
@@ -409,7 +453,10 @@ int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cu
 template <typename T>
 int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(vit_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
@@ -434,10 +481,182 @@ int init_kernel_attrs_t(sm_handle* h) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ persistent ViT
+bool mega_supported(const sm_handle* h) {
+    const sm_config& c = h->cfg;
+    return h->mega_mode > 0 && h->vit_tiled && (c.vit_hidden & 255) == 0 && c.vit_hidden <= 1024 && c.vit_ffn % 128 == 0 &&
+           c.vit_hidden / c.vit_heads == 64;
+}
+
+// tile width of a GEMM op: cost model from the issue-rate microbenchmark (profiles/r01_ncu_full_summary.md):
+// a K=64 slab costs ~150 ns at N=128 (4 MMAs + commit) and ~260 ns at N=256; the epilogue of the last tile is exposed.
+int mega_pick_bn(int rows, int feats, int K, int G) {
+    if (feats % 256 != 0) return 128;
+    const int mt = (rows + 127) / 128, kb = (K + 63) / 64;
+    const double c128 = std::ceil(double(mt) * (feats / 128) / G) * kb * 0.150 + 1.2;
+    const double c256 = std::ceil(double(mt) * (feats / 256) / G) * kb * 0.260 + 2.4;
+    static const int force = getenv("SMB_MEGA_BN") ? atoi(getenv("SMB_MEGA_BN")) : 0;
+    if (force == 128 || force == 256) return force;
+    return c256 < c128 ? 256 : 128;
+}
+
+int mega_build_plan(sm_handle* h, int B) {
+    const sm_config& c = h->cfg;
+    const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn, G = h->num_sms;
+    std::vector<CUtensorMap> maps;
+    std::vector<MegaOp> ops;
+    auto add_map = [&](const void* ptr, int nrows, int K) -> int {
+        const CUtensorMap* m = get_tmap(h, ptr, nrows, K, kGemmBM);
+        if (!m) return -1;
+        maps.push_back(*m);
+        return static_cast<int>(maps.size()) - 1;
+    };
+    auto tiled_rows = [](int feats, int K) { return ((feats + 127) / 128) * ((K + 63) / 64) * 128; };
+    const int m_im = add_map(h->ws_im, B * P, h->kpad), m_h = add_map(h->ws_h, rows, C), m_att = add_map(h->ws_att, rows, C),
+              m_mlp = add_map(h->ws_mlp, rows, F);
+    if (m_im < 0 || m_h < 0 || m_att < 0 || m_mlp < 0) return 1;
+    auto gemm = [&](int map_a, const void* w, int M, int N, int K, const void* bias, void* out, int ldo, int epi, int split) -> int {
+        MegaOp o{};
+        o.type = MOP_GEMM; o.map_a = map_a; o.map_b = add_map(w, tiled_rows(N, K), kGemmBK);
+        if (o.map_b < 0) return 1;
+        o.M = M; o.N = N; o.K = K; o.split_k = split; o.epi = epi; o.w_kb = (K + 63) / 64; o.w = w; o.bias = bias;
+        o.bn = split > 1 || epi == EPI_STORE_F32 ? 128 : mega_pick_bn(M, N, K, G);
+        o.out = out; o.ldo = ldo; o.split_stride = static_cast<long long>(M) * N;
+        ops.push_back(o);
+        return 0;
+    };
+    auto splitk_ln = [&](int nsplit, const void* bias, const void* ln_w, const void* ln_b) {
+        MegaOp o{};
+        o.type = MOP_SPLITK_LN; o.part = h->ws_part; o.nsplit = nsplit; o.part_stride = static_cast<long long>(rows) * C;
+        o.rbias = bias; o.x = h->ws_x; o.ln_w = ln_w; o.ln_b = ln_b; o.h = h->ws_h; o.rows = rows; o.C = C; o.eps = c.vit_eps;
+        ops.push_back(o);
+    };
+    {
+        MegaOp o{};
+        o.type = MOP_IM2COL; o.pixels = h->ws_pixels; o.im = h->ws_im; o.img = c.vit_image; o.patch = c.vit_patch;
+        o.kpad = h->kpad; o.batch = B;
+        ops.push_back(o);
+    }
+    if (gemm(m_im, h->vit_wpatch, B * P, C, h->kpad, nullptr, h->ws_pemb, C, EPI_STORE, 1)) return 1;
+    {
+        MegaOp o{};
+        o.type = MOP_EMBED_LN; o.pemb = h->ws_pemb; o.cls = h->vit_cls; o.pos = h->vit_pos; o.pre_w = h->vit_pre_w;
+        o.pre_b = h->vit_pre_b; o.ln_w = h->vit[0].ln1_w; o.ln_b = h->vit[0].ln1_b; o.x = h->ws_x; o.h = h->ws_h;
+        o.rows = rows; o.C = C; o.S = S; o.eps = c.vit_eps;
+        ops.push_back(o);
+    }
+    const int D = C / c.vit_heads;
+    for (int l = 0; l < c.vit_layers; ++l) {
+        const VitLayer& L = h->vit[l];
+        if (gemm(m_h, L.wqkv, rows, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, 1)) return 1;
+        {
+            MegaOp o{};
+            o.type = MOP_ATTN; o.heads = c.vit_heads; o.batch = B;
+            AttnArgs& a = o.attn;
+            a.q = h->ws_qkv;
+            a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
+            a.v = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(2 * C) * 2;
+            a.o = h->ws_att;
+            a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
+            a.q_ss = a.k_ss = a.v_ss = 3 * C;
+            a.k_hs = a.v_hs = D;
+            a.o_bs = static_cast<long long>(S) * C;
+            a.o_ss = C;
+            a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
+            a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+            ops.push_back(o);
+        }
+        const int s1 = splitk_factor(h, rows, C, C), s2 = splitk_factor(h, rows, C, F);
+        if (gemm(m_att, L.wo, rows, C, C, nullptr, h->ws_part, C, EPI_STORE_F32, s1)) return 1;
+        splitk_ln(s1, L.bo, L.ln2_w, L.ln2_b);
+        if (gemm(m_h, L.w1, rows, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, 1)) return 1;
+        if (gemm(m_mlp, L.w2, rows, C, F, nullptr, h->ws_part, C, EPI_STORE_F32, s2)) return 1;
+        const bool last = l + 1 == c.vit_layers;
+        splitk_ln(s2, L.b2, last ? nullptr : h->vit[l + 1].ln1_w, last ? nullptr : h->vit[l + 1].ln1_b);
+    }
+    {
+        MegaOp o{};
+        o.type = MOP_POOL; o.x = h->ws_x; o.pooled = h->ws_pooled; o.C = C; o.S = S; o.batch = B;
+        ops.push_back(o);
+    }
+    sm_handle::MegaPlan plan;
+    plan.n_ops = static_cast<int>(ops.size());
+    for (auto& o : ops) plan.types.push_back(o.type);
+    plan.d_ops = static_cast<MegaOp*>(dalloc(h, ops.size() * sizeof(MegaOp)));
+    plan.d_maps = static_cast<CUtensorMap*>(dalloc(h, maps.size() * sizeof(CUtensorMap)));
+    if (!plan.d_ops || !plan.d_maps) return fail(h, "mega_build_plan: out of device memory");
+    CUDA_OK(h, cudaMemcpy(plan.d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemcpy(plan.d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    h->mega_plans[B] = plan;
+    return 0;
+}
+
+template <typename T>
+int mega_launch_t(sm_handle* h, const sm_handle::MegaPlan& plan, int op_begin, int op_end, cudaStream_t st) {
+    MegaParams p{};
+    p.ops = plan.d_ops; p.op_begin = op_begin; p.op_end = op_end; p.maps = plan.d_maps; p.sync = h->mega_sync; p.dbg = h->mega_dbg;
+    CUDA_OK(h, launch_ex(h, vit_mega_kernel<T>, dim3(h->num_sms), dim3(kGemmThreads), mega_smem_bytes(), st, 1, p));
+    count_launch(h);
+    return 0;
+}
+
+int run_vit_mega(sm_handle* h, int B, cudaStream_t st) {
+    auto it = h->mega_plans.find(B);
+    if (it == h->mega_plans.end()) {
+        if (h->capturing) return fail(h, "run_vit_mega: plan for B=%d must be built outside graph capture", B);
+        if (mega_build_plan(h, B)) return 1;
+        it = h->mega_plans.find(B);
+    }
+    const sm_handle::MegaPlan& plan = it->second;
+    auto launch = [&](int b, int e) -> int {
+        if (b >= e) return 0;
+        DISPATCH_T(h, T, return mega_launch_t<T>(h, plan, b, e, st);)
+    };
+    if (h->mega_mode >= 2) return launch(0, plan.n_ops);
+    // mode 1: attention ops run as the stand-alone kernel between persistent ranges
+    const sm_config& c = h->cfg;
+    const int C = c.vit_hidden, S = h->S, D = C / c.vit_heads;
+    int begin = 0;
+    for (int i = 0; i < plan.n_ops; ++i) {
+        if (plan.types[i] != MOP_ATTN) continue;
+        if (launch(begin, i)) return 1;
+        AttnArgs a{};
+        a.q = h->ws_qkv;
+        a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
+        a.v = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(2 * C) * 2;
+        a.o = h->ws_att;
+        a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
+        a.q_ss = a.k_ss = a.v_ss = 3 * C;
+        a.k_hs = a.v_hs = D;
+        a.o_bs = static_cast<long long>(S) * C;
+        a.o_ss = C;
+        a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
+        a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+        if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
+        begin = i + 1;
+    }
+    return launch(begin, plan.n_ops);
+}
+
 // ------------------------------------------------------------------------------------------ sub-model runners
 int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, cudaStream_t st) {
     const sm_config& c = h->cfg;
     const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn;
+    if (mega_supported(h) && h->kfilter == 0xFFFFFFFFu && !h->profiling) {
+        const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
+        if (pixels != h->ws_pixels) CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, cudaMemcpyDeviceToDevice, st));
+        if (run_vit_mega(h, B, st)) return 1;
+        if (feats_out != nullptr) {
+            DISPATCH_T(h, T, {
+                vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C);
+                count_launch(h);
+            })
+        }
+        if (pooled_out != nullptr && pooled_out != h->ws_pooled)
+            CUDA_OK(h, cudaMemcpyAsync(pooled_out, h->ws_pooled, static_cast<size_t>(B) * C * h->esz, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(h, cudaGetLastError());
+        return 0;
+    }
     DISPATCH_T(h, T, {
         const long long n = static_cast<long long>(B) * P * h->kpad;
         ProfScope ps_kc_im2col(h, KC_IM2COL, st);
@@ -686,6 +905,23 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     return 0;
 }
 
+// Captures `body` (which must already have run once on a real stream, so tensor maps / plans exist) into a graph.
+template <typename F>
+int capture_graph(sm_handle* h, F&& body, cudaGraphExec_t* out, long long* n_launches, const char* what) {
+    cudaGraph_t g;
+    h->capturing = true;
+    h->captured_launches = 0;
+    CUDA_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(h->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+    h->capturing = false;
+    if (rc || ce != cudaSuccess) return fail(h, "%s: graph capture failed: %s", what, cudaGetErrorString(ce));
+    CUDA_OK(h, cudaGraphInstantiate(out, g, 0));
+    cudaGraphDestroy(g);
+    *n_launches = h->captured_launches;
+    return 0;
+}
+
 }  // namespace
 
 // =========================================================================================== C ABI
@@ -719,6 +955,10 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
+    // experimental bulk-copy + mma.sync GEMV (gemv_tma.cuh): not faster than gemv.cuh on B200 (both sit at the same
+    // ~48 GB/s-per-SM bulk/HBM limit) and 1 fp16 ulp off the oracle on the gate logits -> off unless asked for
+    h->gemv_tma = getenv("SMB_GEMV_TMA") ? atoi(getenv("SMB_GEMV_TMA")) != 0 : false;
+    h->gemv_grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;
     if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(nullptr, "sm_create: cudaStreamCreate failed");
@@ -804,8 +1044,12 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->ws_att = A(rows * C * e);
         h->ws_mlp = A(rows * F * e);
         h->ws_pooled = A(static_cast<size_t>(Bm) * C * e);
+        h->ws_pooled2[0] = A(static_cast<size_t>(Bm) * C * e);
+        h->ws_pooled2[1] = A(static_cast<size_t>(Bm) * C * e);
         h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
         h->ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
+        h->mega_sync = static_cast<unsigned int*>(A(256));
+        h->mega_mode = getenv("SMB_MEGA") ? atoi(getenv("SMB_MEGA")) : 0;
     }
     // ---------------- projector
     if (c.proj_d_model > 0) {
@@ -925,6 +1169,11 @@ void sm_destroy(sm_handle* h) {
     for (auto& g : h->frame_graphs) cudaGraphExecDestroy(g.second);
     if (h->decode_graph) cudaGraphExecDestroy(h->decode_graph);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->vit_stream) cudaStreamDestroy(h->vit_stream);
+    if (h->gate_stream) cudaStreamDestroy(h->gate_stream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    for (auto e : h->ev_vit) if (e) cudaEventDestroy(e);
+    for (auto e : h->ev_gate) if (e) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -991,6 +1240,10 @@ int sm_finalize_weights(sm_handle* h) {
 int sm_stream_reset(sm_handle* h) {
     if (!h) return 1;
     cudaSetDevice(h->device);
+    if (h->pipe_init) {
+        CUDA_OK(h, cudaStreamSynchronize(h->vit_stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->gate_stream));
+    }
     if (h->pj_conv_state) {
         CUDA_OK(h, cudaMemset(h->pj_conv_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_conv * h->esz));
         CUDA_OK(h, cudaMemset(h->pj_ssm_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_state * sizeof(float)));
@@ -1090,6 +1343,93 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
     if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, st));
     if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
+                    float* logits_out, float* logits_host, void* stream, long long* ticket_out) {
+    if (!h || h->cfg.vit_layers <= 0 || h->cfg.proj_d_model <= 0 || h->cfg.gate_layers <= 0)
+        return fail(h, "sm_frame_submit: needs vision tower + projector + gate");
+    if (B < 1 || B > h->cfg.max_frames) return fail(h, "sm_frame_submit: B=%d outside [1, max_frames=%d]", B, h->cfg.max_frames);
+    cudaSetDevice(h->device);
+    const sm_config& c = h->cfg;
+    if (!h->pipe_init) {
+        int lo = 0, hi = 0;
+        CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
+        CUDA_OK(h, cudaStreamCreateWithPriority(&h->vit_stream, cudaStreamNonBlocking, hi));
+        CUDA_OK(h, cudaStreamCreateWithPriority(&h->gate_stream, cudaStreamNonBlocking, lo));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        for (auto& e : h->ev_vit) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : h->ev_gate) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->bg_grid = getenv("SMB_BG_GRID") ? atoi(getenv("SMB_BG_GRID")) : 0;
+        h->pipe_init = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_stream, gs = h->gate_stream;
+    const long long tk = h->ticket;
+    const int slot = static_cast<int>(tk & 1), ring = static_cast<int>(tk & 3);
+    if (tk >= 4) CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));           // at most 4 frames in flight
+    CUDA_OK(h, cudaEventRecord(h->ev_in, st));
+    CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
+    if (tk >= 2) CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_gate[(tk - 2) & 3], 0));   // pooled[slot] has been consumed
+    const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
+    CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, vs));
+    const bool want_feats = feats_out != nullptr;
+    void* pooled = h->ws_pooled2[slot];
+    auto vit_body = [&](cudaStream_t s) -> int { return run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, pooled, s); };
+    auto gate_body = [&](cudaStream_t s) -> int {
+        const int saved_cap = h->gemv_grid_cap;
+        const bool saved_tma = h->gemv_tma;
+        if (h->bg_grid > 0) { h->gemv_grid_cap = h->bg_grid; h->gemv_tma = true; }   // "background" gate experiment
+        int rc = 0;
+        for (int i = 0; i < B && !rc; ++i) {
+            char* tok = static_cast<char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
+            rc = run_projector(h, static_cast<char*>(pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, s);
+            if (!rc) rc = run_gate(h, tok, h->gt_logits + 2 * i, s);
+        }
+        h->gemv_grid_cap = saved_cap;
+        h->gemv_tma = saved_tma;
+        return rc;
+    };
+    auto run_part = [&](int key, cudaStream_t s, auto&& body, const char* what) -> int {
+        if (!c.use_graphs) return body(s);
+        auto it = h->frame_graphs.find(key);
+        if (it == h->frame_graphs.end()) {
+            if (body(s)) return 1;                       // real run: produces this call's outputs
+            CUDA_OK(h, cudaStreamSynchronize(s));
+            cudaGraphExec_t ge;
+            long long n = 0;
+            if (capture_graph(h, body, &ge, &n, what)) return 1;
+            h->frame_graphs[key] = ge;
+            h->frame_graph_launches[key] = n;
+        } else {
+            CUDA_OK(h, cudaGraphLaunch(it->second, s));
+            h->launches += h->frame_graph_launches[key];
+        }
+        return 0;
+    };
+    const int kf = static_cast<int>((h->kfilter & 0xFFFFu) << 12);
+    if (run_part(B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (slot << 10) | kf, vs, vit_body, "sm_frame_submit(tower)")) return 1;
+    if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, vs));
+    CUDA_OK(h, cudaEventRecord(h->ev_vit[slot], vs));
+    CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[slot], 0));
+    if (run_part(B | (1 << 9) | (1 << 11) | (slot << 10) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
+    if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, gs));
+    if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, gs));
+    if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, gs));
+    CUDA_OK(h, cudaEventRecord(h->ev_gate[ring], gs));
+    if (ticket_out) *ticket_out = tk;
+    h->ticket = tk + 1;
+    return 0;
+}
+
+int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host) {
+    if (!h || !h->pipe_init) return fail(h, "sm_frame_wait: nothing submitted");
+    if (ticket < 0 || ticket >= h->ticket || ticket + 4 < h->ticket)
+        return fail(h, "sm_frame_wait: ticket %lld is not in flight (next ticket %lld, ring of 4)", ticket, h->ticket);
+    cudaSetDevice(h->device);
+    cudaEvent_t ev = h->ev_gate[ticket & 3];
+    if (stream != nullptr || !block_host) CUDA_OK(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
+    if (block_host) CUDA_OK(h, cudaEventSynchronize(ev));
     return 0;
 }
 
@@ -1236,6 +1576,16 @@ int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, in
 int sm_test_gemm_trace(sm_handle* h, long long* device_buf) {
     if (!h) return 1;
     h->gemm_dbg = device_buf;
+    return 0;
+}
+
+int sm_debug_mega_trace(sm_handle* h, long long* device_buf, int B, int* n_ops, int* types, int max_ops) {
+    if (!h) return 1;
+    h->mega_dbg = device_buf;
+    auto it = h->mega_plans.find(B);
+    if (n_ops) *n_ops = it == h->mega_plans.end() ? 0 : it->second.n_ops;
+    if (types && it != h->mega_plans.end())
+        for (int i = 0; i < it->second.n_ops && i < max_ops; ++i) types[i] = it->second.types[i];
     return 0;
 }
 

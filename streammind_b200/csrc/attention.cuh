@@ -62,6 +62,12 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uin
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2^-inf = +0, rel. error 2^-22
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 constexpr int kAttnBQ = 64;   // query rows per CTA (4 warps x 16 per key group)
 constexpr int kAttnBK = 64;   // keys per pipeline stage
 constexpr int kAttnGroups = 2;  // key groups per CTA: group g walks key tiles g, g+2, ... (halves the serial chain)
@@ -90,17 +96,20 @@ __device__ __forceinline__ void attn_load_tile(uint8_t* smem_tile, const T* base
     }
 }
 
+// Barrier ids used by the body: 1, 2 = key groups; kAttnBarAll = all kAttnThreads threads of the work item
+// (bar.sync id, count -- so the body also runs on a 256-thread subset of a larger CTA: vit_mega.cuh).
+constexpr int kAttnBarAll = 3;
+
+// One work item = 64 query rows (tile qt) of head h of batch item b; tid in [0, kAttnThreads).
 template <typename T, int D>
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs a) {
-    extern __shared__ __align__(128) uint8_t attn_smem[];
+__device__ __forceinline__ void attention_body(const AttnArgs& a, int qt, int h, int b, uint8_t* attn_smem, int tid) {
     constexpr int TILE = kAttnBK * D * 2;
-    const int tid = threadIdx.x, grp = tid / kAttnGroupThreads, gtid = tid % kAttnGroupThreads;
+    const int grp = tid / kAttnGroupThreads, gtid = tid % kAttnGroupThreads;
     const int warp = gtid >> 5, lane = tid & 31;
     uint8_t* sQ = attn_smem;
     uint8_t* sK = sQ + kAttnBQ * D * 2 + grp * 4 * TILE;   // 2 stages
     uint8_t* sV = sK + 2 * TILE;                            // 2 stages
-    const int q0 = blockIdx.x * kAttnBQ;
-    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * kAttnBQ;
     const int hk = h / a.group;
     const T* qp = reinterpret_cast<const T*>(a.q) + b * a.q_bs + h * D;
     const T* kp = reinterpret_cast<const T*>(a.k) + b * a.k_bs + hk * a.k_hs;
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
     }
     cp_async_commit();
     cp_async_wait<0>();
-    __syncthreads();
+    named_bar_sync(kAttnBarAll, kAttnThreads);
 
     constexpr int KD = D / 16;   // k-steps over the head dim for QK^T
     constexpr int NB = kAttnBK / 8;  // 8-wide key blocks per stage
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
     uint32_t qf[KD][4];
     const int g = lane >> 2, t = lane & 3;
     const int qrow_a = q0 + warp * 16 + g;  // rows owned: qrow_a and qrow_a + 8
+    const bool warp_active = q0 + warp * 16 < a.q_len;   // warps whose 16 rows are all padding only load and sync
 #pragma unroll
     for (int kk = 0; kk < KD; ++kk) {
         const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -146,6 +156,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
         cp_async_commit();
         const uint8_t* tK = sK + st * TILE;
         const uint8_t* tV = sV + st * TILE;
+        if (warp_active) {
         // ---- S = Q K^T  (16 x 64 per warp)
         float s[NB][4];
 #pragma unroll
@@ -162,38 +173,51 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
                 mma16816<T>(s[2 * nb2 + 1], qf[kk], bf[2], bf[3]);
             }
         }
-        // ---- mask + online softmax (rows g and g+8; 4 lanes share a row)
+        // ---- mask + online softmax (rows g and g+8; 4 lanes share a row).  Scores stay unscaled: the scale is
+        // folded into the exponent (one FFMA per element), and only tiles that need it are masked.
         const int kbase = it * kAttnBK;
+        const bool need_mask = a.causal || (kbase + kAttnBK > kv_end);
         float mx[2] = {-INFINITY, -INFINITY};
+        if (need_mask) {
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
+            for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = kbase + nb * 8 + 2 * t + (e & 1);
-                const int qrow = qrow_a + (e >> 1) * 8;
-                bool ok = key < kv_end;
-                if (a.causal) ok = ok && (key <= a.q_pos0 + qrow);
-                const float v = ok ? s[nb][e] * a.scale_log2e : -INFINITY;
-                s[nb][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                for (int e = 0; e < 4; ++e) {
+                    const int key = kbase + nb * 8 + 2 * t + (e & 1);
+                    const int qrow = qrow_a + (e >> 1) * 8;
+                    bool ok = key < kv_end;
+                    if (a.causal) ok = ok && (key <= a.q_pos0 + qrow);
+                    const float v = ok ? s[nb][e] : -INFINITY;
+                    s[nb][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
             }
         }
-        float corr[2], msafe[2];
+        float corr[2], nmsafe[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float mnew = fmaxf(m_run[r], mx[r]);
-            msafe[r] = (mnew == -INFINITY) ? 0.f : mnew;
-            corr[r] = exp2f(m_run[r] - msafe[r]);   // m_run = -inf -> 0
+            const float mnew = fmaxf(m_run[r], mx[r] * a.scale_log2e);   // running max in scaled (log2) units
+            const float msafe = (mnew == -INFINITY) ? 0.f : mnew;
+            corr[r] = ex2_approx(m_run[r] - msafe);   // m_run = -inf -> 0
+            nmsafe[r] = -msafe;
             m_run[r] = mnew;
         }
         float rs[2] = {0.f, 0.f};
         uint32_t pf[NB / 2][4];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-            const float p0 = exp2f(s[nb][0] - msafe[0]), p1 = exp2f(s[nb][1] - msafe[0]);
-            const float p2 = exp2f(s[nb][2] - msafe[1]), p3 = exp2f(s[nb][3] - msafe[1]);
+            const float p0 = ex2_approx(fmaf(s[nb][0], a.scale_log2e, nmsafe[0]));
+            const float p1 = ex2_approx(fmaf(s[nb][1], a.scale_log2e, nmsafe[0]));
+            const float p2 = ex2_approx(fmaf(s[nb][2], a.scale_log2e, nmsafe[1]));
+            const float p3 = ex2_approx(fmaf(s[nb][3], a.scale_log2e, nmsafe[1]));
             // the row sum uses the T-rounded probabilities that actually multiply V
             const uint32_t lo = Cvt<T>::pack2(p0, p1), hi = Cvt<T>::pack2(p2, p3);
             const float2 flo = Cvt<T>::unpack2(lo), fhi = Cvt<T>::unpack2(hi);
@@ -204,10 +228,12 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+        if (__any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f)) {   // the running max moved somewhere in the warp
 #pragma unroll
-        for (int i = 0; i < OD; ++i) {
-            o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
-            o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+            for (int i = 0; i < OD; ++i) {
+                o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+                o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+            }
         }
         // ---- O += P V
 #pragma unroll
@@ -222,6 +248,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
                 mma16816<T>(o_acc[2 * nb2 + 1], pf[kk], bf[2], bf[3]);
             }
         }
+        }   // warp_active
         cp_async_wait<0>();                       // next tile landed (issued before this tile's math)
         named_bar_sync(1 + grp, kAttnGroupThreads);   // group-local: everyone is done with stage st
         st ^= 1;
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
-    __syncthreads();                                // all key tiles consumed: stage memory is free
+    named_bar_sync(kAttnBarAll, kAttnThreads);      // all key tiles consumed: stage memory is free
     float* mb = reinterpret_cast<float*>(attn_smem + kAttnBQ * D * 2) + gtid * (OD * 4 + 4);
     if (grp == 1) {
 #pragma unroll
@@ -243,15 +270,15 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
         mb[OD * 4 + 0] = m_run[0]; mb[OD * 4 + 1] = m_run[1];
         mb[OD * 4 + 2] = l_run[0]; mb[OD * 4 + 3] = l_run[1];
     }
-    __syncthreads();
-    if (grp != 0) return;
+    named_bar_sync(kAttnBarAll, kAttnThreads);
+    if (grp == 0) {
     float sc0[2], sc1[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const float m1 = mb[OD * 4 + r], l1 = mb[OD * 4 + 2 + r];
         const float mm = fmaxf(m_run[r], m1);
-        sc0[r] = m_run[r] == -INFINITY ? 0.f : exp2f(m_run[r] - mm);
-        sc1[r] = m1 == -INFINITY ? 0.f : exp2f(m1 - mm);
+        sc0[r] = m_run[r] == -INFINITY ? 0.f : ex2_approx(m_run[r] - mm);
+        sc1[r] = m1 == -INFINITY ? 0.f : ex2_approx(m1 - mm);
         l_run[r] = l_run[r] * sc0[r] + l1 * sc1[r];
     }
     T* op = reinterpret_cast<T*>(a.o) + b * a.o_bs + h * D;
@@ -268,6 +295,22 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs 
             }
         }
     }
+    }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs a) {
+    extern __shared__ __align__(128) uint8_t attn_smem[];
+    // Launch order = cost order: when the last query tile is partial (ViT: 577 = 9 x 64 + 1) its CTAs come last, so
+    // the full tiles each get an SM of their own and the nearly empty ones share (160 CTAs on 148 SMs).
+    int qt = blockIdx.x, h = blockIdx.y;
+    const int q_tiles = gridDim.x, heads = gridDim.y;
+    if (q_tiles > 1 && (a.q_len % kAttnBQ) != 0) {
+        const int item = blockIdx.x + q_tiles * blockIdx.y, n_full = (q_tiles - 1) * heads;
+        if (item < n_full) { qt = item % (q_tiles - 1); h = item / (q_tiles - 1); }
+        else { qt = q_tiles - 1; h = item - n_full; }
+    }
+    attention_body<T, D>(a, qt, h, blockIdx.z, attn_smem, threadIdx.x);
 }
 
 }  // namespace smb

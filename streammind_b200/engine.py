@@ -82,6 +82,7 @@ class Engine:
         if self.lib.sm_create(C.byref(self._h), device, C.byref(cc)) != 0:
             raise RuntimeError(self.lib.sm_last_error(None).decode())
         self._pinned_logits = torch.empty(cfg.max_frames, 2, dtype=torch.float32).pin_memory()
+        self._pinned_ring = torch.empty(4, cfg.max_frames, 2, dtype=torch.float32).pin_memory()   # frame_submit tickets
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int):
@@ -187,6 +188,35 @@ class Engine:
             toks.data_ptr() if toks is not None else None, logits.data_ptr() if logits is not None else None,
             self._pinned_logits.data_ptr(), self._stream()))
         return feats, toks, logits, self._pinned_logits[:B]
+
+    def frame_submit(self, pixels: torch.Tensor, want_feats: bool = False, want_device_outputs: bool = False):
+        """Pipelined frame_step (sm_frame_submit): returns (ticket, feats|None, toks|None, logits_device|None,
+        logits_pinned_host).  Nothing is ordered on the current stream: call ``frame_wait(ticket)`` before using
+        any output (``block=True`` for the pinned host logits)."""
+        c = self.cfg
+        if pixels.dtype != c.dtype:
+            raise RuntimeError(f"pixels: expected dtype {c.dtype}, got {pixels.dtype}")
+        on_host = 0 if pixels.is_cuda else 1
+        if on_host and not pixels.is_pinned():
+            raise RuntimeError("pixels: host tensors must be pinned")
+        px = pixels.contiguous()
+        B = px.shape[0]
+        feats = torch.empty(B, c.num_patches, c.vit_hidden, dtype=c.dtype, device=self.device) if want_feats else None
+        toks = torch.empty(B, c.proj_d_model, dtype=c.dtype, device=self.device) if want_device_outputs else None
+        logits = torch.empty(B, 2, dtype=torch.float32, device=self.device) if want_device_outputs else None
+        tk = C.c_longlong(0)
+        nxt = getattr(self, "_next_ticket", 0)
+        host = self._pinned_ring[nxt % 4]
+        self._check(self.lib.sm_frame_submit(
+            self._h, px.data_ptr(), on_host, B, feats.data_ptr() if feats is not None else None,
+            toks.data_ptr() if toks is not None else None, logits.data_ptr() if logits is not None else None,
+            host.data_ptr(), self._stream(), C.byref(tk)))
+        self._next_ticket = tk.value + 1
+        return tk.value, feats, toks, logits, host[:B]
+
+    def frame_wait(self, ticket: int, block: bool = True, on_stream: bool = True):
+        """Order the current stream after (on_stream) and/or block the host until (block) ticket's outputs."""
+        self._check(self.lib.sm_frame_wait(self._h, ticket, self._stream() if on_stream else None, 1 if block else 0))
 
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         ids32 = ids.to(device=self.device, dtype=torch.int32).contiguous()

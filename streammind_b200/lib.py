@@ -44,6 +44,8 @@ SYMBOLS = {
     "sm_projector_step": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_gate_score": (_I, [_VP, _VP, _VP, _VP]),
     "sm_frame_step": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "sm_frame_submit": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_longlong)]),
+    "sm_frame_wait": (_I, [_VP, _LL, _VP, _I]),
     "sm_embed_tokens": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_prefill": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_decode": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),
@@ -56,6 +58,7 @@ SYMBOLS = {
     "sm_profile_read": (_I, [_VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sm_profile_class_name": (C.c_char_p, [_I]),
     "sm_debug_kernel_filter": (_I, [_VP, C.c_uint]),
+    "sm_debug_mega_trace": (_I, [_VP, _VP, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I]),
     "sm_launch_count": (_LL, [_VP, _I]),
 }
 

@@ -152,3 +152,67 @@ def test_full_size_golden_from_reference(built_library):
     print("ViT features vs reference fp32:", e)
     assert max(e) < 5e-3, e
     eng.close()
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_pipelined_submit_small(built_library, use_graphs):
+    """sm_frame_submit / sm_frame_wait (tower and gate on two internal streams, up to 4 tickets in flight)
+    against the oracle and against the serial sm_frame_step on the same stream."""
+    dt = torch.float16
+    cfg = engine_config(dt, llm_layers=0, max_frames=2, use_graphs=use_graphs)
+    sd = make_weights(cfg)
+    eng = build_engine(cfg, sd)
+    oc = oracle_configs(cfg)
+    frames = synth.make_frames(0, 0, 12, cfg.vit_image, dtype=dt)
+    _, toks_o, logits_o = _oracle_frames(f32(sd), oc, dt, frames)
+    serial = torch.cat([eng.frame_step(frames[t:t + 2].cuda())[2] for t in range(0, 12, 2)])
+    eng.reset_stream()
+    pinned = frames.pin_memory()
+    tickets, host_views, dev = [], [], []
+    got = []
+    for t in range(0, 12, 2):                       # host frames, lookahead 1: submit t+1 before reading t
+        tk, _, tok, lg, lgh = eng.frame_submit(pinned[t:t + 2], want_device_outputs=True)
+        tickets.append(tk); host_views.append(lgh); dev.append((tok, lg))
+        if len(tickets) > 1:
+            eng.frame_wait(tickets[-2], block=True)
+            got.append(host_views[-2].clone())
+    eng.frame_wait(tickets[-1], block=True)
+    got.append(host_views[-1].clone())
+    torch.cuda.synchronize()
+    got = torch.cat(got)
+    check_close("pipelined logits vs oracle", got, logits_o, 4 * TOL[dt])
+    check_close("pipelined tokens vs oracle", torch.cat([d[0] for d in dev]), toks_o, 2 * TOL[dt])
+    assert torch.equal(torch.cat([d[1] for d in dev]).cpu(), got)
+    check_close("pipelined vs serial logits", got, serial, 1e-3)
+    eng.close()
+
+
+def test_pipelined_and_persistent_full_size_fp16(built_library, monkeypatch):
+    """Full BASELINE shapes: (a) the pipelined path (tower and gate on two internal streams) and (b) the
+    persistent vision-tower kernel (SMB_MEGA=2) reproduce the serial per-kernel path."""
+    dt = torch.float16
+    cfg = engine_config(dt, small=False, llm_layers=0, max_frames=1, use_graphs=True)
+    sd = make_weights(cfg)
+    frames = synth.make_frames(0, 0, 3, 336, dtype=dt).cuda()
+    eng = build_engine(cfg, sd)
+    ref = [eng.frame_step(frames[t:t + 1], want_feats=True) for t in range(3)]
+    torch.cuda.synchronize()
+    eng.reset_stream()
+    outs = []
+    for t in range(3):
+        outs.append(eng.frame_submit(frames[t:t + 1], want_feats=True, want_device_outputs=True))
+    eng.frame_wait(outs[-1][0], block=True)
+    torch.cuda.synchronize()
+    for t in range(3):
+        assert torch.equal(outs[t][1], ref[t][0])                       # tower: same kernels -> bit-identical
+        check_close(f"pipelined tokens {t}", outs[t][2], ref[t][1], 1e-3)
+        check_close(f"pipelined logits {t}", outs[t][3], ref[t][2], 2e-3)
+    eng.close()
+    monkeypatch.setenv("SMB_MEGA", "2")
+    eng2 = build_engine(cfg, sd)
+    for t in range(3):
+        f2, _, lg2, _ = eng2.frame_step(frames[t:t + 1], want_feats=True)
+        torch.cuda.synchronize()
+        check_close(f"persistent-kernel features {t}", f2, ref[t][0], 4e-3)  # two valid fp16 paths: noise floor ~1.6e-3
+        check_close(f"persistent-kernel logits {t}", lg2, ref[t][2], 8e-3)
+    eng2.close()
