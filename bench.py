@@ -28,6 +28,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json's metric, verbatim; config.workload names which of its configs a line measures (configs[1], the
+# default, is the ViT encode + event-gate stream: the LLM decode stage is not triggered in it)
+METRIC = "streaming frames/sec (encode+gate+decode) @336px, Mistral-7B, 1/2/4/8 B200"
+
 # algorithmic work per frame (SURVEY.md section 8d / BASELINE.md section 3)
 VIT_GFLOP_PER_FRAME = 366.0
 GATE_MB_PER_FRAME = 1577.1
@@ -135,7 +139,7 @@ def run_reference_arm(args):
     sec = statistics.mean(times)
     fps = n / sec
     line = {
-        "impl": "reference", "metric": "streaming frames/sec (encode+gate) @336px", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1] on host cores: {n}-frame sample of the 64-frame stream, "
@@ -315,7 +319,7 @@ def run_ours(args):
 
         px_bytes = n_frames * 3 * 336 * 336 * 2
         line = {
-            "metric": "streaming frames/sec (encode+gate) @336px", "value": value, "unit": "frames/s",
+            "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: {n_frames}-frame 336x336 synthetic stream per GPU, CLIP-ViT-L/14-336 "
@@ -431,7 +435,7 @@ def run_decode_workload(args):
         t_tok = DECODE_GB_PER_TOKEN / peaks["hbm"]
         roof_s = n_frames * t_frame + stats["tokens"] * t_tok + stats["fires"] * t_tok
         line = {
-            "metric": "streaming frames/sec (encode+gate+decode) @336px, Mistral-7B", "value": fps, "unit": "frames/s",
+            "metric": METRIC, "value": fps, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": label + "; CLIP-ViT-L/14-336 + projector + gate + Mistral-7B (32 layers, vocab 32002), random-init, one frame per call",

@@ -648,7 +648,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         if (run_vit_mega(h, B, st)) return 1;
         if (feats_out != nullptr) {
             DISPATCH_T(h, T, {
-                vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C);
+                vit_finalize_kernel<T><<<dim3((C / 8 + 3) / 4, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C);
                 count_launch(h);
             })
         }
@@ -658,7 +658,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         return 0;
     }
     DISPATCH_T(h, T, {
-        const long long n = static_cast<long long>(B) * P * h->kpad;
+        const long long n = static_cast<long long>(B) * P * (3 * c.vit_patch + 1);
         ProfScope ps_kc_im2col(h, KC_IM2COL, st);
         if (kon(h, KC_IM2COL)) {
         im2col_kernel<T><<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256, 0, st>>>(
@@ -736,7 +736,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     DISPATCH_T(h, T, {
         ProfScope ps_kc_vit_finalize(h, KC_VIT_FINALIZE, st);
         if (kon(h, KC_VIT_FINALIZE)) {
-        vit_finalize_kernel<T><<<dim3((C + 127) / 128, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
+        vit_finalize_kernel<T><<<dim3((C / 8 + 3) / 4, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
                                                                          (T*)pooled_out, S, C);
         }
         count_launch(h);
@@ -765,7 +765,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t 
     DISPATCH_T(h, T, {
         ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
         if (kon(h, KC_MAMBA_SCAN)) {
-        mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 4 * h->num_sms), 256, scan_smem, st>>>(s);
+        mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 8 * h->num_sms), 256, scan_smem, st>>>(s);
         }
         count_launch(h);
     })

@@ -12,21 +12,25 @@ namespace smb {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ px, T* __restrict__ out, int B, int img, int patch, int kpad) {
-    const int gw = img / patch, P = gw * gw, kreal = 3 * patch * patch;
-    const long long total = static_cast<long long>(B) * P * kpad;
+    // work item = (output row, segment): segments 0 .. 3*patch-1 are one patch line each (patch contiguous pixels ->
+    // patch contiguous columns), the last segment zero-fills the K padding
+    const int gw = img / patch, P = gw * gw, kreal = 3 * patch * patch, nseg = 3 * patch + 1;
+    const long long total = static_cast<long long>(B) * P * nseg;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(i % kpad);
-        const long long row = i / kpad;
-        T v = Cvt<T>::from_f(0.f);
-        if (k < kreal) {
+        const int seg = static_cast<int>(i % nseg);
+        const long long row = i / nseg;
+        T* o = out + row * kpad;
+        if (seg == 3 * patch) {
+            for (int k = kreal; k < kpad; ++k) o[k] = Cvt<T>::from_f(0.f);
+        } else {
             const int b = static_cast<int>(row / P), p = static_cast<int>(row % P);
             const int py = p / gw, pxx = p % gw;
-            const int c = k / (patch * patch), rem = k % (patch * patch);
-            const int ii = rem / patch, jj = rem % patch;
-            v = px[((static_cast<long long>(b) * 3 + c) * img + (py * patch + ii)) * img + pxx * patch + jj];
+            const int c = seg / patch, ii = seg % patch;
+            const T* src = px + ((static_cast<long long>(b) * 3 + c) * img + (py * patch + ii)) * img + pxx * patch;
+            T* d = o + c * patch * patch + ii * patch;
+            for (int jj = 0; jj < patch; ++jj) d[jj] = src[jj];
         }
-        out[i] = v;
     }
 }
 
@@ -244,21 +248,36 @@ __global__ void __launch_bounds__(128) splitk_residual_ln_kernel(
 // feature_select('patch') + mean over patches: feats[f, p, :] = x[f*S + 1 + p, :] (CLS dropped,
 // clip_encoder.py:31-35); pooled[f, :] = T(mean_p feats[f, p, :]) (multimodal_projector/builder.py:405)
 template <typename T>
-__global__ void vit_finalize_kernel(const T* __restrict__ x, T* __restrict__ feats, T* __restrict__ pooled, int S,
-                                    int C) {
+__global__ void __launch_bounds__(128) vit_finalize_kernel(const T* __restrict__ x, T* __restrict__ feats,
+                                                           T* __restrict__ pooled, int S, int C) {
+    // one warp per (frame, 8-column chunk): lanes stride over the patches with 16-byte loads, fp32 partial sums,
+    // one butterfly reduction per chunk (the old one-thread-per-column loop was a 576-step serial chain: 30 us)
     const int f = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int c0 = warp * 8;
+    if (c0 >= C) return;
     const int P = S - 1;
-    float s = 0.f;
-    const T* src = x + (static_cast<long long>(f) * S + 1) * C + c;
-    T* dst = feats ? feats + static_cast<long long>(f) * P * C + c : nullptr;
-    for (int p = 0; p < P; ++p) {
-        const T v = src[static_cast<long long>(p) * C];
-        s += Cvt<T>::to_f(v);
-        if (dst) dst[static_cast<long long>(p) * C] = v;
+    const T* src = x + (static_cast<long long>(f) * S + 1) * C + c0;
+    T* dst = feats ? feats + static_cast<long long>(f) * P * C + c0 : nullptr;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = lane; p < P; p += 32) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * C);
+        if (dst) *reinterpret_cast<uint4*>(dst + static_cast<long long>(p) * C) = u;
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fv = Cvt<T>::unpack2(w[i]);
+            acc[2 * i] += fv.x; acc[2 * i + 1] += fv.y;
+        }
     }
-    if (pooled) pooled[static_cast<long long>(f) * C + c] = Cvt<T>::from_f(s / P);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (pooled && lane == 0) {
+        uint4 o;
+        o.x = Cvt<T>::pack2(acc[0] / P, acc[1] / P); o.y = Cvt<T>::pack2(acc[2] / P, acc[3] / P);
+        o.z = Cvt<T>::pack2(acc[4] / P, acc[5] / P); o.w = Cvt<T>::pack2(acc[6] / P, acc[7] / P);
+        *reinterpret_cast<uint4*>(pooled + static_cast<long long>(f) * C + c0) = o;
+    }
 }
 
 // pooled[f, :] = T(mean_p feats[f, p, :]) for externally supplied features (B2 hook: mm_projector(feats))

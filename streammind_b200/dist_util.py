@@ -19,6 +19,9 @@ def env_rank_world():
 def init(backend: str, device=None):
     rank, world, _ = env_rank_world()
     if world > 1 and not dist.is_initialized():
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; bench.py's stdout must be one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
         dist.init_process_group(backend, **kw)
     return rank, world
