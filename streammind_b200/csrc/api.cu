@@ -437,7 +437,7 @@ int launch_attn_t(sm_handle* h, const AttnArgs& a, int q_tiles, int heads, int b
     if (!kon(h, KC_ATTN)) return 0;
     {
         ProfScope ps(h, KC_ATTN, st);
-        attention_kernel<T, D><<<dim3(q_tiles, heads, batch), kAttnThreads, smem, st>>>(a);
+        CUDA_OK(h, launch_pdl(h, attention_kernel<T, D>, dim3(q_tiles, heads, batch), dim3(kAttnThreads), smem, st, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -648,7 +648,7 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         if (run_vit_mega(h, B, st)) return 1;
         if (feats_out != nullptr) {
             DISPATCH_T(h, T, {
-                vit_finalize_kernel<T><<<dim3((C / 8 + 3) / 4, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C);
+                CUDA_OK(h, launch_pdl(h, vit_finalize_kernel<T>, dim3((C / 8 + 3) / 4, B), dim3(128), 0, st, (const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C));
                 count_launch(h);
             })
         }
@@ -661,8 +661,8 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
         const long long n = static_cast<long long>(B) * P * (3 * c.vit_patch + 1);
         ProfScope ps_kc_im2col(h, KC_IM2COL, st);
         if (kon(h, KC_IM2COL)) {
-        im2col_kernel<T><<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256, 0, st>>>(
-            reinterpret_cast<const T*>(pixels), reinterpret_cast<T*>(h->ws_im), B, c.vit_image, c.vit_patch, h->kpad);
+        CUDA_OK(h, launch_pdl(h, im2col_kernel<T>, dim3(static_cast<int>(std::min<long long>((n + 255) / 256, 4096))), dim3(256), 0, st,
+            reinterpret_cast<const T*>(pixels), reinterpret_cast<T*>(h->ws_im), B, c.vit_image, c.vit_patch, h->kpad));
         }
         count_launch(h);
     })
@@ -672,10 +672,10 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     DISPATCH_T(h, T, {
         ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
         if (kon(h, KC_LAYERNORM)) {
-        vit_embed_ln_kernel<T, 32><<<ln_blocks, warps_per_block * 32, 0, st>>>(
+        CUDA_OK(h, launch_pdl(h, vit_embed_ln_kernel<T, 32>, dim3(ln_blocks), dim3(warps_per_block * 32), 0, st,
             (const T*)h->ws_pemb, (const T*)h->vit_cls, (const T*)h->vit_pos, (const T*)h->vit_pre_w,
             (const T*)h->vit_pre_b, (const T*)h->vit[0].ln1_w, (const T*)h->vit[0].ln1_b, (T*)h->ws_x, (T*)h->ws_h, rows,
-            S, C, c.vit_eps);
+            S, C, c.vit_eps));
         }
         count_launch(h);
     })
@@ -690,9 +690,9 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
             DISPATCH_T(h, T, {
                 ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
                 if (kon(h, KC_LAYERNORM)) {
-                splitk_residual_ln_kernel<T><<<rows, C / 8, 0, st>>>(
-                    h->ws_part, S, static_cast<long long>(rows) * C, (const T*)bias, (T*)h->ws_x, (const T*)ln_w,
-                    (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                CUDA_OK(h, launch_pdl(h, splitk_residual_ln_kernel<T>, dim3(rows), dim3(C / 8), 0, st,
+                    (const float*)h->ws_part, S, static_cast<long long>(rows) * C, (const T*)bias, (T*)h->ws_x, (const T*)ln_w,
+                    (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps));
                 }
                 count_launch(h);
             })
@@ -702,8 +702,8 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
                 DISPATCH_T(h, T, {
                     ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
                     if (kon(h, KC_LAYERNORM)) {
-                    layernorm_kernel<T><<<ln_blocks, warps_per_block * 32, 0, st>>>(
-                        (const T*)h->ws_x, (const T*)ln_w, (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps);
+                    CUDA_OK(h, launch_pdl(h, layernorm_kernel<T>, dim3(ln_blocks), dim3(warps_per_block * 32), 0, st,
+                        (const T*)h->ws_x, (const T*)ln_w, (const T*)ln_b, (T*)h->ws_h, rows, C, c.vit_eps));
                     }
                     count_launch(h);
                 })
@@ -736,8 +736,8 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     DISPATCH_T(h, T, {
         ProfScope ps_kc_vit_finalize(h, KC_VIT_FINALIZE, st);
         if (kon(h, KC_VIT_FINALIZE)) {
-        vit_finalize_kernel<T><<<dim3((C / 8 + 3) / 4, B), 128, 0, st>>>((const T*)h->ws_x, (T*)feats_out,
-                                                                         (T*)pooled_out, S, C);
+        CUDA_OK(h, launch_pdl(h, vit_finalize_kernel<T>, dim3((C / 8 + 3) / 4, B), dim3(128), 0, st, (const T*)h->ws_x, (T*)feats_out,
+                                                                         (T*)pooled_out, S, C));
         }
         count_launch(h);
     })
@@ -765,7 +765,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t 
     DISPATCH_T(h, T, {
         ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
         if (kon(h, KC_MAMBA_SCAN)) {
-        mamba_scan_step_kernel<T><<<std::min((Di + 7) / 8, 8 * h->num_sms), 256, scan_smem, st>>>(s);
+        CUDA_OK(h, launch_pdl(h, mamba_scan_step_kernel<T>, dim3(std::min((Di + 7) / 8, 8 * h->num_sms)), dim3(256), scan_smem, st, s));
         }
         count_launch(h);
     })
@@ -810,7 +810,7 @@ int run_decode_step(sm_handle* h, cudaStream_t st) {
     const int QKV = (Hq + 2 * Hk) * D;
     if (D != 128) return fail(h, "llm decode: head_dim %d not supported (128)", D);
     DISPATCH_T(h, T, {
-        gather_rows_kernel<T><<<1, 256, 0, st>>>((const T*)h->lm_embed, h->d_tok, (T*)h->lw_x, 1, H);
+        CUDA_OK(h, launch_pdl(h, gather_rows_kernel<T>, dim3(1), dim3(256), 0, st, (const T*)h->lm_embed, (const int*)h->d_tok, (T*)h->lw_x, 1, H));
         count_launch(h);
     })
     const float scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
@@ -820,14 +820,14 @@ int run_decode_step(sm_handle* h, cudaStream_t st) {
         a.nw = L.in_ln; a.eps = c.llm_eps;
         if (launch_gemv(h, a, 1, st)) return 1;
         DISPATCH_T(h, T, {
-            rope_append_kernel<T><<<8, 256, 0, st>>>((T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], 1, Hq, Hk, D,
-                                                     c.llm_max_ctx, h->d_pos, 0, c.llm_rope_theta);
+            CUDA_OK(h, launch_pdl(h, rope_append_kernel<T>, dim3(8), dim3(256), 0, st, (T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], 1, Hq, Hk, D,
+                                                     c.llm_max_ctx, (const int*)h->d_pos, 0, c.llm_rope_theta));
             count_launch(h);
-            decode_attn_partial_kernel<T, 128><<<dim3(h->dec_splits, Hk), 128, 0, st>>>(
+            CUDA_OK(h, launch_pdl(h, decode_attn_partial_kernel<T, 128>, dim3(h->dec_splits, Hk), dim3(128), 0, st,
                 (const T*)h->lw_qkv, (const T*)h->kc[l], (const T*)h->vc[l], h->lw_part, Hq, Hk, c.llm_max_ctx,
-                h->d_pos, 0, scale_log2e);
+                (const int*)h->d_pos, 0, scale_log2e));
             count_launch(h);
-            decode_attn_combine_kernel<T, 128><<<Hq, 128, 0, st>>>(h->lw_part, (T*)h->lw_att, h->dec_splits);
+            CUDA_OK(h, launch_pdl(h, decode_attn_combine_kernel<T, 128>, dim3(Hq), dim3(128), 0, st, (const float*)h->lw_part, (T*)h->lw_att, h->dec_splits));
             count_launch(h);
         })
         a = gv(L.wo, H, Hq * D, PRO_PLAIN, h->lw_att, GEPI_RESID, nullptr);

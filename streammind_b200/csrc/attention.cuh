@@ -301,6 +301,8 @@ __device__ __forceinline__ void attention_body(const AttnArgs& a, int qt, int h,
 template <typename T, int D>
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs a) {
     extern __shared__ __align__(128) uint8_t attn_smem[];
+    pdl_trigger();
+    pdl_wait();
     // Launch order = cost order: when the last query tile is partial (ViT: 577 = 9 x 64 + 1) its CTAs come last, so
     // the full tiles each get an SM of their own and the nearly empty ones share (160 CTAs on 148 SMs).
     int qt = blockIdx.x, h = blockIdx.y;

@@ -282,6 +282,8 @@ struct ScanArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) mamba_scan_step_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t scan_smem[];
+    pdl_trigger();
+    pdl_wait();
     T* xdb = reinterpret_cast<T*>(scan_smem);
     const int nx = a.dt_rank + 2 * a.d_state;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) xdb[i] = reinterpret_cast<const T*>(a.xdb)[i];

@@ -12,6 +12,8 @@ namespace smb {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ px, T* __restrict__ out, int B, int img, int patch, int kpad) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     // work item = (output row, segment): segments 0 .. 3*patch-1 are one patch line each (patch contiguous pixels ->
     // patch contiguous columns), the last segment zero-fills the K padding
     const int gw = img / patch, P = gw * gw, kreal = 3 * patch * patch, nseg = 3 * patch + 1;
@@ -79,6 +81,8 @@ __global__ void vit_embed_ln_kernel(const T* __restrict__ patch_emb, const T* __
                                     const T* __restrict__ pos, const T* pre_w, const T* pre_b, const T* ln_w,
                                     const T* ln_b, T* __restrict__ x, T* __restrict__ h, int rows, int S, int C,
                                     float eps) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int f = warp / S, p = warp % S;
@@ -113,6 +117,8 @@ __global__ void vit_embed_ln_kernel(const T* __restrict__ patch_emb, const T* __
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                                  T* __restrict__ h, int rows, int C, float eps) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const T* xr = x + static_cast<long long>(warp) * C;
@@ -182,6 +188,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) splitk_residual_ln_kernel(
     const float* __restrict__ part, int nsplit, long long split_stride, const T* __restrict__ bias, T* __restrict__ x,
     const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ h, int rows, int C, float eps) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     __shared__ float red[8];
     const int row = blockIdx.x, c0 = threadIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -250,6 +258,8 @@ __global__ void __launch_bounds__(128) splitk_residual_ln_kernel(
 template <typename T>
 __global__ void __launch_bounds__(128) vit_finalize_kernel(const T* __restrict__ x, T* __restrict__ feats,
                                                            T* __restrict__ pooled, int S, int C) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     // one warp per (frame, 8-column chunk): lanes stride over the patches with 16-byte loads, fp32 partial sums,
     // one butterfly reduction per chunk (the old one-thread-per-column loop was a 576-step serial chain: 30 us)
     const int f = blockIdx.y;
@@ -300,6 +310,8 @@ __global__ void pool_kernel(const T* __restrict__ feats, T* __restrict__ pooled,
 template <typename T>
 __global__ void rope_append_kernel(T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, int rows, int Hq,
                                    int Hk, int D, int max_ctx, const int* pos0_ptr, int pos0_host, float theta) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     const int pos0 = pos0_ptr ? *pos0_ptr : pos0_host;
     const int half = D / 2;
     const int per_row = (Hq + Hk) * half + Hk * D;
@@ -349,6 +361,8 @@ __global__ void __launch_bounds__(128) decode_attn_partial_kernel(const T* __res
                                                                   const T* __restrict__ vc, float* __restrict__ part,
                                                                   int Hq, int Hk, int max_ctx, const int* kv_len_ptr,
                                                                   int kv_len_host, float scale_log2e) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     // 4 warps; each warp owns keys kbeg + warp, +4, ...; lane owns D/32 dims.  group <= 8.
     constexpr int VPL = D / 32;
     const int kv_len = kv_len_ptr ? (*kv_len_ptr + 1) : kv_len_host;  // device counter holds the position of the new token
@@ -437,6 +451,8 @@ __global__ void __launch_bounds__(128) decode_attn_partial_kernel(const T* __res
 
 template <typename T, int D>
 __global__ void decode_attn_combine_kernel(const float* __restrict__ part, T* __restrict__ out, int nsplit) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     const int h = blockIdx.x, d = threadIdx.x;
     const float* p = part + static_cast<long long>(h) * nsplit * (D + 2);
     float mm = -INFINITY;
@@ -492,6 +508,8 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int n, int* __re
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,
                                    int n, int C) {
+    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
     const int r = blockIdx.x;
     if (r >= n) return;
     const T* src = table + static_cast<long long>(ids[r]) * C;
