@@ -323,6 +323,10 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
         a.dbg_mode = dm;
     }
+    {
+        static const int pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
+        a.pre_weights = pre;
+    }
     a.dbg = h->gemm_dbg;
     if (h->gemm_dbg) h->gemm_dbg += 8;   // one 8-slot record per launch
     const CUtensorMap* tc = ta;  // placeholder when unused

@@ -42,6 +42,7 @@ struct GemmArgs {
     int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
                     // 16 KiB operand tile contiguous (full-rate DRAM bursts instead of 128-byte strided reads)
     int w_kb;       // k-blocks per n_tile in that layout
+    int pre_weights;   // request the first ring of weight tiles before griddepcontrol.wait (see the producer)
     int dbg_mode;   // microbenchmark aid: 1 = no MMA issue (TMA + barriers only), 2 = no TMA (MMA + barriers only)
     long long* dbg; // optional: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
 };
@@ -222,44 +223,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here
-    if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 1), static_cast<unsigned long long>(gtimer()));
 
     if (warp == 0) {
         // ---------------- TMA producer: the whole warp walks the ring, one elected lane issues
         // weights are streamed once; activations are re-read by every CTA column -> keep them in L2
         const uint64_t pol_a = args.swap ? kEvictFirst : kEvictLast;
         const uint64_t pol_b = args.swap ? kEvictLast : kEvictNormal;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int a_slice = kGemmBM / CS;
+        const bool a_is_tiled_w = args.w_tiled && args.swap;
+        auto load_a = [&](int stage, int kg) {   // A tile: whole (CS = 1) or this CTA's 128/CS-row slice multicast to the cluster
+            uint8_t* a_dst = smem_a + stage * A_BYTES + crank * a_slice * 128;
+            const int ac0 = a_is_tiled_w ? 0 : kg * kGemmBK;
+            const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kg) * kGemmBM : a0) + crank * a_slice;
+            if (CS > 1) tma_load_2d_mc(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, cmask, pol_a);
+            else tma_load_2d(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, pol_a);
+        };
+        auto load_b = [&](int stage, int kg) {
+            if (!args.w_tiled || args.swap) {
+                tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kg * kGemmBK, b0, pol_b);
+            } else {                  // B = tiled weights, BN rows = BN/128 whole tiles or a slice of one
+                const int nld = BN > kGemmBM ? BN / kGemmBM : 1;
+                for (int j = 0; j < nld; ++j)
+                    tma_load_2d(smem_b + stage * B_BYTES + j * (kGemmBM * 128), &tmap_b, &full_bar[stage], 0,
+                                ((b0 / kGemmBM + j) * args.w_kb + kg) * kGemmBM + (b0 % kGemmBM), pol_b);
+            }
+        };
+        // The weight operand never depends on the previous kernel: with programmatic dependent launch this CTA is
+        // often resident while its predecessor still runs, so the first ring of WEIGHT tiles is requested before
+        // griddepcontrol.wait and only the activation tiles wait for it (hides the cold-HBM ramp of every GEMM).
+        const bool can_pre = CS == 1 && args.dbg_mode == 0 && args.pre_weights != 0;
+        const int npre = can_pre ? min(NSTAGE, num_kb) : 0;
+        if (npre > 0 && elect_one_sync()) {
+            for (int kb = 0; kb < npre; ++kb) {
+                mbar_arrive_expect_tx(&full_bar[kb], A_BYTES + B_BYTES);
+                if (args.swap) load_a(kb, kb_begin + kb); else load_b(kb, kb_begin + kb);
+            }
+        }
+        __syncwarp();
+        pdl_wait();   // the previous kernel's outputs (activations) are visible from here
+        if (dbg && lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 1), static_cast<unsigned long long>(gtimer()));
+        if (npre > 0 && elect_one_sync()) {
+            for (int kb = 0; kb < npre; ++kb) {
+                if (args.swap) load_b(kb, kb_begin + kb); else load_a(kb, kb_begin + kb);
+            }
+        }
+        __syncwarp();
+        int stage = npre == NSTAGE ? 0 : npre;
+        uint32_t phase = npre == NSTAGE ? 1 : 0;
+        for (int kb = npre; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (args.dbg_mode == 2 || args.dbg_mode == 3) {
                 if (elect_one_sync()) mbar_arrive(&full_bar[stage]);
             } else if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                // A tile: whole (CS = 1) or this CTA's 128/CS-row slice multicast to the cluster
-                const int a_slice = kGemmBM / CS;
-                uint8_t* a_dst = smem_a + stage * A_BYTES + crank * a_slice * 128;
-                const bool a_is_tiled_w = args.w_tiled && args.swap;
                 const int kg = kb_begin + kb;   // global k-block index
-                const int ac0 = a_is_tiled_w ? 0 : kg * kGemmBK;
-                const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kg) * kGemmBM : a0) + crank * a_slice;
-                if (CS > 1) tma_load_2d_mc(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, cmask, pol_a);
-                else tma_load_2d(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, pol_a);
-                if (!args.w_tiled || args.swap) {
-                    tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kg * kGemmBK, b0, pol_b);
-                } else {                  // B = tiled weights, BN rows = BN/128 whole tiles or a slice of one
-                    const int nld = BN > kGemmBM ? BN / kGemmBM : 1;
-                    for (int j = 0; j < nld; ++j)
-                        tma_load_2d(smem_b + stage * B_BYTES + j * (kGemmBM * 128), &tmap_b, &full_bar[stage], 0,
-                                    ((b0 / kGemmBM + j) * args.w_kb + kg) * kGemmBM + (b0 % kGemmBM), pol_b);
-                }
+                load_a(stage, kg);
+                load_b(stage, kg);
             }
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
+        pdl_wait();
         // ---------------- MMA issuer: whole warp waits, one elected lane issues tcgen05.mma / commit
         const uint32_t idesc = umma_idesc_f16(kGemmBM, BN, Cvt<T>::kBf16);
         int stage = 0;
@@ -291,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         // ---------------- epilogue warps 2..9
+        pdl_wait();
         const int lane_base = (warp & 3) * 32;
         const int chalf = (warp - 2) >> 2;   // 0: even 32-column chunks, 1: odd chunks
         const int a_row = a0 + lane_base + lane;  // A row owned by this thread
