@@ -203,8 +203,8 @@ def run_ours(args):
     preds = []
 
     def step_e2e():
-        """Pinned-host frames in, every gate decision read back on the host.  Pipelined mode keeps one frame of
-        lookahead: frame t+1 is submitted before the host blocks on the decision of frame t."""
+        """Pinned-host frames in, every gate decision read back on the host.  Pipelined mode keeps `lookahead`
+        frames in flight: frame t+lookahead is submitted before the host blocks on the decision of frame t."""
         preds.clear()
         if not pipelined:
             for t in range(0, n_frames, chunk):
@@ -213,17 +213,18 @@ def run_ours(args):
                 for i in range(lg.shape[0]):
                     preds.append(int(lg[i, 1] > lg[i, 0]))
             return
-        prev = None
+        inflight = []
+        def drain_one(on_stream):
+            tk, _, _, _, lgh = inflight.pop(0)
+            eng.frame_wait(tk, block=True, on_stream=on_stream)
+            for i in range(lgh.shape[0]):
+                preds.append(int(lgh[i, 1] > lgh[i, 0]))
         for t in range(0, n_frames, chunk):
-            cur = eng.frame_submit(frames_host[t:t + chunk])
-            if prev is not None:
-                eng.frame_wait(prev[0], block=True, on_stream=False)
-                for i in range(prev[4].shape[0]):
-                    preds.append(int(prev[4][i, 1] > prev[4][i, 0]))
-            prev = cur
-        eng.frame_wait(prev[0], block=True, on_stream=True)
-        for i in range(prev[4].shape[0]):
-            preds.append(int(prev[4][i, 1] > prev[4][i, 0]))
+            inflight.append(eng.frame_submit(frames_host[t:t + chunk]))
+            if len(inflight) > args.lookahead:
+                drain_one(False)
+        while inflight:
+            drain_one(len(inflight) == 1)
 
     def barrier():
         if world > 1:
@@ -326,7 +327,8 @@ def run_ours(args):
                                    f"(23 layers) + Mamba projector step + 4-layer Mistral gate, fp16, random-init, "
                                    f"{chunk} frame(s) per call",
                        "frames_per_step": n_frames, "chunk": chunk, "cuda_graphs": cfg.use_graphs,
-                       "pipelined": pipelined,
+                       "pipelined": pipelined, "frames_in_flight": (8 if pipelined else 1), "tower_lanes": (int(os.environ.get("SMB_LANES", "4")) if pipelined else 1),
+                       "e2e_lookahead": (args.lookahead if pipelined else 0),
                        "l2_policy": "inputs larger than L2: 2.41 GB of weights are re-streamed per frame (L2 = 126 MB)",
                        "parallelism": f"{world} independent stream(s), one per GPU, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": px_bytes,
@@ -474,6 +476,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="serial sm_frame_step instead of sm_frame_submit/wait")
+    ap.add_argument("--lookahead", type=int, default=4, help="e2e: frames submitted ahead of the decision being read (<= 7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

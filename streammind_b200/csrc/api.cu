@@ -58,6 +58,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 }  // namespace
 
+constexpr int kMaxLanes = 4;      // concurrent vision towers of the pipelined path
+constexpr int kTicketRing = 8;    // frames in flight (sm_frame_submit tickets)
+
 struct sm_handle {
     sm_config cfg{};
     int device = 0;
@@ -88,6 +91,12 @@ struct sm_handle {
     void *ws_im = nullptr, *ws_pemb = nullptr, *ws_x = nullptr, *ws_h = nullptr, *ws_qkv = nullptr, *ws_att = nullptr,
          *ws_mlp = nullptr, *ws_pooled = nullptr, *ws_pixels = nullptr, *ws_feats = nullptr;
     float* ws_part = nullptr;   // split-K partial sums [4][rows][C] fp32
+    // Two complete sets of tower activations ("lanes"): sm_frame_submit runs the towers of consecutive frames on two
+    // streams at the same time, so the kernels of one frame fill the SMs the other frame's small GEMMs leave idle.
+    // The ws_* fields above always point at the lane selected by select_lane() (lane 0 outside sm_frame_submit).
+    struct VitWs { void *ws_im, *ws_pemb, *ws_x, *ws_h, *ws_qkv, *ws_att, *ws_mlp, *ws_pixels, *ws_feats; float* ws_part; };
+    VitWs lanes[kMaxLanes] = {};
+    int cur_lane = 0;
     // persistent vision-tower kernel (vit_mega.cuh): one op list + tensor-map array per chunk size B
     struct MegaPlan { MegaOp* d_ops = nullptr; CUtensorMap* d_maps = nullptr; int n_ops = 0; std::vector<int> types; };
     std::map<int, MegaPlan> mega_plans;
@@ -119,11 +128,14 @@ struct sm_handle {
     int dec_splits = 16;
     // ---- pipelined frame path (sm_frame_submit): tower on vit_stream, projector + gate on gate_stream
     bool pipe_init = false;
-    cudaStream_t vit_stream = nullptr, gate_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_vit[2] = {nullptr, nullptr}, ev_gate[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_lanes = 4;                   // towers of consecutive tickets run on this many streams / activation sets (<= kMaxLanes)
+    int plan_div = 2;                  // GEMM tile planner: accept the widest tile that yields >= num_sms / plan_div CTAs
+    int split_sms = 0;                 // SMs a split-K GEMM may fill (0 = all)
+    cudaStream_t vit_streams[kMaxLanes] = {}, gate_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_vit[kMaxLanes] = {}, ev_gate[kTicketRing] = {};
     long long ticket = 0;
     int bg_grid = 0;                   // > 0: projector/gate GEMVs of the pipelined path on this many CTAs (experiment; measured slower)
-    void* ws_pooled2[2] = {nullptr, nullptr};
+    void* ws_pooled2[kMaxLanes] = {};
     // ---- graphs
     std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
     std::map<int, long long> frame_graph_launches;
@@ -178,6 +190,13 @@ void add_tiled_slot(sm_handle* h, const std::string& name, void* matrix_base, in
     h->slots[name] = s;
 }
 inline size_t tiled_elems(int n, int k) { return static_cast<size_t>((n + 127) / 128) * ((k + 63) / 64) * 128 * 64; }
+
+inline void select_lane(sm_handle* h, int lane) {
+    const sm_handle::VitWs& w = h->lanes[lane];
+    h->ws_im = w.ws_im; h->ws_pemb = w.ws_pemb; h->ws_x = w.ws_x; h->ws_h = w.ws_h; h->ws_qkv = w.ws_qkv;
+    h->ws_att = w.ws_att; h->ws_mlp = w.ws_mlp; h->ws_pixels = w.ws_pixels; h->ws_feats = w.ws_feats; h->ws_part = w.ws_part;
+    h->cur_lane = lane;
+}
 
 inline void count_launch(sm_handle* h) {
     if (h->capturing) h->captured_launches++; else h->launches++;
@@ -256,7 +275,7 @@ const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int 
 // ------------------------------------------------------------------------------------------ GEMM
 struct GemmPlan { int swap, bn; };
 
-GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi) {
+GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi, int plan_div) {
     // Rule distilled from the graph-timed sweep in profiles/r01_gemm_plan_sweep.md: on B200 one tcgen05.mma
     // costs >= ~105 clocks whatever its N, so a CTA's mainloop lasts ~250 ns per K=64 slab for any tile width;
     // the best plan is the widest feature tile that still yields about half a wave of CTAs.  Transposed (swap)
@@ -269,9 +288,9 @@ GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi) {
     // measured (profiles/r01_gemm_plan_sweep.md, one streaming frame = 577 tokens): the wide fc1 GEMM is fastest with
     // weight rows on the MMA lanes and 160 tokens per tile (4 x 32 = 128 CTAs, no 2-byte-strided stores: TMA store)
     static const int fc1_swap = getenv("SMB_FC1_SWAP") ? atoi(getenv("SMB_FC1_SWAP")) : 1;
-    if (fc1_swap && !residual && mt == 5 && feats >= 4096 && feats % 128 == 0) return {1, 160};
+    if (fc1_swap && plan_div <= 2 && !residual && mt == 5 && feats >= 4096 && feats % 128 == 0) return {1, 160};
     for (int bn : {256, 128, 64, 32})
-        if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / 2) return {0, bn};
+        if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / plan_div) return {0, bn};
     return {0, std::min(32, feats)};
 }
 
@@ -281,7 +300,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
                   int split_k = 1) {
     if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
     if (!kon(h, KC_GEMM)) return 0;
-    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi);
+    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div);
     if (force_swap >= 0) p.swap = force_swap;
     if (force_bn > 0) p.bn = force_bn;
     if (!p.swap && (feats % 16 != 0)) return fail(h, "gemm: non-swapped layout needs features %% 16 == 0");
@@ -364,9 +383,10 @@ int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feat
 // ~ k-blocks x 250 ns and the only way to shorten it is to give each CTA fewer k-blocks.
 int splitk_factor(const sm_handle* h, int tokens, int feats, int K) {
     static const int max_split = getenv("SMB_SPLITK") ? atoi(getenv("SMB_SPLITK")) : 4;
+    const int split_sms = h->split_sms;
     const int tiles = ((tokens + 127) / 128) * ((feats + 127) / 128);
     const int kb = (K + kGemmBK - 1) / kGemmBK;
-    int s = std::min({max_split, h->num_sms / std::max(1, tiles), kb / 4});
+    int s = std::min({max_split, (split_sms > 0 ? split_sms : h->num_sms) / std::max(1, tiles), kb / 4});
     while (s > 1 && (s - 1) * ((kb + s - 1) / s) >= kb) --s;   // every split gets at least one k-block
     return s < 2 ? 1 : s;
 }
@@ -591,7 +611,7 @@ int mega_build_plan(sm_handle* h, int B) {
     if (!plan.d_ops || !plan.d_maps) return fail(h, "mega_build_plan: out of device memory");
     CUDA_OK(h, cudaMemcpy(plan.d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
     CUDA_OK(h, cudaMemcpy(plan.d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    h->mega_plans[B] = plan;
+    h->mega_plans[B | (h->cur_lane << 16)] = plan;
     return 0;
 }
 
@@ -605,11 +625,12 @@ int mega_launch_t(sm_handle* h, const sm_handle::MegaPlan& plan, int op_begin, i
 }
 
 int run_vit_mega(sm_handle* h, int B, cudaStream_t st) {
-    auto it = h->mega_plans.find(B);
+    const int pkey = B | (h->cur_lane << 16);
+    auto it = h->mega_plans.find(pkey);
     if (it == h->mega_plans.end()) {
         if (h->capturing) return fail(h, "run_vit_mega: plan for B=%d must be built outside graph capture", B);
         if (mega_build_plan(h, B)) return 1;
-        it = h->mega_plans.find(B);
+        it = h->mega_plans.find(pkey);
     }
     const sm_handle::MegaPlan& plan = it->second;
     auto launch = [&](int b, int e) -> int {
@@ -1048,10 +1069,23 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->ws_att = A(rows * C * e);
         h->ws_mlp = A(rows * F * e);
         h->ws_pooled = A(static_cast<size_t>(Bm) * C * e);
-        h->ws_pooled2[0] = A(static_cast<size_t>(Bm) * C * e);
-        h->ws_pooled2[1] = A(static_cast<size_t>(Bm) * C * e);
+        for (auto& pp : h->ws_pooled2) pp = A(static_cast<size_t>(Bm) * C * e);
         h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
         h->ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
+        h->lanes[0] = {h->ws_im, h->ws_pemb, h->ws_x, h->ws_h, h->ws_qkv, h->ws_att, h->ws_mlp, h->ws_pixels, h->ws_feats, h->ws_part};
+        for (int ln = 1; ln < kMaxLanes; ++ln) {
+            sm_handle::VitWs& w = h->lanes[ln];
+            w.ws_pixels = A(static_cast<size_t>(Bm) * 3 * c.vit_image * c.vit_image * e);
+            w.ws_im = A(static_cast<size_t>(Bm) * h->P * h->kpad * e);
+            w.ws_pemb = A(static_cast<size_t>(Bm) * h->P * C * e);
+            w.ws_x = A(rows * C * e);
+            w.ws_h = A(rows * C * e);
+            w.ws_qkv = A(rows * 3 * C * e);
+            w.ws_att = A(rows * C * e);
+            w.ws_mlp = A(rows * F * e);
+            w.ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
+            w.ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
+        }
         h->mega_sync = static_cast<unsigned int*>(A(256));
         h->mega_mode = getenv("SMB_MEGA") ? atoi(getenv("SMB_MEGA")) : 0;
     }
@@ -1173,7 +1207,7 @@ void sm_destroy(sm_handle* h) {
     for (auto& g : h->frame_graphs) cudaGraphExecDestroy(g.second);
     if (h->decode_graph) cudaGraphExecDestroy(h->decode_graph);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
-    if (h->vit_stream) cudaStreamDestroy(h->vit_stream);
+    for (auto st : h->vit_streams) if (st) cudaStreamDestroy(st);
     if (h->gate_stream) cudaStreamDestroy(h->gate_stream);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto e : h->ev_vit) if (e) cudaEventDestroy(e);
@@ -1245,7 +1279,7 @@ int sm_stream_reset(sm_handle* h) {
     if (!h) return 1;
     cudaSetDevice(h->device);
     if (h->pipe_init) {
-        CUDA_OK(h, cudaStreamSynchronize(h->vit_stream));
+        for (auto st : h->vit_streams) CUDA_OK(h, cudaStreamSynchronize(st));
         CUDA_OK(h, cudaStreamSynchronize(h->gate_stream));
     }
     if (h->pj_conv_state) {
@@ -1360,7 +1394,8 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
     if (!h->pipe_init) {
         int lo = 0, hi = 0;
         CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
-        CUDA_OK(h, cudaStreamCreateWithPriority(&h->vit_stream, cudaStreamNonBlocking, hi));
+        for (auto& vst : h->vit_streams) CUDA_OK(h, cudaStreamCreateWithPriority(&vst, cudaStreamNonBlocking, hi));
+        h->n_lanes = std::max(1, std::min(kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : 4));
         CUDA_OK(h, cudaStreamCreateWithPriority(&h->gate_stream, cudaStreamNonBlocking, lo));
         CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         for (auto& e : h->ev_vit) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1368,13 +1403,26 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         h->bg_grid = getenv("SMB_BG_GRID") ? atoi(getenv("SMB_BG_GRID")) : 0;
         h->pipe_init = true;
     }
-    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_stream, gs = h->gate_stream;
     const long long tk = h->ticket;
-    const int slot = static_cast<int>(tk & 1), ring = static_cast<int>(tk & 3);
-    if (tk >= 4) CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));           // at most 4 frames in flight
+    const int lane = static_cast<int>(tk % h->n_lanes), slot = lane, ring = static_cast<int>(tk % kTicketRing);
+    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane], gs = h->gate_stream;
+    struct LaneGuard {   // every exit path leaves lane 0 and the serial tile planner selected for the other entry points
+        sm_handle* h; int div, ssm;
+        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; }
+    } lane_guard{h, h->plan_div, h->split_sms};
+    select_lane(h, lane);
+    // With several towers in flight the SMs are kept busy by the other frames, so a GEMM is planned for bytes per
+    // flop (wide tiles, fewer CTAs, less split-K) instead of for its own latency (measured: +6 % at 2 lanes).
+    if (h->n_lanes > 1) {
+        static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 4;
+        static const int ssm = getenv("SMB_SPLIT_SMS") ? atoi(getenv("SMB_SPLIT_SMS")) : 0;
+        h->plan_div = pdiv;
+        h->split_sms = ssm;
+    }
+    if (tk >= kTicketRing) CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));           // at most kTicketRing frames in flight
     CUDA_OK(h, cudaEventRecord(h->ev_in, st));
     CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
-    if (tk >= 2) CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_gate[(tk - 2) & 3], 0));   // pooled[slot] has been consumed
+    if (tk >= h->n_lanes) CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_gate[(tk - h->n_lanes) % kTicketRing], 0));   // pooled[slot] has been consumed
     const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
     CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, vs));
     const bool want_feats = feats_out != nullptr;
@@ -1412,11 +1460,11 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         return 0;
     };
     const int kf = static_cast<int>((h->kfilter & 0xFFFFu) << 12);
-    if (run_part(B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (slot << 10) | kf, vs, vit_body, "sm_frame_submit(tower)")) return 1;
+    if (run_part(B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (lane << 28) | kf, vs, vit_body, "sm_frame_submit(tower)")) return 1;
     if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, vs));
     CUDA_OK(h, cudaEventRecord(h->ev_vit[slot], vs));
     CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[slot], 0));
-    if (run_part(B | (1 << 9) | (1 << 11) | (slot << 10) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
+    if (run_part(B | (1 << 9) | (1 << 11) | (lane << 28) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
     if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, gs));
     if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, gs));
     if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, gs));
@@ -1428,10 +1476,10 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
 
 int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host) {
     if (!h || !h->pipe_init) return fail(h, "sm_frame_wait: nothing submitted");
-    if (ticket < 0 || ticket >= h->ticket || ticket + 4 < h->ticket)
-        return fail(h, "sm_frame_wait: ticket %lld is not in flight (next ticket %lld, ring of 4)", ticket, h->ticket);
+    if (ticket < 0 || ticket >= h->ticket || ticket + kTicketRing < h->ticket)
+        return fail(h, "sm_frame_wait: ticket %lld is not in flight (next ticket %lld, ring of %d)", ticket, h->ticket, kTicketRing);
     cudaSetDevice(h->device);
-    cudaEvent_t ev = h->ev_gate[ticket & 3];
+    cudaEvent_t ev = h->ev_gate[ticket % kTicketRing];
     if (stream != nullptr || !block_host) CUDA_OK(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
     if (block_host) CUDA_OK(h, cudaEventSynchronize(ev));
     return 0;
@@ -1586,7 +1634,7 @@ int sm_test_gemm_trace(sm_handle* h, long long* device_buf) {
 int sm_debug_mega_trace(sm_handle* h, long long* device_buf, int B, int* n_ops, int* types, int max_ops) {
     if (!h) return 1;
     h->mega_dbg = device_buf;
-    auto it = h->mega_plans.find(B);
+    auto it = h->mega_plans.find(B);   // lane 0
     if (n_ops) *n_ops = it == h->mega_plans.end() ? 0 : it->second.n_ops;
     if (types && it != h->mega_plans.end())
         for (int i = 0; i < it->second.n_ops && i < max_ops; ++i) types[i] = it->second.types[i];
