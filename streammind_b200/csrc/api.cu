@@ -273,25 +273,36 @@ const CUtensorMap* get_tmap(sm_handle* h, const void* ptr, int rows, int K, int 
 }
 
 // ------------------------------------------------------------------------------------------ GEMM
-struct GemmPlan { int swap, bn; };
+struct GemmPlan { int swap, bn, bm2; };
 
-GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi, int plan_div) {
+// 256-row dual-accumulator tiles (GemmArgs::bm2): worth it when the tile count (x split-K) still feeds the machine --
+// several towers in flight (plan_div >= 4) or a chunk of frames; they halve the weight bytes each SM ingests.
+bool plan_bm2(int tokens, int feats, int split_k, int num_sms, int plan_div) {
+    static const int mode = getenv("SMB_BM2") ? atoi(getenv("SMB_BM2")) : 0;   // measured: no gain (chunk 8: 962 vs 958 frames/s; B=1 x 4 lanes: 431 vs 633) -> opt-in
+    if (mode == 0 || feats % 256 != 0 || tokens <= 256) return false;
+    if (mode == 2) return true;
+    const int tiles = ((tokens + 255) / 256) * (feats / 256) * std::max(1, split_k);
+    return plan_div >= 4 ? tiles >= num_sms / (2 * plan_div) : tiles >= num_sms;
+}
+
+GemmPlan plan_gemm(int tokens, int feats, int K, int num_sms, int epi, int plan_div, int split_k = 1) {
     // Rule distilled from the graph-timed sweep in profiles/r01_gemm_plan_sweep.md: on B200 one tcgen05.mma
     // costs >= ~105 clocks whatever its N, so a CTA's mainloop lasts ~250 ns per K=64 slab for any tile width;
     // the best plan is the widest feature tile that still yields about half a wave of CTAs.  Transposed (swap)
     // tiles only pay off for a handful of tokens (weight rows fill the 128 MMA lanes, tokens ride on N >= 16).
     (void)K;
     const bool residual = epi == EPI_RESIDUAL || epi == EPI_STORE_F32;
-    if (tokens <= 64 && !residual) return {1, std::max(16, (tokens + 15) / 16 * 16)};
-    if (feats % 16 != 0) return {1, std::min(256, std::max(16, (tokens + 15) / 16 * 16))};
+    if (tokens <= 64 && !residual) return {1, std::max(16, (tokens + 15) / 16 * 16), 0};
+    if (feats % 16 != 0) return {1, std::min(256, std::max(16, (tokens + 15) / 16 * 16)), 0};
+    if (plan_bm2(tokens, feats, split_k, num_sms, plan_div)) return {0, 256, 1};
     const int mt = (tokens + 127) / 128;
     // measured (profiles/r01_gemm_plan_sweep.md, one streaming frame = 577 tokens): the wide fc1 GEMM is fastest with
     // weight rows on the MMA lanes and 160 tokens per tile (4 x 32 = 128 CTAs, no 2-byte-strided stores: TMA store)
     static const int fc1_swap = getenv("SMB_FC1_SWAP") ? atoi(getenv("SMB_FC1_SWAP")) : 1;
-    if (fc1_swap && plan_div <= 2 && !residual && mt == 5 && feats >= 4096 && feats % 128 == 0) return {1, 160};
+    if (fc1_swap && plan_div <= 2 && !residual && mt == 5 && feats >= 4096 && feats % 128 == 0) return {1, 160, 0};
     for (int bn : {256, 128, 64, 32})
-        if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / plan_div) return {0, bn};
-    return {0, std::min(32, feats)};
+        if (bn <= feats && mt * ((feats + bn - 1) / bn) >= num_sms / plan_div) return {0, bn, 0};
+    return {0, std::min(32, feats), 0};
 }
 
 template <typename T>
@@ -300,9 +311,14 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
                   int split_k = 1) {
     if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
     if (!kon(h, KC_GEMM)) return 0;
-    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div);
-    if (force_swap >= 0) p.swap = force_swap;
-    if (force_bn > 0) p.bn = force_bn;
+    GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div, split_k);
+    if (force_swap == 2) {                 // forced 256 x 256 dual-accumulator tile
+        if (feats % 256 != 0) return fail(h, "gemm: the 256-row tile needs features %% 256 == 0");
+        p.swap = 0; p.bn = 256; p.bm2 = 1;
+    } else {
+        if (force_swap >= 0) { p.swap = force_swap; p.bm2 = 0; }
+        if (force_bn > 0) { p.bn = force_bn; p.bm2 = 0; }
+    }
     if (!p.swap && (feats % 16 != 0)) return fail(h, "gemm: non-swapped layout needs features %% 16 == 0");
     const CUtensorMap *ta, *tb;
     GemmArgs a{};
@@ -315,7 +331,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         ta = get_tmap(h, x, tokens, K, kGemmBM);
         tb = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, std::min(p.bn, kGemmBM)) : get_tmap(h, w, feats, K, p.bn);
         a.Ma = tokens; a.Nb = feats;
-        grid = dim3((tokens + kGemmBM - 1) / kGemmBM, (feats + p.bn - 1) / p.bn);
+        grid = dim3((tokens + kGemmBM * (p.bm2 ? 2 : 1) - 1) / (kGemmBM * (p.bm2 ? 2 : 1)), (feats + p.bn - 1) / p.bn);
     } else {
         ta = w_tiled ? get_tmap(h, w, w_rows_tiled, kGemmBK, kGemmBM) : get_tmap(h, w, feats, K, kGemmBM);
         tb = get_tmap(h, x, tokens, K, p.bn);
@@ -337,7 +353,8 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     if (split_k > 1) { grid.z = split_k; a.split_k = split_k; a.split_stride = static_cast<long long>(tokens) * feats; }
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
-    a.nstage = gemm_num_stages(p.bn); a.epi = epi;
+    a.bm2 = p.bm2;
+    a.nstage = gemm_num_stages(p.bn, p.bm2); a.epi = epi;
     {
         static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
         a.dbg_mode = dm;
@@ -360,7 +377,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         static const int dbg_stages = getenv("SMB_GEMM_STAGES") ? atoi(getenv("SMB_GEMM_STAGES")) : 0;   // tuning knob
         if (dbg_stages > 0 && dbg_stages < a.nstage) a.nstage = dbg_stages;
     }
-    const int smem = gemm_smem_bytes(p.bn);
+    const int smem = gemm_smem_bytes(p.bn, p.bm2);
     {
         ProfScope ps(h, KC_GEMM, st);
         CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads), smem, st, CS, *ta, *tb, *tc, a));
@@ -381,10 +398,10 @@ int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feat
 // Split-K factor for a residual GEMM whose 128x128 tiles alone cannot fill the SMs (streaming B = 1):
 // every MMA instruction costs >= ~105 clocks whatever its N (profiles/r01_gemm_phases.md), so a CTA's time is
 // ~ k-blocks x 250 ns and the only way to shorten it is to give each CTA fewer k-blocks.
-int splitk_factor(const sm_handle* h, int tokens, int feats, int K) {
+int splitk_factor(const sm_handle* h, int tokens, int feats, int K, bool bm2 = false) {
     static const int max_split = getenv("SMB_SPLITK") ? atoi(getenv("SMB_SPLITK")) : 4;
     const int split_sms = h->split_sms;
-    const int tiles = ((tokens + 127) / 128) * ((feats + 127) / 128);
+    const int tiles = bm2 ? ((tokens + 255) / 256) * ((feats + 255) / 256) : ((tokens + 127) / 128) * ((feats + 127) / 128);
     const int kb = (K + kGemmBK - 1) / kGemmBK;
     int s = std::min({max_split, (split_sms > 0 ? split_sms : h->num_sms) / std::max(1, tiles), kb / 4});
     while (s > 1 && (s - 1) * ((kb + s - 1) / s) >= kb) --s;   // every split gets at least one k-block
@@ -709,9 +726,11 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     // partials whose fixed-order sum, the residual add and the LayerNorm run in one row kernel.
     auto residual_gemm_ln = [&](const void* a_in, const void* W, int K, const void* bias, const void* ln_w,
                                 const void* ln_b) -> int {
-        const int S = ((C & 255) == 0 && C <= 1024) ? splitk_factor(h, rows, C, K) : 1;
+        const bool bm2 = h->vit_tiled && plan_bm2(rows, C, 3, h->num_sms, h->plan_div);
+        const int S = ((C & 255) == 0 && C <= 1024) ? splitk_factor(h, rows, C, K, bm2) : 1;
         if (S > 1) {
-            if (launch_gemm(h, a_in, rows, W, C, K, nullptr, h->ws_part, C, EPI_STORE_F32, st, 0, 128, h->vit_tiled, S)) return 1;
+            // forced plan: 128-wide tiles, or (force_swap = 2) the 256 x 256 dual-accumulator tile
+            if (launch_gemm(h, a_in, rows, W, C, K, nullptr, h->ws_part, C, EPI_STORE_F32, st, bm2 ? 2 : 0, bm2 ? 256 : 128, h->vit_tiled, S)) return 1;
             DISPATCH_T(h, T, {
                 ProfScope ps_kc_layernorm(h, KC_LAYERNORM, st);
                 if (kon(h, KC_LAYERNORM)) {

@@ -42,6 +42,9 @@ struct GemmArgs {
     int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
                     // 16 KiB operand tile contiguous (full-rate DRAM bursts instead of 128-byte strided reads)
     int w_kb;       // k-blocks per n_tile in that layout
+    int bm2;        // 1: the CTA owns a 256-row tile = two 128-row halves that share every B (weight) stage; two
+                    // accumulators in TMEM (columns 0 and 256).  Halves the weight bytes an SM ingests per output
+                    // element (the L2 -> SM rate, ~48 B/clk/SM measured, bounds the 128-row tile).  Non-swapped only.
     int pre_weights;   // request the first ring of weight tiles before griddepcontrol.wait (see the producer)
     int dbg_mode;   // microbenchmark aid: 1 = no MMA issue (TMA + barriers only), 2 = no TMA (MMA + barriers only)
     long long* dbg; // optional: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
@@ -60,12 +63,12 @@ constexpr int kGemmEpiThreads = 256;
 constexpr int kGemmMaxStages = 8;
 constexpr int kGemmSmemBudget = 200 * 1024;
 
-inline int gemm_stage_bytes(int bn) { return kGemmBM * kGemmBK * 2 + bn * kGemmBK * 2; }
-inline int gemm_num_stages(int bn) {
-    int s = kGemmSmemBudget / gemm_stage_bytes(bn);
+inline int gemm_stage_bytes(int bn, int bm2 = 0) { return (bm2 ? 2 : 1) * kGemmBM * kGemmBK * 2 + bn * kGemmBK * 2; }
+inline int gemm_num_stages(int bn, int bm2 = 0) {
+    int s = kGemmSmemBudget / gemm_stage_bytes(bn, bm2);
     return s > kGemmMaxStages ? kGemmMaxStages : s;
 }
-inline int gemm_smem_bytes(int bn) { return gemm_num_stages(bn) * gemm_stage_bytes(bn) + 1024 + 256 + 1024; }
+inline int gemm_smem_bytes(int bn, int bm2 = 0) { return gemm_num_stages(bn, bm2) * gemm_stage_bytes(bn, bm2) + 1024 + 256 + 1024; }
 
 template <typename T> __device__ __forceinline__ float quick_gelu_t(float h) {
     // every intermediate is materialised in T by the reference: 1.702*x, sigmoid(.), x*(.)
@@ -174,10 +177,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
     const int BN = args.bn;
     const int NSTAGE = args.nstage;
-    constexpr int A_BYTES = kGemmBM * kGemmBK * 2;
+    constexpr int A_HALF = kGemmBM * kGemmBK * 2;
+    const int NH = args.bm2 ? 2 : 1;                 // 128-row halves of the A tile
+    const int A_BYTES = NH * A_HALF;
     const int B_BYTES = BN * kGemmBK * 2;
     const bool ksplit = args.dbg_mode >= 3 && BN <= 128;   // experiment: one accumulator per K=16 step
-    const uint32_t TMEM_COLS = ksplit ? 512u : BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
+    const uint32_t TMEM_COLS = (ksplit || args.bm2) ? 512u : BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int lane = threadIdx.x & 31;
     long long* dbg = args.dbg;   // per-launch record: [0] = min CTA start, [i] = max over CTAs of phase i end
     if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(dbg), static_cast<unsigned long long>(gtimer()));
-    const int a0 = blockIdx.x * kGemmBM;  // first A row of this tile
+    const int a0 = blockIdx.x * kGemmBM * (args.bm2 ? 2 : 1);  // first A row of this tile
     const int b0 = blockIdx.y * BN;       // first B row of this tile
     const int total_kb = (args.K + kGemmBK - 1) / kGemmBK;
     const int kb_per = args.split_k > 1 ? (total_kb + args.split_k - 1) / args.split_k : total_kb;
@@ -237,6 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int ac1 = (a_is_tiled_w ? (blockIdx.x * args.w_kb + kg) * kGemmBM : a0) + crank * a_slice;
             if (CS > 1) tma_load_2d_mc(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, cmask, pol_a);
             else tma_load_2d(a_dst, &tmap_a, &full_bar[stage], ac0, ac1, pol_a);
+            if (NH == 2) tma_load_2d(a_dst + A_HALF, &tmap_a, &full_bar[stage], ac0, ac1 + kGemmBM, pol_a);   // rows past Ma: zero fill
         };
         auto load_b = [&](int stage, int kg) {
             if (!args.w_tiled || args.swap) {
@@ -305,6 +311,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in (addr>>4) units
                         umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
+                    if (NH == 2) {   // second 128-row half against the same B stage -> accumulator at column 256
+                        const uint64_t adesc1 = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * A_BYTES + A_HALF));
+#pragma unroll
+                        for (int k = 0; k < kGemmBK / 16; ++k)
+                            umma_f16(tmem_base + 256u, adesc1 + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
                 // frees the smem slot once these MMAs have read it -- in every CTA that multicasts into it
                 if (CS > 1) umma_commit_mc(&empty_bar[stage], cmask);
@@ -319,12 +331,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         pdl_wait();
         const int lane_base = (warp & 3) * 32;
         const int chalf = (warp - 2) >> 2;   // 0: even 32-column chunks, 1: odd chunks
-        const int a_row = a0 + lane_base + lane;  // A row owned by this thread
+        int a_row = a0 + lane_base + lane;  // A row owned by this thread (first 128-row half)
         T* out_t = reinterpret_cast<T*>(args.out);
         float* out_f = reinterpret_cast<float*>(args.out);
         const T* bias = reinterpret_cast<const T*>(args.bias);
         const int epi = args.epi;
-        const bool a_ok = a_row < args.Ma;
+        bool a_ok = a_row < args.Ma;
         // While the mainloop runs: stage the bias of this tile's columns in smem (non-swapped layout)
         float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [256] floats, 16-byte aligned
         if (!args.swap) {
@@ -340,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 3), static_cast<unsigned long long>(gtimer()));
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
+        uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
         // 32-column chunks, TMEM load of chunk c+1 (and residual read) in flight while chunk c is processed
         const int nchunk = (BN + 31) / 32;
         uint32_t rbA[32], rbB[32];
@@ -385,6 +397,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // this warp's chunks: chalf, chalf + 2, ...
         const int nmine = nchunk > chalf ? (nchunk - chalf + 1) / 2 : 0;
         auto chunk_of = [&](int k) { return chalf + 2 * k; };
+        const int half_stage_bytes = (BN / 64) * (kGemmBM * 128);   // staging tile of one 128-row half
+        for (int hh = 0; hh < NH; ++hh) {
+        if (hh == 1) {   // second 128-row half: accumulator at TMEM column 256, rows + 128, its own staging tile
+            a_row += kGemmBM;
+            a_ok = a_row < args.Ma;
+            taddr += 256u;
+            cx.a_row = a_row;
+            cx.stage = smem_a + half_stage_bytes;
+        }
         if (nmine > 0) {
             prefetch_res(chunk_of(0), xrA);
             __syncwarp();
@@ -411,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (has2) tmem_wait_ld();
             }
         }
+        }   // hh
         if (dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 4), static_cast<unsigned long long>(gtimer()));
         if (args.tma_store) {
             // the mainloop is over (accum_bar): the operand ring is free and doubles as the staging tile
@@ -418,8 +440,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             named_bar_sync(1, kGemmEpiThreads);
             if (warp == 2 && elect_one_sync()) {
                 if (!args.swap) {
-                    for (int cb = 0; cb < BN / 64; ++cb)
-                        if (b0 + cb * 64 < args.Nb) tma_store_2d(&tmap_c, smem_a + cb * (kGemmBM * 128), b0 + cb * 64, a0);
+                    for (int hh = 0; hh < NH; ++hh)
+                        for (int cb = 0; cb < BN / 64; ++cb)
+                            if (b0 + cb * 64 < args.Nb && a0 + hh * kGemmBM < args.Ma)
+                                tma_store_2d(&tmap_c, smem_a + hh * half_stage_bytes + cb * (kGemmBM * 128), b0 + cb * 64,
+                                             a0 + hh * kGemmBM);
                 } else {
                     for (int cb = 0; cb < 2; ++cb)
                         if (a0 + cb * 64 < args.Ma) tma_store_2d(&tmap_c, smem_a + cb * (BN * 128), a0 + cb * 64, b0);

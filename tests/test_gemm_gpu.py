@@ -34,6 +34,9 @@ def _ref(x, w, b):
     (128, 128, 64, 0, 128), (128, 128, 64, 1, 128), (128, 256, 256, 0, 64), (577, 1024, 1024, 0, 128),
     (577, 3072, 1024, 0, 256), (577, 1024, 4096, 1, 160), (576, 1024, 640, 0, 128), (37, 512, 1024, 1, 48),
     (1, 4096, 4096, 1, 16), (1154, 4096, 1024, -1, 0), (64, 6144, 4096, -1, 0), (300, 1024, 1000, 0, 32),
+    # swap = 2: 256 x 256 tile, two TMEM accumulators sharing each weight stage (GemmArgs::bm2)
+    (577, 1024, 1024, 2, 256), (577, 3072, 1024, 2, 256), (1154, 4096, 1024, 2, 256), (300, 512, 384, 2, 256),
+    (257, 256, 4096, 2, 256),
 ])
 def test_gemm_store(eng, dt, M, N, K, swap, bn):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -48,7 +51,7 @@ def test_gemm_store(eng, dt, M, N, K, swap, bn):
     assert emax < tol and el2 < tol, (emax, el2)
 
 
-@pytest.mark.parametrize("swap", [0, 1])
+@pytest.mark.parametrize("swap", [0, 1, 2])
 def test_gemm_epilogues(eng, swap):
     dt = torch.float16
     g = torch.Generator(device="cuda").manual_seed(5)
