@@ -132,10 +132,14 @@ struct sm_handle {
     int plan_div = 2;                  // GEMM tile planner: accept the widest tile that yields >= num_sms / plan_div CTAs
     int split_sms = 0;                 // SMs a split-K GEMM may fill (0 = all)
     cudaStream_t vit_streams[kMaxLanes] = {}, gate_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_vit[kMaxLanes] = {}, ev_gate[kTicketRing] = {};
+    cudaEvent_t ev_in = nullptr, ev_vit[kTicketRing] = {}, ev_gate[kTicketRing] = {};
     long long ticket = 0;
     int bg_grid = 0;                   // > 0: projector/gate GEMVs of the pipelined path on this many CTAs (experiment; measured slower)
-    void* ws_pooled2[kMaxLanes] = {};
+    void* pooled_ring = nullptr;       // [kTicketRing][max_frames][C]: pooled patch means, one slot per ticket in flight
+    struct PendingTicket { void* toks_out; float* logits_out; float* logits_host; int B; };
+    PendingTicket pend[4] = {};        // tickets whose towers are enqueued but whose gate batch is still open
+    int n_pending = 0, gate_batch = 4;
+    long long first_pending = 0;
     // ---- graphs
     std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
     std::map<int, long long> frame_graph_launches;
@@ -434,19 +438,34 @@ template <typename T>
 int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (a.K % 8 != 0) return fail(h, "gemv: K=%d must be a multiple of 8", a.K);
     if (!kon(h, KC_GEMV)) return 0;
-    if (h->gemv_tma && gemv_tma_supported(a.K)) return launch_gemv_tma_t<T>(h, a, nmat, st);
-    a.seg_len = 1024;
+    if (h->gemv_tma && a.nv_host <= 1 && gemv_tma_supported(a.K)) return launch_gemv_tma_t<T>(h, a, nmat, st);
+    const int nv = std::max(1, a.nv_host);
+    a.seg_len = nv == 1 ? 1024 : 2048;
     static const int grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;   // experiment: background-sized grids
-    int grid = std::min(a.N, grid_cap > 0 ? grid_cap : 2 * h->num_sms);
+    int grid = std::min(a.N, grid_cap > 0 ? grid_cap : (nv == 1 ? 2 : 1) * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;
     grid = (a.N + rows_per_cta - 1) / rows_per_cta;
     const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
-    const size_t smem = ((a.K * 2 + 15) & ~15) + static_cast<size_t>(nmat) * rows_per_cta * nseg * sizeof(float);
-    if (smem > 100 * 1024) return fail(h, "gemv: K=%d too large for the staging buffer", a.K);
+    const int xpitch = (a.K + 7) & ~7;
+    const size_t smem = ((static_cast<size_t>(nv) * xpitch * 2 + 15) & ~size_t(15)) +
+                        static_cast<size_t>(nmat) * nv * rows_per_cta * nseg * sizeof(float);
+    if (smem > (nv == 1 ? 100u : 200u) * 1024) return fail(h, "gemv: K=%d x %d vectors too large for the staging buffer", a.K, nv);
     {
         ProfScope ps(h, KC_GEMV, st);
-        if (nmat == 1) CUDA_OK(h, launch_pdl(h, gemv_kernel<T, 1>, dim3(grid), dim3(kGemvThreads), smem, st, a));
-        else CUDA_OK(h, launch_pdl(h, gemv_kernel<T, 2>, dim3(grid), dim3(kGemvThreads), smem, st, a));
+        const dim3 g(grid), b(kGemvThreads);
+#define SMB_GEMV_CASE(NM, NVV) CUDA_OK(h, launch_pdl(h, gemv_kernel<T, NM, NVV>, g, b, smem, st, a))
+        switch (nmat * 10 + nv) {
+            case 11: SMB_GEMV_CASE(1, 1); break;
+            case 12: SMB_GEMV_CASE(1, 2); break;
+            case 13: SMB_GEMV_CASE(1, 3); break;
+            case 14: SMB_GEMV_CASE(1, 4); break;
+            case 21: SMB_GEMV_CASE(2, 1); break;
+            case 22: SMB_GEMV_CASE(2, 2); break;
+            case 23: SMB_GEMV_CASE(2, 3); break;
+            case 24: SMB_GEMV_CASE(2, 4); break;
+            default: return fail(h, "gemv: %d matrices x %d vectors not instantiated", nmat, nv);
+        }
+#undef SMB_GEMV_CASE
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -496,6 +515,12 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(vit_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    {
+        auto big = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); };
+        CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 2>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 3>));
+        CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 4>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 2>));
+        CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 3>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 4>));
+    }
     CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -789,23 +814,35 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
     return 0;
 }
 
-int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t st) {
+// nv consecutive frames (<= kGemvBatch) in one pass over the weights: every GEMV takes nv input vectors, the two
+// sequential pieces (conv window in the in_proj epilogue, SSM state in the scan kernel) walk the frames in order.
+constexpr int kGemvBatch = 4;
+
+int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaStream_t st) {
     const sm_config& c = h->cfg;
     const int Dm = c.proj_d_model, Di = h->d_inner, R = h->dt_rank, N = c.proj_d_state, C = c.vit_hidden;
+    const int nxp = (R + 2 * N + 7) & ~7;
+    auto batched = [&](GemvArgs& a, long long xs, long long ys, long long rs = 0, long long zs = 0) {
+        a.nv_host = nv; a.x_stride = xs; a.y_stride = ys; a.resid_stride = rs; a.z_stride = zs;
+    };
     GemvArgs a = gv(h->pj_pre_w, Dm, C, PRO_PLAIN, pooled, GEPI_LEAKY, h->pj_h0);
     a.bias = h->pj_pre_b;
+    batched(a, C, Dm);
     if (launch_gemv(h, a, 1, st)) return 1;
     a = gv(h->pj_in, 2 * Di, Dm, PRO_LAYERNORM, h->pj_h0, GEPI_MAMBA_CONV, h->pj_xc);
     a.nw = h->pj_norm_w; a.nb = h->pj_norm_b; a.eps = c.proj_eps;
     a.conv_state = h->pj_conv_state; a.conv_w = h->pj_conv_w; a.conv_b = h->pj_conv_b; a.z_out = h->pj_z;
     a.d_inner = Di; a.d_conv = c.proj_d_conv;
+    batched(a, Dm, Di, 0, Di);
     if (launch_gemv(h, a, 1, st)) return 1;
     a = gv(h->pj_xproj, R + 2 * N, Di, PRO_PLAIN, h->pj_xc, GEPI_STORE, h->pj_xdb);
+    batched(a, Di, nxp);
     if (launch_gemv(h, a, 1, st)) return 1;
     ScanArgs s{};
     s.W_dt = h->pj_dt_w; s.b_dt = h->pj_dt_b; s.A_log = h->pj_alog; s.D = h->pj_D; s.xdb = h->pj_xdb; s.x = h->pj_xc;
     s.z = h->pj_z; s.state = h->pj_ssm_state; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
-    const int scan_smem = ((R + 2 * N) * 2 + 15) & ~15;
+    s.nv = nv; s.xdb_stride = nxp; s.x_stride = Di; s.z_stride = Di; s.y_stride = Di;
+    const int scan_smem = (nv * nxp * 2 + 15) & ~15;
     DISPATCH_T(h, T, {
         ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
         if (kon(h, KC_MAMBA_SCAN)) {
@@ -815,36 +852,59 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, cudaStream_t 
     })
     a = gv(h->pj_out, Dm, Di, PRO_PLAIN, h->pj_y, GEPI_ADD_TO, h->pj_r2);
     a.resid = h->pj_h0;
+    batched(a, Di, Dm, Dm);
     if (launch_gemv(h, a, 1, st)) return 1;
     a = gv(h->pj_post_w, Dm, Dm, PRO_LN_LEAKY, h->pj_r2, GEPI_STORE, tok_out);
     a.nw = h->pj_nf_w; a.nb = h->pj_nf_b; a.eps = c.proj_eps; a.bias = h->pj_post_b;
+    batched(a, Dm, Dm);
     if (launch_gemv(h, a, 1, st)) return 1;
     return 0;
 }
 
-int run_gate(sm_handle* h, const void* tok, float* logits_out, cudaStream_t st) {
+int run_gate(sm_handle* h, const void* tok, float* logits_out, int nv, cudaStream_t st) {
     const sm_config& c = h->cfg;
     const int H = c.proj_d_model, Hq = c.gate_heads, Hk = c.gate_kv_heads, D = c.gate_head_dim, F = c.gate_ffn;
-    CUDA_OK(h, cudaMemcpyAsync(h->gt_h, tok, static_cast<size_t>(H) * h->esz, cudaMemcpyDeviceToDevice, st));
+    auto batched = [&](GemvArgs& a, long long xs, long long ys, long long rs = 0) {
+        a.nv_host = nv; a.x_stride = xs; a.y_stride = ys; a.resid_stride = rs;
+    };
+    CUDA_OK(h, cudaMemcpyAsync(h->gt_h, tok, static_cast<size_t>(nv) * H * h->esz, cudaMemcpyDeviceToDevice, st));
     for (int l = 0; l < c.gate_layers; ++l) {
         const MistralLayer& L = h->gate[l];
         GemvArgs a = gv(L.wqkv, Hk * D, H, PRO_RMSNORM, h->gt_h, GEPI_STORE, h->gt_v);
         a.nw = L.in_ln; a.eps = c.gate_eps;
+        batched(a, H, Hk * D);
         if (launch_gemv(h, a, 1, st)) return 1;
         a = gv(L.wo, H, Hq * D, PRO_GQA_EXPAND, h->gt_v, GEPI_RESID, nullptr);
         a.resid = h->gt_h; a.gqa_rep = Hq / Hk; a.head_dim = D;
+        batched(a, Hk * D, 0, H);
         if (launch_gemv(h, a, 1, st)) return 1;
         a = gv(L.wgu, F, H, PRO_RMSNORM, h->gt_h, GEPI_SWIGLU, h->gt_m);
         a.W1 = reinterpret_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz;
         a.nw = L.post_ln; a.eps = c.gate_eps;
+        batched(a, H, F);
         if (launch_gemv(h, a, 2, st)) return 1;
         a = gv(L.wd, H, F, PRO_PLAIN, h->gt_m, GEPI_RESID, nullptr);
         a.resid = h->gt_h;
+        batched(a, F, 0, H);
         if (launch_gemv(h, a, 1, st)) return 1;
     }
     GemvArgs a = gv(h->gt_head, 2, H, PRO_RMSNORM, h->gt_h, GEPI_F32, logits_out);
     a.nw = h->gt_norm; a.eps = c.gate_eps;
+    batched(a, H, 2);
     return launch_gemv(h, a, 1, st);
+}
+
+// projector + gate for n frames: batches of <= kGemvBatch frames share every weight pass
+int run_proj_gate(sm_handle* h, const void* pooled, void* toks, float* logits, int n, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    static const int max_batch = getenv("SMB_GEMV_BATCH") ? std::max(1, std::min(kGemvBatch, atoi(getenv("SMB_GEMV_BATCH")))) : kGemvBatch;
+    for (int i = 0; i < n; i += max_batch) {
+        const int nv = std::min(max_batch, n - i);
+        char* tok = static_cast<char*>(toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
+        if (run_projector(h, static_cast<const char*>(pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, nv, st)) return 1;
+        if (run_gate(h, tok, logits + 2 * i, nv, st)) return 1;
+    }
+    return 0;
 }
 
 // one decode step: feeds the token in d_tok at position *d_pos, leaves the next token in d_tok
@@ -963,6 +1023,66 @@ int capture_graph(sm_handle* h, F&& body, cudaGraphExec_t* out, long long* n_lau
     CUDA_OK(h, cudaGraphInstantiate(out, g, 0));
     cudaGraphDestroy(g);
     *n_launches = h->captured_launches;
+    return 0;
+}
+
+// Enqueue projector + gate for the pending tickets (towers already enqueued) as ONE batch on the gate stream:
+// consecutive frames share every pass over the projector / gate weights (run_proj_gate).
+int pipe_flush_gate(sm_handle* h) {
+    const int np = h->n_pending;
+    if (np == 0) return 0;
+    const sm_config& c = h->cfg;
+    cudaStream_t gs = h->gate_stream;
+    const long long first = h->first_pending;
+    const int slot0 = static_cast<int>(first % kTicketRing);
+    int nframes = 0;
+    for (int i = 0; i < np; ++i) {
+        CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[(first + i) % kTicketRing], 0));
+        nframes += h->pend[i].B;
+    }
+    const size_t pooled_sz = static_cast<size_t>(c.vit_hidden) * h->esz, tok_sz = static_cast<size_t>(c.proj_d_model) * h->esz;
+    // pending tickets are consecutive ring slots and (np > 1) single frames: their pooled vectors are contiguous
+    char* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(slot0) * h->cfg.max_frames * pooled_sz;
+    auto gate_body = [&](cudaStream_t s) -> int {
+        const int saved_cap = h->gemv_grid_cap;
+        const bool saved_tma = h->gemv_tma;
+        if (h->bg_grid > 0) { h->gemv_grid_cap = h->bg_grid; h->gemv_tma = true; }   // "background" gate experiment
+        const int rc = run_proj_gate(h, pooled, h->pj_toks, h->gt_logits, nframes, s);
+        h->gemv_grid_cap = saved_cap;
+        h->gemv_tma = saved_tma;
+        return rc;
+    };
+    if (!c.use_graphs) {
+        if (gate_body(gs)) return 1;
+    } else {
+        const int key = nframes | (1 << 9) | (1 << 11) | (slot0 << 24) | static_cast<int>((h->kfilter & 0xFFFu) << 12);
+        auto it = h->frame_graphs.find(key);
+        if (it == h->frame_graphs.end()) {
+            if (gate_body(gs)) return 1;                 // real run: produces this batch's outputs
+            CUDA_OK(h, cudaStreamSynchronize(gs));
+            cudaGraphExec_t ge;
+            long long n = 0;
+            if (capture_graph(h, gate_body, &ge, &n, "sm_frame_submit(gate)")) return 1;
+            h->frame_graphs[key] = ge;
+            h->frame_graph_launches[key] = n;
+        } else {
+            CUDA_OK(h, cudaGraphLaunch(it->second, gs));
+            h->launches += h->frame_graph_launches[key];
+        }
+    }
+    int f0 = 0;
+    for (int i = 0; i < np; ++i) {
+        const sm_handle::PendingTicket& p = h->pend[i];
+        const char* tk_src = static_cast<const char*>(h->pj_toks) + static_cast<size_t>(f0) * tok_sz;
+        const float* lg_src = h->gt_logits + 2 * f0;
+        if (p.toks_out) CUDA_OK(h, cudaMemcpyAsync(p.toks_out, tk_src, p.B * tok_sz, cudaMemcpyDeviceToDevice, gs));
+        if (p.logits_out) CUDA_OK(h, cudaMemcpyAsync(p.logits_out, lg_src, static_cast<size_t>(p.B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, gs));
+        if (p.logits_host) CUDA_OK(h, cudaMemcpyAsync(p.logits_host, lg_src, static_cast<size_t>(p.B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, gs));
+        f0 += p.B;
+    }
+    for (int i = 0; i < np; ++i) CUDA_OK(h, cudaEventRecord(h->ev_gate[(first + i) % kTicketRing], gs));
+    h->first_pending = first + np;
+    h->n_pending = 0;
     return 0;
 }
 
@@ -1088,7 +1208,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->ws_att = A(rows * C * e);
         h->ws_mlp = A(rows * F * e);
         h->ws_pooled = A(static_cast<size_t>(Bm) * C * e);
-        for (auto& pp : h->ws_pooled2) pp = A(static_cast<size_t>(Bm) * C * e);
+        h->pooled_ring = A(static_cast<size_t>(kTicketRing) * Bm * C * e);
         h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
         h->ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
         h->lanes[0] = {h->ws_im, h->ws_pemb, h->ws_x, h->ws_h, h->ws_qkv, h->ws_att, h->ws_mlp, h->ws_pixels, h->ws_feats, h->ws_part};
@@ -1136,11 +1256,13 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->pj_nf_b = A(Dm * e); add_slot(h, p + "mamba_model.norm_fn.bias", h->pj_nf_b, 1, Dm);
         h->pj_post_w = A(static_cast<size_t>(Dm) * Dm * e); add_slot(h, p + "post_net.fc3.weight", h->pj_post_w, Dm, Dm);
         h->pj_post_b = A(Dm * e); add_slot(h, p + "post_net.fc3.bias", h->pj_post_b, 1, Dm);
-        h->pj_h0 = A(Dm * e); h->pj_xc = A(Di * e); h->pj_z = A(Di * e); h->pj_xdb = A((R + 2 * N) * e + 64);
-        h->pj_y = A(Di * e); h->pj_r2 = A(Dm * e);
+        constexpr int NB = 4;   // kGemvBatch frames share one pass over the weights
+        if (N > 32) { delete h; return fail(nullptr, "sm_create: projector d_state %d > 32 not supported", N); }
+        h->pj_h0 = A(NB * Dm * e); h->pj_xc = A(NB * Di * e); h->pj_z = A(NB * Di * e); h->pj_xdb = A(NB * ((R + 2 * N + 7) & ~7) * e + 64);
+        h->pj_y = A(NB * Di * e); h->pj_r2 = A(NB * Dm * e);
         h->pj_conv_state = A(static_cast<size_t>(Di) * W * e);
         h->pj_ssm_state = static_cast<float*>(A(static_cast<size_t>(Di) * N * sizeof(float)));
-        h->pj_toks = A(static_cast<size_t>(Bm) * Dm * e);
+        h->pj_toks = A(static_cast<size_t>(std::max(Bm, 4)) * Dm * e);
     }
     // ---------------- gate
     if (c.gate_layers > 0) {
@@ -1165,8 +1287,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         }
         h->gt_norm = A(H * e); add_slot(h, p + "model.norm.weight", h->gt_norm, 1, H);
         h->gt_head = A(static_cast<size_t>(2) * H * e); add_slot(h, p + "lm_head.weight", h->gt_head, 2, H);
-        h->gt_h = A(H * e); h->gt_v = A(static_cast<size_t>(Hk) * D * e); h->gt_m = A(F * e);
-        h->gt_logits = static_cast<float*>(A(static_cast<size_t>(Bm) * 2 * sizeof(float)));
+        h->gt_h = A(4 * H * e); h->gt_v = A(static_cast<size_t>(4) * Hk * D * e); h->gt_m = A(static_cast<size_t>(4) * F * e);
+        h->gt_logits = static_cast<float*>(A(static_cast<size_t>(std::max(Bm, 4)) * 2 * sizeof(float)));
     }
     // ---------------- LLM
     if (c.llm_layers > 0) {
@@ -1298,6 +1420,7 @@ int sm_stream_reset(sm_handle* h) {
     if (!h) return 1;
     cudaSetDevice(h->device);
     if (h->pipe_init) {
+        if (pipe_flush_gate(h)) return 1;
         for (auto st : h->vit_streams) CUDA_OK(h, cudaStreamSynchronize(st));
         CUDA_OK(h, cudaStreamSynchronize(h->gate_stream));
     }
@@ -1332,10 +1455,10 @@ int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, v
 int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, void* stream) {
     if (!h || h->cfg.proj_d_model <= 0) return fail(h, "sm_projector_step: projector not configured");
     cudaSetDevice(h->device);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; i += kGemvBatch) {
         const char* src = static_cast<const char*>(pooled) + static_cast<size_t>(i) * h->cfg.vit_hidden * h->esz;
         char* dst = static_cast<char*>(tok_out) + static_cast<size_t>(i) * h->cfg.proj_d_model * h->esz;
-        if (run_projector(h, src, dst, static_cast<cudaStream_t>(stream))) return 1;
+        if (run_projector(h, src, dst, std::min(kGemvBatch, n - i), static_cast<cudaStream_t>(stream))) return 1;
     }
     return 0;
 }
@@ -1343,7 +1466,7 @@ int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, vo
 int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream) {
     if (!h || h->cfg.gate_layers <= 0) return fail(h, "sm_gate_score: gate not configured");
     cudaSetDevice(h->device);
-    return run_gate(h, tok, logits_out, static_cast<cudaStream_t>(stream));
+    return run_gate(h, tok, logits_out, 1, static_cast<cudaStream_t>(stream));
 }
 
 int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
@@ -1359,12 +1482,7 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
     const bool want_feats = feats_out != nullptr;
     auto body = [&](cudaStream_t s) -> int {
         if (run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, h->ws_pooled, s)) return 1;
-        for (int i = 0; i < B; ++i) {
-            char* tok = static_cast<char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
-            if (run_projector(h, static_cast<char*>(h->ws_pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, s)) return 1;
-            if (run_gate(h, tok, h->gt_logits + 2 * i, s)) return 1;
-        }
-        return 0;
+        return run_proj_gate(h, h->ws_pooled, h->pj_toks, h->gt_logits, B, s);
     };
     if (c.use_graphs) {
         const int key = B | (want_feats ? 1 << 8 : 0) | static_cast<int>((h->kfilter & 0xFFFFu) << 9);
@@ -1415,6 +1533,8 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
         for (auto& vst : h->vit_streams) CUDA_OK(h, cudaStreamCreateWithPriority(&vst, cudaStreamNonBlocking, hi));
         h->n_lanes = std::max(1, std::min(kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : 4));
+        h->gate_batch = std::max(1, std::min(kGemvBatch, getenv("SMB_GATE_BATCH") ? atoi(getenv("SMB_GATE_BATCH")) : kGemvBatch));
+        if (h->gate_batch == 3) h->gate_batch = 2;   // groups must tile the ticket ring (8)
         CUDA_OK(h, cudaStreamCreateWithPriority(&h->gate_stream, cudaStreamNonBlocking, lo));
         CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         for (auto& e : h->ev_vit) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1423,8 +1543,8 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         h->pipe_init = true;
     }
     const long long tk = h->ticket;
-    const int lane = static_cast<int>(tk % h->n_lanes), slot = lane, ring = static_cast<int>(tk % kTicketRing);
-    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane], gs = h->gate_stream;
+    const int lane = static_cast<int>(tk % h->n_lanes), ring = static_cast<int>(tk % kTicketRing);
+    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane];
     struct LaneGuard {   // every exit path leaves lane 0 and the serial tile planner selected for the other entry points
         sm_handle* h; int div, ssm;
         ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; }
@@ -1438,58 +1558,48 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         h->plan_div = pdiv;
         h->split_sms = ssm;
     }
-    if (tk >= kTicketRing) CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));           // at most kTicketRing frames in flight
+    // the ring slot (events, pooled vector) of ticket tk - kTicketRing is reused: its gate must have been enqueued and finished
+    if (tk >= kTicketRing) {
+        if (h->first_pending <= tk - kTicketRing && pipe_flush_gate(h)) return 1;
+        CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));
+    }
     CUDA_OK(h, cudaEventRecord(h->ev_in, st));
     CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
-    if (tk >= h->n_lanes) CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_gate[(tk - h->n_lanes) % kTicketRing], 0));   // pooled[slot] has been consumed
     const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
     CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, vs));
     const bool want_feats = feats_out != nullptr;
-    void* pooled = h->ws_pooled2[slot];
+    void* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(ring) * c.max_frames * c.vit_hidden * h->esz;
     auto vit_body = [&](cudaStream_t s) -> int { return run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, pooled, s); };
-    auto gate_body = [&](cudaStream_t s) -> int {
-        const int saved_cap = h->gemv_grid_cap;
-        const bool saved_tma = h->gemv_tma;
-        if (h->bg_grid > 0) { h->gemv_grid_cap = h->bg_grid; h->gemv_tma = true; }   // "background" gate experiment
-        int rc = 0;
-        for (int i = 0; i < B && !rc; ++i) {
-            char* tok = static_cast<char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
-            rc = run_projector(h, static_cast<char*>(pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, s);
-            if (!rc) rc = run_gate(h, tok, h->gt_logits + 2 * i, s);
-        }
-        h->gemv_grid_cap = saved_cap;
-        h->gemv_tma = saved_tma;
-        return rc;
-    };
-    auto run_part = [&](int key, cudaStream_t s, auto&& body, const char* what) -> int {
-        if (!c.use_graphs) return body(s);
+    if (!c.use_graphs) {
+        if (vit_body(vs)) return 1;
+    } else {
+        const int key = B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (lane << 28) | (ring << 24) | static_cast<int>((h->kfilter & 0xFFFu) << 12);
         auto it = h->frame_graphs.find(key);
         if (it == h->frame_graphs.end()) {
-            if (body(s)) return 1;                       // real run: produces this call's outputs
-            CUDA_OK(h, cudaStreamSynchronize(s));
+            if (vit_body(vs)) return 1;                      // real run: produces this call's outputs
+            CUDA_OK(h, cudaStreamSynchronize(vs));
             cudaGraphExec_t ge;
             long long n = 0;
-            if (capture_graph(h, body, &ge, &n, what)) return 1;
+            if (capture_graph(h, vit_body, &ge, &n, "sm_frame_submit(tower)")) return 1;
             h->frame_graphs[key] = ge;
             h->frame_graph_launches[key] = n;
         } else {
-            CUDA_OK(h, cudaGraphLaunch(it->second, s));
+            CUDA_OK(h, cudaGraphLaunch(it->second, vs));
             h->launches += h->frame_graph_launches[key];
         }
-        return 0;
-    };
-    const int kf = static_cast<int>((h->kfilter & 0xFFFFu) << 12);
-    if (run_part(B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (lane << 28) | kf, vs, vit_body, "sm_frame_submit(tower)")) return 1;
+    }
     if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, vs));
-    CUDA_OK(h, cudaEventRecord(h->ev_vit[slot], vs));
-    CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[slot], 0));
-    if (run_part(B | (1 << 9) | (1 << 11) | (lane << 28) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
-    if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, gs));
-    if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, gs));
-    if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, gs));
-    CUDA_OK(h, cudaEventRecord(h->ev_gate[ring], gs));
+    CUDA_OK(h, cudaEventRecord(h->ev_vit[ring], vs));
+    // projector + gate: batched over up to gate_batch consecutive single-frame tickets (aligned groups, so a batch
+    // never wraps around the ring); multi-frame tickets are batched inside the call
+    if (h->n_pending == 0) h->first_pending = tk;
+    h->pend[h->n_pending++] = {toks_out, logits_out, logits_host, B};
     if (ticket_out) *ticket_out = tk;
     h->ticket = tk + 1;
+    const bool batchable = B == 1 && c.max_frames == 1 && h->gate_batch > 1;   // ring slots are then contiguous single vectors
+    if (!batchable || h->n_pending >= h->gate_batch || (tk + 1) % h->gate_batch == 0) {
+        if (pipe_flush_gate(h)) return 1;
+    }
     return 0;
 }
 
@@ -1498,6 +1608,7 @@ int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host) 
     if (ticket < 0 || ticket >= h->ticket || ticket + kTicketRing < h->ticket)
         return fail(h, "sm_frame_wait: ticket %lld is not in flight (next ticket %lld, ring of %d)", ticket, h->ticket, kTicketRing);
     cudaSetDevice(h->device);
+    if (h->n_pending > 0 && ticket >= h->first_pending && pipe_flush_gate(h)) return 1;   // its gate batch is still open
     cudaEvent_t ev = h->ev_gate[ticket % kTicketRing];
     if (stream != nullptr || !block_host) CUDA_OK(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
     if (block_host) CUDA_OK(h, cudaEventSynchronize(ev));

@@ -53,6 +53,10 @@ struct GemvArgs {
     const void* conv_b;    // T [d_inner]
     void* z_out;           // T [d_inner]
     int d_inner, d_conv;
+    // NV > 1 (template): the same weights against NV input vectors (consecutive frames of a chunk / of the frames in
+    // flight): every weight byte is streamed once for NV frames.  Element strides between the vectors:
+    long long x_stride, y_stride, resid_stride, z_stride;
+    int nv_host;   // host-side copy of NV (selects the template instance)
 };
 
 constexpr int kGemvThreads = 512;
@@ -81,11 +85,12 @@ __device__ __forceinline__ float dot8(const uint4& w, const T* xs) {
     return s;
 }
 
-template <typename T, int NMAT>
-__global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a) {
+template <typename T, int NMAT, int NV = 1>
+__global__ void __launch_bounds__(kGemvThreads, NV == 1 ? 2 : 1) gemv_kernel(const GemvArgs a) {
     extern __shared__ __align__(16) uint8_t gemv_smem[];
-    T* xs = reinterpret_cast<T*>(gemv_smem);                                   // [K]
-    float* part = reinterpret_cast<float*>(gemv_smem + ((a.K * 2 + 15) & ~15));  // [NMAT][rows][nseg]
+    const int xpitch = (a.K + 7) & ~7;                                          // elements per staged vector
+    T* xs = reinterpret_cast<T*>(gemv_smem);                                   // [NV][xpitch]
+    float* part = reinterpret_cast<float*>(gemv_smem + ((NV * xpitch * 2 + 15) & ~15));  // [NMAT][NV][rows][nseg]
     __shared__ float red[kGemvWarps * 2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
     const T* W1 = reinterpret_cast<const T*>(a.W1);
 
     // ---- issue the first item's weight loads before touching the input vector
-    constexpr int UNR = 4;  // 16-byte chunks in flight per matrix per lane per batch
+    constexpr int UNR = NV == 1 ? 4 : 8;  // 16-byte chunks in flight per matrix per lane per batch (NV > 1: one CTA per SM)
     uint4 wbuf[NMAT][UNR];
     int item = warp;
     auto issue = [&](int it, int batch) {
@@ -119,11 +124,14 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
     if (item < nitems) issue(item, 0);   // weights never depend on the previous kernel
     pdl_wait();
 
-    // ---- stage pro(x) in shared memory
-    {
-        const T* x0 = reinterpret_cast<const T*>(a.x0);
+    // ---- stage pro(x) in shared memory (one vector after the other)
+#pragma unroll 1
+    for (int v = 0; v < NV; ++v) {
+        const T* x0 = reinterpret_cast<const T*>(a.x0) + v * a.x_stride;
         const T* nw = reinterpret_cast<const T*>(a.nw);
         const T* nb = reinterpret_cast<const T*>(a.nb);
+        T* xs = reinterpret_cast<T*>(gemv_smem) + v * xpitch;   // shadows the base pointer: this vector's slot
+        if (v > 0) __syncthreads();                             // red[] of the previous vector has been consumed
         if (a.pro == PRO_PLAIN) {
             for (int k = threadIdx.x * 8; k < a.K; k += kGemvThreads * 8)
                 *reinterpret_cast<uint4*>(xs + k) = *reinterpret_cast<const uint4*>(x0 + k);
@@ -187,25 +195,36 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
         const int kbeg = seg * a.seg_len;
         const int kend = min(a.K, kbeg + a.seg_len);
         const int nbatch = (kend - kbeg + UNR * 256 - 1) / (UNR * 256);
-        float acc0 = 0.f, acc1 = 0.f;
+        float acc0[NV], acc1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { acc0[v] = 0.f; acc1[v] = 0.f; }
         for (int b = 0; b < nbatch; ++b) {
             if (b > 0) issue(item, b);
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 const int k = kbeg + (b * UNR + u) * 256 + lane * 8;
                 if (k < kend) {
-                    acc0 += dot8<T>(wbuf[0][u], xs + k);
-                    if (NMAT == 2) acc1 += dot8<T>(wbuf[1][u], xs + k);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        acc0[v] += dot8<T>(wbuf[0][u], xs + v * xpitch + k);
+                        if (NMAT == 2) acc1[v] += dot8<T>(wbuf[1][u], xs + v * xpitch + k);
+                    }
                 }
             }
         }
         const int next = item + kGemvWarps;
         if (next < nitems) issue(next, 0);  // keep HBM requests in flight across the reduction
-        acc0 = warp_sum(acc0);
-        if (NMAT == 2) acc1 = warp_sum(acc1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            acc0[v] = warp_sum(acc0[v]);
+            if (NMAT == 2) acc1[v] = warp_sum(acc1[v]);
+        }
         if (lane == 0) {
-            part[item] = acc0;
-            if (NMAT == 2) part[nitems + item] = acc1;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                part[(0 * NV + v) * nitems + item] = acc0[v];
+                if (NMAT == 2) part[(1 * NV + v) * nitems + item] = acc1[v];
+            }
         }
     }
     __syncthreads();
@@ -213,21 +232,23 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
     // ---- epilogue: one thread per row, fixed-order sum of the K-segment partials
     for (int r = threadIdx.x; r < nrows; r += kGemvThreads) {
         const int n = r0 + r;
+#pragma unroll 1
+        for (int v = 0; v < NV; ++v) {       // vectors in order: the Mamba conv window rolls once per frame
         float acc = 0.f, accb = 0.f;
         for (int s = 0; s < nseg; ++s) {
-            acc += part[r * nseg + s];
-            if (NMAT == 2) accb += part[nitems + r * nseg + s];
+            acc += part[(0 * NV + v) * nitems + r * nseg + s];
+            if (NMAT == 2) accb += part[(1 * NV + v) * nitems + r * nseg + s];
         }
         const T* bias = reinterpret_cast<const T*>(a.bias);
         if (bias != nullptr) acc += Cvt<T>::to_f(bias[n]);
-        T* y = reinterpret_cast<T*>(a.y);
-        T* resid = reinterpret_cast<T*>(a.resid);
+        T* y = reinterpret_cast<T*>(a.y) + v * a.y_stride;
+        T* resid = reinterpret_cast<T*>(a.resid) + v * a.resid_stride;
         switch (a.epi) {
             case GEPI_STORE: y[n] = Cvt<T>::from_f(acc); break;
             case GEPI_LEAKY: y[n] = Cvt<T>::from_f(leaky_relu_f(rnd<T>(acc))); break;
             case GEPI_RESID: resid[n] = Cvt<T>::from_f(Cvt<T>::to_f(resid[n]) + rnd<T>(acc)); break;
             case GEPI_ADD_TO: y[n] = Cvt<T>::from_f(Cvt<T>::to_f(resid[n]) + rnd<T>(acc)); break;
-            case GEPI_F32: reinterpret_cast<float*>(a.y)[n] = rnd<T>(acc); break;  // logits leave lm_head in T
+            case GEPI_F32: (reinterpret_cast<float*>(a.y) + v * a.y_stride)[n] = rnd<T>(acc); break;  // logits leave lm_head in T
             case GEPI_SWIGLU: {
                 const float g = rnd<T>(silu_f(rnd<T>(acc)));
                 y[n] = Cvt<T>::from_f(g * rnd<T>(accb));
@@ -251,11 +272,12 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvArgs a)
                     c = rnd<T>(c + Cvt<T>::to_f(reinterpret_cast<const T*>(a.conv_b)[n]));
                     y[n] = Cvt<T>::from_f(silu_f(c));
                 } else {
-                    reinterpret_cast<T*>(a.z_out)[n - a.d_inner] = Cvt<T>::from_f(acc);
+                    (reinterpret_cast<T*>(a.z_out) + v * a.z_stride)[n - a.d_inner] = Cvt<T>::from_f(acc);
                 }
                 break;
             }
         }
+        }   // v
     }
 }
 
@@ -277,6 +299,8 @@ struct ScanArgs {
     float* state;       // fp32 [d_inner][d_state]
     void* y;            // T [d_inner]
     int d_inner, dt_rank, d_state;
+    int nv;             // consecutive frames processed in order (xdb / x / z / y strided per frame)
+    long long xdb_stride, x_stride, z_stride, y_stride;
 };
 
 template <typename T>
@@ -284,42 +308,54 @@ __global__ void __launch_bounds__(256) mamba_scan_step_kernel(const ScanArgs a) 
     extern __shared__ __align__(16) uint8_t scan_smem[];
     pdl_trigger();
     pdl_wait();
-    T* xdb = reinterpret_cast<T*>(scan_smem);
-    const int nx = a.dt_rank + 2 * a.d_state;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) xdb[i] = reinterpret_cast<const T*>(a.xdb)[i];
+    T* xdb = reinterpret_cast<T*>(scan_smem);                 // [nv][nxp]
+    const int nx = a.dt_rank + 2 * a.d_state, nxp = (nx + 7) & ~7;
+    const int nv = max(1, a.nv);
+    for (int i = threadIdx.x; i < nx * nv; i += blockDim.x) {
+        const int v = i / nx, j = i % nx;
+        xdb[v * nxp + j] = reinterpret_cast<const T*>(a.xdb)[v * a.xdb_stride + j];
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int d = blockIdx.x * wpb + warp; d < a.d_inner; d += gridDim.x * wpb) {
         const T* w = reinterpret_cast<const T*>(a.W_dt) + static_cast<size_t>(d) * a.dt_rank;
-        float acc = 0.f;
-        for (int k = lane * 8; k < a.dt_rank; k += 256) {
-            if (k + 8 <= a.dt_rank) {
-                acc += dot8<T>(ldg_stream(w + k), xdb + k);
-            } else {
-                for (int j = k; j < a.dt_rank; ++j) acc += Cvt<T>::to_f(w[j]) * Cvt<T>::to_f(xdb[j]);
+        const float bdt = Cvt<T>::to_f(reinterpret_cast<const T*>(a.b_dt)[d]);
+        const float Dd = Cvt<T>::to_f(reinterpret_cast<const T*>(a.D)[d]);
+        // this lane's state element (d_state <= 32) stays in a register across the frames of the batch
+        const bool has_n = lane < a.d_state;
+        float* sp = a.state + static_cast<size_t>(d) * a.d_state + lane;
+        float hst = has_n ? *sp : 0.f;
+        const float A = has_n ? -__expf(Cvt<T>::to_f(reinterpret_cast<const T*>(a.A_log)[static_cast<size_t>(d) * a.d_state + lane])) : 0.f;
+        for (int v = 0; v < nv; ++v) {
+            const T* xv_db = xdb + v * nxp;
+            float acc = 0.f;
+            for (int k = lane * 8; k < a.dt_rank; k += 256) {
+                if (k + 8 <= a.dt_rank) {
+                    acc += dot8<T>(ldg_stream(w + k), xv_db + k);
+                } else {
+                    for (int j = k; j < a.dt_rank; ++j) acc += Cvt<T>::to_f(w[j]) * Cvt<T>::to_f(xv_db[j]);
+                }
+            }
+            acc = warp_sum(acc);
+            const float dtl = rnd<T>(acc) + bdt;
+            const float dt = dtl > 20.0f ? dtl : log1pf(__expf(dtl));  // F.softplus, threshold 20
+            const float xv = Cvt<T>::to_f(reinterpret_cast<const T*>(a.x)[v * a.x_stride + d]);
+            float contrib = 0.f;
+            if (has_n) {
+                const float Bn = Cvt<T>::to_f(xv_db[a.dt_rank + lane]);
+                const float Cn = Cvt<T>::to_f(xv_db[a.dt_rank + a.d_state + lane]);
+                hst = hst * __expf(dt * A) + dt * Bn * xv;
+                contrib = hst * Cn;
+            }
+            contrib = warp_sum(contrib);
+            if (lane == 0) {
+                const float zv = Cvt<T>::to_f(reinterpret_cast<const T*>(a.z)[v * a.z_stride + d]);
+                const float yv = (contrib + Dd * xv) * silu_f(zv);
+                reinterpret_cast<T*>(a.y)[v * a.y_stride + d] = Cvt<T>::from_f(yv);
             }
         }
-        acc = warp_sum(acc);
-        const float dtl = rnd<T>(acc) + Cvt<T>::to_f(reinterpret_cast<const T*>(a.b_dt)[d]);
-        const float dt = dtl > 20.0f ? dtl : log1pf(__expf(dtl));  // F.softplus, threshold 20
-        const float xv = Cvt<T>::to_f(reinterpret_cast<const T*>(a.x)[d]);
-        float contrib = 0.f;
-        for (int n = lane; n < a.d_state; n += 32) {
-            const float A = -__expf(Cvt<T>::to_f(reinterpret_cast<const T*>(a.A_log)[static_cast<size_t>(d) * a.d_state + n]));
-            const float Bn = Cvt<T>::to_f(xdb[a.dt_rank + n]);
-            const float Cn = Cvt<T>::to_f(xdb[a.dt_rank + a.d_state + n]);
-            float* sp = a.state + static_cast<size_t>(d) * a.d_state + n;
-            const float h = (*sp) * __expf(dt * A) + dt * Bn * xv;
-            *sp = h;
-            contrib += h * Cn;
-        }
-        contrib = warp_sum(contrib);
-        if (lane == 0) {
-            const float zv = Cvt<T>::to_f(reinterpret_cast<const T*>(a.z)[d]);
-            const float yv = (contrib + Cvt<T>::to_f(reinterpret_cast<const T*>(a.D)[d]) * xv) * silu_f(zv);
-            reinterpret_cast<T*>(a.y)[d] = Cvt<T>::from_f(yv);
-        }
+        if (has_n) *sp = hst;
     }
 }
 
