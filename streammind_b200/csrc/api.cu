@@ -58,7 +58,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 }  // namespace
 
-constexpr int kMaxLanes = 4;      // concurrent vision towers of the pipelined path
+constexpr int kMaxLanes = 8;      // concurrent vision towers of the pipelined path (SMB_LANES overrides)
 constexpr int kTicketRing = 8;    // frames in flight (sm_frame_submit tickets)
 
 struct sm_handle {
@@ -128,9 +128,11 @@ struct sm_handle {
     int dec_splits = 16;
     // ---- pipelined frame path (sm_frame_submit): tower on vit_stream, projector + gate on gate_stream
     bool pipe_init = false;
-    int n_lanes = 4;                   // towers of consecutive tickets run on this many streams / activation sets (<= kMaxLanes)
+    int n_lanes = 8;                   // towers of consecutive tickets run on this many streams / activation sets (<= kMaxLanes)
     int plan_div = 2;                  // GEMM tile planner: accept the widest tile that yields >= num_sms / plan_div CTAs
     int split_sms = 0;                 // SMs a split-K GEMM may fill (0 = all)
+    int max_split = 4;                 // split-K cap of the residual GEMMs (serial path: fill the SMs; pipelined: 1)
+    int gemm_pre = 1;                  // GemmArgs::pre_weights
     cudaStream_t vit_streams[kMaxLanes] = {}, gate_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_vit[kTicketRing] = {}, ev_gate[kTicketRing] = {};
     long long ticket = 0;
@@ -363,10 +365,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
         a.dbg_mode = dm;
     }
-    {
-        static const int pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
-        a.pre_weights = pre;
-    }
+    a.pre_weights = h->gemm_pre;
     a.dbg = h->gemm_dbg;
     if (h->gemm_dbg) h->gemm_dbg += 8;   // one 8-slot record per launch
     const CUtensorMap* tc = ta;  // placeholder when unused
@@ -403,7 +402,7 @@ int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feat
 // every MMA instruction costs >= ~105 clocks whatever its N (profiles/r01_gemm_phases.md), so a CTA's time is
 // ~ k-blocks x 250 ns and the only way to shorten it is to give each CTA fewer k-blocks.
 int splitk_factor(const sm_handle* h, int tokens, int feats, int K, bool bm2 = false) {
-    static const int max_split = getenv("SMB_SPLITK") ? atoi(getenv("SMB_SPLITK")) : 4;
+    const int max_split = h->max_split;
     const int split_sms = h->split_sms;
     const int tiles = bm2 ? ((tokens + 255) / 256) * ((feats + 255) / 256) : ((tokens + 127) / 128) * ((feats + 127) / 128);
     const int kb = (K + kGemmBK - 1) / kGemmBK;
@@ -1119,6 +1118,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
+    h->max_split = getenv("SMB_SPLITK") ? std::max(1, atoi(getenv("SMB_SPLITK"))) : 4;
+    h->gemm_pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
     // experimental bulk-copy + mma.sync GEMV (gemv_tma.cuh): not faster than gemv.cuh on B200 (both sit at the same
     // ~48 GB/s-per-SM bulk/HBM limit) and 1 fp16 ulp off the oracle on the gate logits -> off unless asked for
     h->gemv_tma = getenv("SMB_GEMV_TMA") ? atoi(getenv("SMB_GEMV_TMA")) != 0 : false;
@@ -1532,7 +1533,7 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         int lo = 0, hi = 0;
         CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
         for (auto& vst : h->vit_streams) CUDA_OK(h, cudaStreamCreateWithPriority(&vst, cudaStreamNonBlocking, hi));
-        h->n_lanes = std::max(1, std::min(kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : 4));
+        h->n_lanes = std::max(1, std::min(kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : 8));
         h->gate_batch = std::max(1, std::min(kGemvBatch, getenv("SMB_GATE_BATCH") ? atoi(getenv("SMB_GATE_BATCH")) : kGemvBatch));
         if (h->gate_batch == 3) h->gate_batch = 2;   // groups must tile the ticket ring (8)
         CUDA_OK(h, cudaStreamCreateWithPriority(&h->gate_stream, cudaStreamNonBlocking, lo));
@@ -1546,17 +1547,23 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
     const int lane = static_cast<int>(tk % h->n_lanes), ring = static_cast<int>(tk % kTicketRing);
     cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane];
     struct LaneGuard {   // every exit path leaves lane 0 and the serial tile planner selected for the other entry points
-        sm_handle* h; int div, ssm;
-        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; }
-    } lane_guard{h, h->plan_div, h->split_sms};
+        sm_handle* h; int div, ssm, msp, pre;
+        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; }
+    } lane_guard{h, h->plan_div, h->split_sms, h->max_split, h->gemm_pre};
     select_lane(h, lane);
     // With several towers in flight the SMs are kept busy by the other frames, so a GEMM is planned for bytes per
     // flop (wide tiles, fewer CTAs, less split-K) instead of for its own latency (measured: +6 % at 2 lanes).
     if (h->n_lanes > 1) {
-        static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 4;
+        // Measured at 4 lanes + gate batching (frames/s): split-K 4 -> 894, 2 -> 955, none -> 1025 (fp32 partials and
+        // their reduction cost more bytes than the idle SMs are worth once other frames fill them).
+        static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 8;
         static const int ssm = getenv("SMB_SPLIT_SMS") ? atoi(getenv("SMB_SPLIT_SMS")) : 0;
+        static const int msp = getenv("SMB_PIPE_SPLITK") ? std::max(1, atoi(getenv("SMB_PIPE_SPLITK"))) : 1;
+        static const int pre = getenv("SMB_PIPE_PRE") ? atoi(getenv("SMB_PIPE_PRE")) : 0;
         h->plan_div = pdiv;
         h->split_sms = ssm;
+        h->max_split = msp;
+        h->gemm_pre = pre;
     }
     // the ring slot (events, pooled vector) of ticket tk - kTicketRing is reused: its gate must have been enqueued and finished
     if (tk >= kTicketRing) {
