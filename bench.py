@@ -263,52 +263,81 @@ def run_ours(args):
 
     if rank == 0:
         peaks = _peaks()
-        # ---- per-kernel-class pass: the SAME captured step, restricted to one kernel class at a time
-        # (sm_debug_kernel_filter), replayed over the stream and timed with CUDA events on the launch
-        # stream.  Unlike event pairs around single launches this adds no per-launch measurement cost.
-        def class_ms_per_frame(classes):
+        # ---- per-kernel-class pass: the SAME step (same graphs, same tile plans, same number of frames in flight),
+        # restricted to one kernel class at a time (sm_debug_kernel_filter) and timed with CUDA events on the
+        # launch stream.  In the pipelined mode several towers run concurrently, so a class's ms/frame is its
+        # share of the machine's time per frame (launch durations overlap); per-launch latency is reported from
+        # the serial pass below.
+        def class_ms_per_frame(classes, fn):
             eng.kernel_filter(classes)
             eng.reset_stream()
             for _ in range(2):
-                step_serial()
+                fn()
             torch.cuda.synchronize()
             eng.launch_count(reset=True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(2):
-                step_serial()
+                fn()
             e1.record()
             torch.cuda.synchronize()
             n = eng.launch_count(reset=True)
             eng.kernel_filter(None)
             return e0.elapsed_time(e1) / (2 * n_frames), n / (2 * n_frames)
-        prof = {}
+        prof, prof_serial = {}, {}
         for cls in Engine.KERNEL_CLASSES:
-            ms_pf, n_pf = class_ms_per_frame([cls])
-            prof[cls] = (ms_pf, n_pf)
+            prof[cls] = class_ms_per_frame([cls], step_device)
+        for cls in ("gemm_tc_kernel", "gemv_kernel"):
+            prof_serial[cls] = class_ms_per_frame([cls], step_serial) if pipelined else prof[cls]
         eng.reset_stream()
-        nprof = 1
+        if pipelined:                       # rank-local timing (no collectives inside the rank-0 block)
+            step_serial(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_serial(); e1.record(); torch.cuda.synchronize()
+            serial_ms = e0.elapsed_time(e1)
+        else:
+            serial_ms = ms / args.steps
+        eng.reset_stream()
         tot_ms = sum(v[0] for v in prof.values())
         per_frame = {k: {"ms_per_frame": v[0], "share_of_class_sum": v[0] / tot_ms} for k, v in prof.items()}
-        launches_pf = {"gemm_tc_kernel": 93, "gemv_kernel": 22}
+        frame_ms = ms / args.steps / n_frames
+        gate_batch = (int(os.environ.get("SMB_GATE_BATCH", "4")) if (pipelined and chunk == 1) else min(4, chunk))
         gemm, gemv = prof.get("gemm_tc_kernel", (0, 1)), prof.get("gemv_kernel", (0, 1))
-        gemm_tf = VIT_GFLOP_PER_FRAME * (334.65 / 366.0) * nprof / gemm[0] if gemm[0] else 0.0   # GEMM share of ViT flops
-        gemv_gbs = (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) * nprof / gemv[0] if gemv[0] else 0.0
+        gemm_gflop = VIT_GFLOP_PER_FRAME * (334.65 / 366.0)                     # GEMM share of the ViT flops
+        gemv_mb_streamed = (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) / gate_batch   # weights are streamed once per batch
+        gemm_tf = gemm_gflop / gemm[0] if gemm[0] else 0.0
+        gemv_gbs = gemv_mb_streamed / gemv[0] if gemv[0] else 0.0
         roof_gemv = {"kernel": "gemv_kernel", "bound": "hbm", "achieved": gemv_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": gemv_gbs / peaks["hbm"], "traffic": None,
-                     "share_of_step": gemv[0] / (ms / args.steps / n_frames),
-                     "avg_launch_us": 1e3 * gemv[0] / launches_pf["gemv_kernel"],
-                     "algorithmic_bytes_per_frame": (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) * 1e6}
+                     "frac": gemv_gbs / peaks["hbm"], "traffic": 234.99e6,
+                     "traffic_note": "dram read bytes of the largest launch (gate|up of one gate layer, 2 x 14336 x 4096 x 2 B = "
+                                     "234.9 MB algorithmic, shared by 4 frames) from ncu --set full, profiles/r01_ncu_pipelined.md: no re-reads",
+                     "share_of_step": gemv[0] / frame_ms,
+                     "avg_launch_us": 1e3 * gemv[0] * gate_batch / 22.0,
+                     "launches_per_weight_pass": 22,
+                     "frames_per_weight_pass": gate_batch,
+                     "bytes_streamed_per_frame": gemv_mb_streamed * 1e6,
+                     "algorithmic_bytes_per_frame_unbatched": (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) * 1e6,
+                     "serial_b1": {"ms_per_frame": prof_serial["gemv_kernel"][0],
+                                   "achieved_GBps": (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) / prof_serial["gemv_kernel"][0]}}
         roof_gemm = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"],
-                     "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"], "traffic": None,
-                     "share_of_step": gemm[0] / (ms / args.steps / n_frames),
-                     "avg_launch_us": 1e3 * gemm[0] / launches_pf["gemm_tc_kernel"],
-                     "algorithmic_flops_per_frame": VIT_GFLOP_PER_FRAME * (334.65 / 366.0) * 1e9}
+                     "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"], "traffic": 9.04e6,
+                     "traffic_note": "mean dram bytes per launch of the 4 per-layer GEMMs with the pipelined tile plans (ncu --set "
+                                     "full, profiles/r01_ncu_pipelined.md: qkv 7.56, out 4.55, fc1 9.67, fc2 14.39 MB) vs 6.3 MB of "
+                                     "weights per launch on average: weights are read once, activations mostly from L2",
+                     "share_of_step": gemm[0] / frame_ms,
+                     "avg_launch_us": 1e3 * prof_serial["gemm_tc_kernel"][0] / 93.0,
+                     "launches_per_frame": 93,
+                     "algorithmic_flops_per_frame": gemm_gflop * 1e9,
+                     "note": "achieved = GEMM flops per frame / the GEMM class's machine time per frame with all lanes in "
+                             "flight; avg_launch_us is the latency of one launch in the serial B=1 pass",
+                     "serial_b1": {"ms_per_frame": prof_serial["gemm_tc_kernel"][0],
+                                   "achieved_TFLOPs": gemm_gflop / prof_serial["gemm_tc_kernel"][0]}}
         dominant, secondary = (roof_gemm, roof_gemv) if gemm[0] >= gemv[0] else (roof_gemv, roof_gemm)
         dominant["peak_source"] = secondary["peak_source"] = peaks["source"]
-        # frame-level roofline: streaming B=1 is HBM-bound by the weights re-read per frame
-        frame_roof_ms = max(VIT_GFLOP_PER_FRAME / peaks["tf_sustained"],
-                            (578.8 + GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) / peaks["hbm"]) if chunk == 1 else None
+        # frame-level roofline (with the gate weights shared by gate_batch frames)
+        t_tensor = VIT_GFLOP_PER_FRAME / peaks["tf_sustained"]
+        t_hbm = (578.8 + gemv_mb_streamed) / peaks["hbm"]
+        frame_roof_ms = max(t_tensor, t_hbm)
 
         # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
         cpu = None
@@ -339,9 +368,12 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": dominant,
             "roofline_secondary": secondary,
-            "frame_roofline": {"ms_per_frame_at_peak": frame_roof_ms,
-                               "frac": (frame_roof_ms / (ms / args.steps / n_frames)) if frame_roof_ms else None,
-                               "note": "serial per-frame bound max(tensor, HBM) at streaming B=1"},
+            "frame_roofline": {"ms_per_frame_at_peak": frame_roof_ms, "tensor_ms": t_tensor, "hbm_ms": t_hbm,
+                               "frac": frame_roof_ms / frame_ms,
+                               "note": "per-frame bound max(tensor: 366 GFLOP of ViT, HBM: ViT weights once per frame + "
+                                       "projector/gate weights once per gate_batch frames) at the measured peaks"},
+            "serial_b1": {"value": world * n_frames / (serial_ms / 1e3), "unit": "frames/s", "measured_on": "rank 0",
+                          "note": "same stream through the serial sm_frame_step (one frame in flight, no batching)"},
             "kernel_breakdown": per_frame,
             "cpu_baseline": cpu,
             "gate_fire_rate": sum(preds) / max(1, len(preds)),
