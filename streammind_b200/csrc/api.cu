@@ -439,21 +439,25 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (!kon(h, KC_GEMV)) return 0;
     if (h->gemv_tma && a.nv_host <= 1 && gemv_tma_supported(a.K)) return launch_gemv_tma_t<T>(h, a, nmat, st);
     const int nv = std::max(1, a.nv_host);
+    static const bool use_seg = getenv("SMB_GEMV_SEG") ? atoi(getenv("SMB_GEMV_SEG")) != 0 : false;   // measured slower (latency-bound at 1 CTA/SM): opt-in
+    const bool seg_kernel = nv > 1 && use_seg;      // segment-stationary batched kernel (gemv_seg_kernel)
+    const int nvt = nv <= 1 ? 1 : (seg_kernel ? (nv <= 2 ? 2 : 4) : nv);
     a.seg_len = nv == 1 ? 1024 : 2048;
     static const int grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;   // experiment: background-sized grids
     int grid = std::min(a.N, grid_cap > 0 ? grid_cap : (nv == 1 ? 2 : 1) * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;
     grid = (a.N + rows_per_cta - 1) / rows_per_cta;
-    const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
+    const int nseg = seg_kernel ? (a.K + kGemvSeg - 1) / kGemvSeg : (a.K + a.seg_len - 1) / a.seg_len;
     const int xpitch = (a.K + 7) & ~7;
-    const size_t smem = ((static_cast<size_t>(nv) * xpitch * 2 + 15) & ~size_t(15)) +
-                        static_cast<size_t>(nmat) * nv * rows_per_cta * nseg * sizeof(float);
+    const size_t smem = ((static_cast<size_t>(nvt) * xpitch * 2 + 15) & ~size_t(15)) +
+                        static_cast<size_t>(nmat) * nvt * rows_per_cta * nseg * sizeof(float);
     if (smem > (nv == 1 ? 100u : 200u) * 1024) return fail(h, "gemv: K=%d x %d vectors too large for the staging buffer", a.K, nv);
     {
         ProfScope ps(h, KC_GEMV, st);
         const dim3 g(grid), b(kGemvThreads);
 #define SMB_GEMV_CASE(NM, NVV) CUDA_OK(h, launch_pdl(h, gemv_kernel<T, NM, NVV>, g, b, smem, st, a))
-        switch (nmat * 10 + nv) {
+#define SMB_GEMV_SEG_CASE(NM, NVV) CUDA_OK(h, launch_pdl(h, gemv_seg_kernel<T, NM, NVV>, g, b, smem, st, a, nv))
+        switch ((seg_kernel ? 100 : 0) + nmat * 10 + nvt) {
             case 11: SMB_GEMV_CASE(1, 1); break;
             case 12: SMB_GEMV_CASE(1, 2); break;
             case 13: SMB_GEMV_CASE(1, 3); break;
@@ -462,9 +466,14 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
             case 22: SMB_GEMV_CASE(2, 2); break;
             case 23: SMB_GEMV_CASE(2, 3); break;
             case 24: SMB_GEMV_CASE(2, 4); break;
+            case 112: SMB_GEMV_SEG_CASE(1, 2); break;
+            case 114: SMB_GEMV_SEG_CASE(1, 4); break;
+            case 122: SMB_GEMV_SEG_CASE(2, 2); break;
+            case 124: SMB_GEMV_SEG_CASE(2, 4); break;
             default: return fail(h, "gemv: %d matrices x %d vectors not instantiated", nmat, nv);
         }
 #undef SMB_GEMV_CASE
+#undef SMB_GEMV_SEG_CASE
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -519,6 +528,8 @@ int init_kernel_attrs_t(sm_handle* h) {
         CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 2>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 3>));
         CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 4>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 2>));
         CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 3>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 4>));
+        CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 1, 2>)); CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 1, 4>));
+        CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 2, 2>)); CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 2, 4>));
     }
     CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
