@@ -102,6 +102,10 @@ struct sm_handle {
     std::map<int, MegaPlan> mega_plans;
     unsigned int* mega_sync = nullptr;
     long long* mega_dbg = nullptr;
+    // persistent GEMM launches (one vit_mega_kernel op per launch: tile loop, double-buffered accumulator)
+    struct PGemm { MegaOp* d_op = nullptr; CUtensorMap* d_maps = nullptr; int tiles = 0; };
+    std::map<std::tuple<const void*, const void*, const void*, int, int, int>, PGemm> pgemms;
+    int pgemm = 0;        // > 0: tiles per CTA of the persistent GEMM (pipelined path), 0: one tile per CTA (gemm_tc_kernel)
     int mega_mode = 2;   // 0 = one kernel per op (round-1 path), 1 = persistent kernel, attention as separate launches, 2 = one launch
     // ---- projector
     int d_inner = 0, dt_rank = 0;
@@ -125,7 +129,7 @@ struct sm_handle {
     float *lw_logits = nullptr, *lw_part = nullptr;
     int *d_pos = nullptr, *d_tok = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_done = nullptr, *d_stop = nullptr;
     int kv_len = 0;
-    int dec_splits = 16;
+    int dec_splits = 64;   // KV slices per kv head of the decode attention (SMB_DEC_SPLITS); measured at ctx 2k: 16 -> 280, 32 -> 302, 64 -> 305 tokens/s
     // ---- pipelined frame path (sm_frame_submit): tower on vit_stream, projector + gate on gate_stream
     bool pipe_init = false;
     int n_lanes = 8;                   // towers of consecutive tickets run on this many streams / activation sets (<= kMaxLanes)
@@ -390,9 +394,58 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     return 0;
 }
 
+// One GEMM as a persistent launch of vit_mega_kernel (single op): G CTAs loop over the 128 x bn tiles, the epilogue
+// of tile i overlaps the mainloop of tile i+1 (two TMEM accumulators) and barriers / TMEM are set up once per CTA.
+template <typename T>
+int launch_gemm_persistent_t(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias,
+                             void* out, int ldo, int epi, int bn, cudaStream_t st) {
+    if (!kon(h, KC_GEMM)) return 0;
+    auto key = std::make_tuple(x, w, static_cast<const void*>(out), tokens, epi, bn);
+    auto it = h->pgemms.find(key);
+    if (it == h->pgemms.end()) {
+        if (h->capturing) return fail(h, "persistent gemm: plans must be built outside graph capture");
+        const int w_kb = (K + 63) / 64;
+        const CUtensorMap* ta = get_tmap(h, x, tokens, K, kGemmBM);
+        const CUtensorMap* tb = get_tmap(h, w, ((feats + 127) / 128) * w_kb * 128, kGemmBK, kGemmBM);
+        if (!ta || !tb) return 1;
+        CUtensorMap maps[2] = {*ta, *tb};
+        MegaOp o{};
+        o.type = MOP_GEMM; o.map_a = 0; o.map_b = 1; o.M = tokens; o.N = feats; o.K = K; o.bn = bn; o.split_k = 1; o.epi = epi;
+        o.w_kb = w_kb; o.w = w; o.bias = bias; o.out = out; o.ldo = ldo; o.split_stride = 0;
+        sm_handle::PGemm pg;
+        pg.d_op = static_cast<MegaOp*>(dalloc(h, sizeof(MegaOp)));
+        pg.d_maps = static_cast<CUtensorMap*>(dalloc(h, sizeof(maps)));
+        if (!pg.d_op || !pg.d_maps) return fail(h, "persistent gemm: out of device memory");
+        CUDA_OK(h, cudaMemcpy(pg.d_op, &o, sizeof o, cudaMemcpyHostToDevice));
+        CUDA_OK(h, cudaMemcpy(pg.d_maps, maps, sizeof maps, cudaMemcpyHostToDevice));
+        pg.tiles = ((tokens + 127) / 128) * (feats / bn);
+        it = h->pgemms.emplace(key, pg).first;
+    }
+    const sm_handle::PGemm& pg = it->second;
+    const int G = std::max(1, std::min(h->num_sms, (pg.tiles + h->pgemm - 1) / h->pgemm));
+    MegaParams p{};
+    p.ops = pg.d_op; p.op_begin = 0; p.op_end = 1; p.maps = pg.d_maps; p.sync = h->mega_sync; p.single = 1; p.dbg = nullptr;
+    {
+        ProfScope ps(h, KC_GEMM, st);
+        CUDA_OK(h, launch_ex(h, vit_mega_kernel<T>, dim3(G), dim3(kGemmThreads), mega_smem_bytes(), st, 1, p));
+    }
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
                 int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false,
                 int split_k = 1) {
+    if (h->pgemm > 0 && w_tiled && split_k == 1 && force_swap < 0 && force_bn == 0 && feats % 128 == 0 && ldo == feats &&
+        h->mega_sync != nullptr && tokens > 64) {
+        const GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div, 1);
+        if (!p.swap && !p.bm2 && (p.bn == 128 || p.bn == 256)) {
+            if (h->cfg.dtype == SM_DTYPE_BF16)
+                return launch_gemm_persistent_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, p.bn, st);
+            return launch_gemm_persistent_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, p.bn, st);
+        }
+    }
     if (h->cfg.dtype == SM_DTYPE_BF16)
         return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
     return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
@@ -1129,6 +1182,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
+    if (getenv("SMB_DEC_SPLITS")) h->dec_splits = std::max(1, std::min(128, atoi(getenv("SMB_DEC_SPLITS"))));
     h->max_split = getenv("SMB_SPLITK") ? std::max(1, atoi(getenv("SMB_SPLITK"))) : 4;
     h->gemm_pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
     // experimental bulk-copy + mma.sync GEMV (gemv_tma.cuh): not faster than gemv.cuh on B200 (both sit at the same
@@ -1558,9 +1612,9 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
     const int lane = static_cast<int>(tk % h->n_lanes), ring = static_cast<int>(tk % kTicketRing);
     cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane];
     struct LaneGuard {   // every exit path leaves lane 0 and the serial tile planner selected for the other entry points
-        sm_handle* h; int div, ssm, msp, pre;
-        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; }
-    } lane_guard{h, h->plan_div, h->split_sms, h->max_split, h->gemm_pre};
+        sm_handle* h; int div, ssm, msp, pre, pg;
+        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; h->pgemm = pg; }
+    } lane_guard{h, h->plan_div, h->split_sms, h->max_split, h->gemm_pre, h->pgemm};
     select_lane(h, lane);
     // With several towers in flight the SMs are kept busy by the other frames, so a GEMM is planned for bytes per
     // flop (wide tiles, fewer CTAs, less split-K) instead of for its own latency (measured: +6 % at 2 lanes).
@@ -1575,6 +1629,8 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         h->split_sms = ssm;
         h->max_split = msp;
         h->gemm_pre = pre;
+        static const int pgm = getenv("SMB_PGEMM") ? std::max(0, atoi(getenv("SMB_PGEMM"))) : 0;
+        h->pgemm = pgm;
     }
     // the ring slot (events, pooled vector) of ticket tk - kTicketRing is reused: its gate must have been enqueued and finished
     if (tk >= kTicketRing) {

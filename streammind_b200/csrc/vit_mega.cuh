@@ -69,6 +69,7 @@ struct MegaParams {
     int op_begin, op_end;
     const CUtensorMap* maps;
     unsigned int* sync;   // [0] = barrier arrivals of this launch, [1] = exited CTAs (the last one zeroes both)
+    int single;           // 1: one stand-alone GEMM op per launch (persistent GEMM): no grid barrier, no exit bookkeeping
     long long* dbg;       // optional trace, 4 slots per op: max over CTAs of [barrier passed, work done, arrived] (globaltimer ns)
 };
 
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) vit_mega_kernel(const MegaPar
             const int type = gop.type;
             const MegaShape op = mega_shape(gop);
             // pull this op's weights towards L2 before waiting for the previous op to finish everywhere
-            if (type == MOP_GEMM) {
+            if (type == MOP_GEMM && !P.single) {
                 const char* wbase = reinterpret_cast<const char*>(gop.w);
                 const int ntl = mega_ntiles(op);
                 for (int t = blockIdx.x; t < ntl; t += G) {
@@ -421,12 +422,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) vit_mega_kernel(const MegaPar
                     const int nchunk = BN / 32;
                     const int nmine = nchunk > chalf ? (nchunk - chalf + 1) / 2 : 0;
                     uint32_t rbA[32], rbB[32];
-                    const uint4 xr[4] = {};
+                    const T* out_t = reinterpret_cast<const T*>(ga.out);
                     auto process = [&](int c, const uint32_t (&rb)[32]) {
                         if (!a_ok) return;
+                        uint4 xr[4] = {};
+                        if (epi == EPI_RESIDUAL) {   // in-place residual stream: this thread's 32 columns of its row
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (b0 + c * 32 + q * 8 < op.N && c * 32 + q * 8 < BN)
+                                    xr[q] = *reinterpret_cast<const uint4*>(out_t + static_cast<size_t>(a_row) * ga.ldo + b0 + c * 32 + q * 8);
+                        }
                         switch (epi) {
                             case EPI_STORE: epi_chunk<T, false, EPI_STORE, false>(cx, c * 32, rb, xr); break;
                             case EPI_QUICK_GELU: epi_chunk<T, false, EPI_QUICK_GELU, false>(cx, c * 32, rb, xr); break;
+                            case EPI_RESIDUAL: epi_chunk<T, false, EPI_RESIDUAL, false>(cx, c * 32, rb, xr); break;
                             default: epi_chunk<T, false, EPI_STORE_F32, false>(cx, c * 32, rb, xr); break;
                         }
                     };
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) vit_mega_kernel(const MegaPar
                     named_bar_sync(kMegaEpiBar, kGemmEpiThreads);   // smem of this item is free again
                 }
             }
+            if (P.single) continue;
             // ---- this CTA's part of the op is done and visible: arrive on the grid barrier
             if (P.dbg && et == 0) atomicMax(reinterpret_cast<unsigned long long*>(P.dbg + 4 * oi + 1), static_cast<unsigned long long>(gtimer()));
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) vit_mega_kernel(const MegaPar
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !P.single) {
         const unsigned int old = atomicAdd(P.sync + 1, 1u);
         if (old == G - 1) {   // every CTA is past its last barrier wait: clean up for the next launch
             P.sync[0] = 0;
