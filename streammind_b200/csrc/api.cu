@@ -1149,6 +1149,15 @@ int pipe_flush_gate(sm_handle* h) {
     return 0;
 }
 
+// The serial entry points share the stream state (Mamba conv / SSM state, gate scratch) with the pipelined path:
+// close the open gate batch and order the caller's stream after the last pipelined gate before touching it.
+int pipe_join(sm_handle* h, cudaStream_t st) {
+    if (!h->pipe_init || h->ticket == 0) return 0;
+    if (pipe_flush_gate(h)) return 1;
+    CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_gate[(h->ticket - 1) % kTicketRing], 0));
+    return 0;
+}
+
 }  // namespace
 
 // =========================================================================================== C ABI
@@ -1503,6 +1512,7 @@ int sm_vit_encode(sm_handle* h, const void* pixels, int B, void* feats_out, void
     if (!h || h->cfg.vit_layers <= 0) return fail(h, "sm_vit_encode: vision tower not configured");
     if (B < 1 || B > h->cfg.max_frames) return fail(h, "sm_vit_encode: B=%d outside [1, max_frames=%d]", B, h->cfg.max_frames);
     cudaSetDevice(h->device);
+    if (pipe_join(h, static_cast<cudaStream_t>(stream))) return 1;
     return run_vit(h, pixels, B, feats_out, pooled_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -1521,6 +1531,7 @@ int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, v
 int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, void* stream) {
     if (!h || h->cfg.proj_d_model <= 0) return fail(h, "sm_projector_step: projector not configured");
     cudaSetDevice(h->device);
+    if (pipe_join(h, static_cast<cudaStream_t>(stream))) return 1;
     for (int i = 0; i < n; i += kGemvBatch) {
         const char* src = static_cast<const char*>(pooled) + static_cast<size_t>(i) * h->cfg.vit_hidden * h->esz;
         char* dst = static_cast<char*>(tok_out) + static_cast<size_t>(i) * h->cfg.proj_d_model * h->esz;
@@ -1532,6 +1543,7 @@ int sm_projector_step(sm_handle* h, const void* pooled, int n, void* tok_out, vo
 int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream) {
     if (!h || h->cfg.gate_layers <= 0) return fail(h, "sm_gate_score: gate not configured");
     cudaSetDevice(h->device);
+    if (pipe_join(h, static_cast<cudaStream_t>(stream))) return 1;
     return run_gate(h, tok, logits_out, 1, static_cast<cudaStream_t>(stream));
 }
 
@@ -1542,6 +1554,7 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
     if (B < 1 || B > h->cfg.max_frames) return fail(h, "sm_frame_step: B=%d outside [1, max_frames=%d]", B, h->cfg.max_frames);
     cudaSetDevice(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pipe_join(h, st)) return 1;
     const sm_config& c = h->cfg;
     const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
     CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
@@ -1639,6 +1652,7 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
     }
     CUDA_OK(h, cudaEventRecord(h->ev_in, st));
     CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
+    if (h->n_pending == 0) CUDA_OK(h, cudaStreamWaitEvent(h->gate_stream, h->ev_in, 0));   // ... and earlier serial calls on it are ordered before this gate batch
     const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
     CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, vs));
     const bool want_feats = feats_out != nullptr;

@@ -221,3 +221,28 @@ def test_pipelined_and_persistent_full_size_fp16(built_library, monkeypatch):
         check_close(f"persistent-kernel features {t}", f2, ref[t][0], 4e-3)  # two valid fp16 paths: noise floor ~1.6e-3
         check_close(f"persistent-kernel logits {t}", lg2, ref[t][2], 8e-3)
     eng2.close()
+
+
+def test_serial_and_pipelined_calls_interleave(built_library):
+    """The serial entry points and the pipelined path share one stream state: mixing them must keep frame order."""
+    dt = torch.float16
+    cfg = engine_config(dt, llm_layers=0, max_frames=1, use_graphs=True)
+    sd = make_weights(cfg)
+    eng = build_engine(cfg, sd)
+    frames = synth.make_frames(0, 0, 10, cfg.vit_image, dtype=dt).cuda()
+    ref = torch.cat([eng.frame_step(frames[t:t + 1])[2] for t in range(10)])
+    torch.cuda.synchronize()
+    eng.reset_stream()
+    got = []
+    tk = [eng.frame_submit(frames[t:t + 1], want_device_outputs=True) for t in range(3)]        # open batch of 3
+    got += [x[3] for x in tk]
+    got.append(eng.frame_step(frames[3:4])[2])                                                  # serial call joins first
+    tk = [eng.frame_submit(frames[t:t + 1], want_device_outputs=True) for t in range(4, 9)]     # full batch + 1
+    got += [x[3] for x in tk]
+    _, pooled = eng.vit_encode(frames[9:10], want_feats=False)                                  # component hooks join too
+    tok = eng.projector_step(pooled)
+    got.append(eng.gate_score(tok[0]).reshape(1, 2))
+    eng.frame_wait(tk[-1][0], block=True)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(got), ref)
+    eng.close()
