@@ -356,7 +356,8 @@ def run_ours(args):
                                    f"(23 layers) + Mamba projector step + 4-layer Mistral gate, fp16, random-init, "
                                    f"{chunk} frame(s) per call",
                        "frames_per_step": n_frames, "chunk": chunk, "cuda_graphs": cfg.use_graphs,
-                       "pipelined": pipelined, "frames_in_flight": (8 if pipelined else 1), "tower_lanes": (int(os.environ.get("SMB_LANES", "8")) if pipelined else 1),
+                       "pipelined": pipelined, "frames_in_flight": (16 if pipelined else 1),
+                       "tower_batch": (int(os.environ.get("SMB_TOWER_BATCH", "8")) if (pipelined and chunk == 1) else 1),
                        "gate_batch": (int(os.environ.get("SMB_GATE_BATCH", "4")) if pipelined else min(4, chunk)),
                        "e2e_lookahead": (args.lookahead if pipelined else 0),
                        "l2_policy": "inputs larger than L2: 2.41 GB of weights are re-streamed per frame (L2 = 126 MB)",
@@ -509,7 +510,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="serial sm_frame_step instead of sm_frame_submit/wait")
-    ap.add_argument("--lookahead", type=int, default=7, help="e2e: frames submitted ahead of the decision being read (<= 7)")
+    ap.add_argument("--lookahead", type=int, default=15, help="e2e: frames submitted ahead of the decision being read (<= 15)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -107,11 +107,12 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
  * `stream` at call time.  Outputs are NOT ordered on `stream`: *ticket identifies the call, and
  * sm_frame_wait(ticket, stream, block_host) makes `stream` wait for (stream != NULL or block_host == 0) and/or
  * blocks the host until (block_host != 0) that call's outputs -- including the pinned-host logits -- are
- * complete.  At most 8 tickets are in flight (the 9th submit blocks the host on the oldest); their towers run
- * concurrently on separate streams and activation buffers ("lanes"), and the projector + gate of up to 4 consecutive
- * single-frame tickets share one pass over the projector / gate weights (the batch is closed by the 4th ticket or by
- * sm_frame_wait on one of its tickets).  Results are
- * identical to sm_frame_step (same kernels and arithmetic; stream state advances in ticket order). */
+ * complete.  At most 16 tickets are in flight (the 17th submit blocks the host on the oldest).  On a streaming handle
+ * (max_frames == 1) the towers of up to 8 consecutive tickets run as ONE chunk (pixels are staged at submit time) and
+ * projector + gate share each pass over their weights between 4 frames; the batch is closed by its 8th ticket or by
+ * sm_frame_wait / a serial entry point touching one of its tickets.  Otherwise every ticket runs its own tower on one
+ * of 8 streams ("lanes").  Results are identical to sm_frame_step (same kernels and arithmetic; stream state advances in
+ * ticket order). */
 int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
                     float* logits_out, float* logits_host, void* stream, long long* ticket);
 int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host);

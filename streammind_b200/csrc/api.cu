@@ -59,7 +59,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 }  // namespace
 
 constexpr int kMaxLanes = 8;      // concurrent vision towers of the pipelined path (SMB_LANES overrides)
-constexpr int kTicketRing = 8;    // frames in flight (sm_frame_submit tickets)
+constexpr int kTicketRing = 16;   // frames in flight (sm_frame_submit tickets)
+constexpr int kTowerBatch = 8;    // single-frame tickets whose towers run as one chunk (pipelined path)
 
 struct sm_handle {
     sm_config cfg{};
@@ -94,7 +95,8 @@ struct sm_handle {
     // Two complete sets of tower activations ("lanes"): sm_frame_submit runs the towers of consecutive frames on two
     // streams at the same time, so the kernels of one frame fill the SMs the other frame's small GEMMs leave idle.
     // The ws_* fields above always point at the lane selected by select_lane() (lane 0 outside sm_frame_submit).
-    struct VitWs { void *ws_im, *ws_pemb, *ws_x, *ws_h, *ws_qkv, *ws_att, *ws_mlp, *ws_pixels, *ws_feats; float* ws_part; };
+    struct VitWs { void *ws_im, *ws_pemb, *ws_x, *ws_h, *ws_qkv, *ws_att, *ws_mlp, *ws_pixels, *ws_feats; float* ws_part;
+                   int cap_frames, part_frames; };   // frames the activation buffers / the split-K partial buffer hold
     VitWs lanes[kMaxLanes] = {};
     int cur_lane = 0;
     // persistent vision-tower kernel (vit_mega.cuh): one op list + tensor-map array per chunk size B
@@ -142,10 +144,14 @@ struct sm_handle {
     long long ticket = 0;
     int bg_grid = 0;                   // > 0: projector/gate GEMVs of the pipelined path on this many CTAs (experiment; measured slower)
     void* pooled_ring = nullptr;       // [kTicketRing][max_frames][C]: pooled patch means, one slot per ticket in flight
-    struct PendingTicket { void* toks_out; float* logits_out; float* logits_host; int B; };
-    PendingTicket pend[4] = {};        // tickets whose towers are enqueued but whose gate batch is still open
+    struct PendingTicket { void* feats_out; void* toks_out; float* logits_out; float* logits_host; int B; };
+    PendingTicket pend[kTowerBatch] = {};   // tickets of the open batch (towers enqueued or, in tower-batch mode, only copied in)
     int n_pending = 0, gate_batch = 4;
     long long first_pending = 0;
+    int tower_batch = 1;               // > 1: the towers of this many consecutive single-frame tickets run as ONE chunk
+    void* px_ring = nullptr;           // [kTicketRing][3*H*W] staged pixels of the tickets in flight (tower-batch mode)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_px[kTicketRing] = {};
     // ---- graphs
     std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
     std::map<int, long long> frame_graph_launches;
@@ -457,6 +463,7 @@ int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feat
 int splitk_factor(const sm_handle* h, int tokens, int feats, int K, bool bm2 = false) {
     const int max_split = h->max_split;
     const int split_sms = h->split_sms;
+    if (h->S > 0 && tokens > h->lanes[h->cur_lane].part_frames * h->S) return 1;   // partial-sum buffer of this lane is smaller
     const int tiles = bm2 ? ((tokens + 255) / 256) * ((feats + 255) / 256) : ((tokens + 127) / 128) * ((feats + 127) / 128);
     const int kb = (K + kGemmBK - 1) / kGemmBK;
     int s = std::min({max_split, (split_sms > 0 ? split_sms : h->num_sms) / std::max(1, tiles), kb / 4});
@@ -1089,23 +1096,86 @@ int capture_graph(sm_handle* h, F&& body, cudaGraphExec_t* out, long long* n_lau
     return 0;
 }
 
-// Enqueue projector + gate for the pending tickets (towers already enqueued) as ONE batch on the gate stream:
-// consecutive frames share every pass over the projector / gate weights (run_proj_gate).
-int pipe_flush_gate(sm_handle* h) {
+// Pipelined-path tile planner: with several towers in flight (or a chunk of frames) the SMs are kept busy by other
+// work, so a GEMM is planned for bytes per flop (wide tiles, no split-K) instead of for its own latency.
+// Measured at 4 lanes + gate batching (frames/s): split-K 4 -> 894, 2 -> 955, none -> 1025.
+struct PipePlanScope {
+    sm_handle* h; int div, ssm, msp, pre, pg;
+    explicit PipePlanScope(sm_handle* h_) : h(h_), div(h_->plan_div), ssm(h_->split_sms), msp(h_->max_split), pre(h_->gemm_pre), pg(h_->pgemm) {
+        static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 8;
+        static const int s_sm = getenv("SMB_SPLIT_SMS") ? atoi(getenv("SMB_SPLIT_SMS")) : 0;
+        static const int s_k = getenv("SMB_PIPE_SPLITK") ? std::max(1, atoi(getenv("SMB_PIPE_SPLITK"))) : 1;
+        static const int s_pre = getenv("SMB_PIPE_PRE") ? atoi(getenv("SMB_PIPE_PRE")) : 0;
+        static const int s_pg = getenv("SMB_PGEMM") ? std::max(0, atoi(getenv("SMB_PGEMM"))) : 0;
+        if (h->n_lanes > 1 || h->tower_batch > 1) { h->plan_div = pdiv; h->split_sms = s_sm; h->max_split = s_k; h->gemm_pre = s_pre; h->pgemm = s_pg; }
+    }
+    ~PipePlanScope() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; h->pgemm = pg; }
+};
+
+// run `body` on stream s: directly, or through a graph captured after the first (real) run
+template <typename F>
+int pipe_run_part(sm_handle* h, int key, cudaStream_t s, F&& body, const char* what) {
+    if (!h->cfg.use_graphs) return body(s);
+    auto it = h->frame_graphs.find(key);
+    if (it == h->frame_graphs.end()) {
+        if (body(s)) return 1;                       // real run: produces this call's outputs
+        CUDA_OK(h, cudaStreamSynchronize(s));
+        cudaGraphExec_t ge;
+        long long n = 0;
+        if (capture_graph(h, body, &ge, &n, what)) return 1;
+        h->frame_graphs[key] = ge;
+        h->frame_graph_launches[key] = n;
+    } else {
+        CUDA_OK(h, cudaGraphLaunch(it->second, s));
+        h->launches += h->frame_graph_launches[key];
+    }
+    return 0;
+}
+
+// Close the open batch of tickets.  Tower-batch mode: the towers of the pending single-frame tickets run as ONE chunk
+// (pixels staged in px_ring) on the batch's lane; otherwise the towers were enqueued at submit time.  Then projector +
+// gate for all pending frames as ONE batch on the gate stream: consecutive frames share every pass over the
+// projector / gate weights (run_proj_gate).
+int pipe_flush(sm_handle* h) {
     const int np = h->n_pending;
     if (np == 0) return 0;
     const sm_config& c = h->cfg;
     cudaStream_t gs = h->gate_stream;
     const long long first = h->first_pending;
     const int slot0 = static_cast<int>(first % kTicketRing);
-    int nframes = 0;
-    for (int i = 0; i < np; ++i) {
-        CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[(first + i) % kTicketRing], 0));
-        nframes += h->pend[i].B;
-    }
+    const int kf = static_cast<int>((h->kfilter & 0xFFFu) << 12);
     const size_t pooled_sz = static_cast<size_t>(c.vit_hidden) * h->esz, tok_sz = static_cast<size_t>(c.proj_d_model) * h->esz;
-    // pending tickets are consecutive ring slots and (np > 1) single frames: their pooled vectors are contiguous
-    char* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(slot0) * h->cfg.max_frames * pooled_sz;
+    // pending tickets are consecutive ring slots and (np > 1) single frames: their pooled vectors / pixels are contiguous
+    char* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(slot0) * c.max_frames * pooled_sz;
+    int nframes = 0;
+    for (int i = 0; i < np; ++i) nframes += h->pend[i].B;
+
+    if (h->tower_batch > 1) {
+        PipePlanScope plan(h);
+        const int lane = 1 + static_cast<int>((first / h->tower_batch) % h->n_lanes);   // lanes 1..3 hold a chunk (lane 0: max_frames)
+        if (np > h->lanes[lane].cap_frames) return fail(h, "pipe_flush: %d frames exceed lane capacity %d", np, h->lanes[lane].cap_frames);
+        cudaStream_t vs = h->vit_streams[lane];
+        select_lane(h, lane);
+        bool want_feats = false;
+        for (int i = 0; i < np; ++i) {
+            CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_px[(first + i) % kTicketRing], 0));
+            want_feats = want_feats || h->pend[i].feats_out != nullptr;
+        }
+        const size_t frame_px = static_cast<size_t>(3) * c.vit_image * c.vit_image * h->esz;
+        const void* px = static_cast<const char*>(h->px_ring) + static_cast<size_t>(slot0) * frame_px;
+        auto vit_body = [&](cudaStream_t s) -> int { return run_vit(h, px, np, want_feats ? h->ws_feats : nullptr, pooled, s); };
+        if (pipe_run_part(h, np | (want_feats ? 1 << 8 : 0) | (1 << 9) | (1 << 10) | (lane << 28) | (slot0 << 24) | kf, vs, vit_body,
+                          "sm_frame_submit(tower batch)")) return 1;
+        const size_t feats_sz = static_cast<size_t>(h->P) * c.vit_hidden * h->esz;
+        for (int i = 0; i < np; ++i)
+            if (h->pend[i].feats_out)
+                CUDA_OK(h, cudaMemcpyAsync(h->pend[i].feats_out, static_cast<const char*>(h->ws_feats) + i * feats_sz, feats_sz, cudaMemcpyDeviceToDevice, vs));
+        CUDA_OK(h, cudaEventRecord(h->ev_vit[slot0], vs));
+        CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[slot0], 0));
+    } else {
+        for (int i = 0; i < np; ++i) CUDA_OK(h, cudaStreamWaitEvent(gs, h->ev_vit[(first + i) % kTicketRing], 0));
+    }
+
     auto gate_body = [&](cudaStream_t s) -> int {
         const int saved_cap = h->gemv_grid_cap;
         const bool saved_tma = h->gemv_tma;
@@ -1115,24 +1185,7 @@ int pipe_flush_gate(sm_handle* h) {
         h->gemv_tma = saved_tma;
         return rc;
     };
-    if (!c.use_graphs) {
-        if (gate_body(gs)) return 1;
-    } else {
-        const int key = nframes | (1 << 9) | (1 << 11) | (slot0 << 24) | static_cast<int>((h->kfilter & 0xFFFu) << 12);
-        auto it = h->frame_graphs.find(key);
-        if (it == h->frame_graphs.end()) {
-            if (gate_body(gs)) return 1;                 // real run: produces this batch's outputs
-            CUDA_OK(h, cudaStreamSynchronize(gs));
-            cudaGraphExec_t ge;
-            long long n = 0;
-            if (capture_graph(h, gate_body, &ge, &n, "sm_frame_submit(gate)")) return 1;
-            h->frame_graphs[key] = ge;
-            h->frame_graph_launches[key] = n;
-        } else {
-            CUDA_OK(h, cudaGraphLaunch(it->second, gs));
-            h->launches += h->frame_graph_launches[key];
-        }
-    }
+    if (pipe_run_part(h, nframes | (1 << 9) | (1 << 11) | (slot0 << 24) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
     int f0 = 0;
     for (int i = 0; i < np; ++i) {
         const sm_handle::PendingTicket& p = h->pend[i];
@@ -1153,7 +1206,7 @@ int pipe_flush_gate(sm_handle* h) {
 // close the open gate batch and order the caller's stream after the last pipelined gate before touching it.
 int pipe_join(sm_handle* h, cudaStream_t st) {
     if (!h->pipe_init || h->ticket == 0) return 0;
-    if (pipe_flush_gate(h)) return 1;
+    if (pipe_flush(h)) return 1;
     CUDA_OK(h, cudaStreamWaitEvent(st, h->ev_gate[(h->ticket - 1) % kTicketRing], 0));
     return 0;
 }
@@ -1286,20 +1339,25 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->pooled_ring = A(static_cast<size_t>(kTicketRing) * Bm * C * e);
         h->ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
         h->ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
-        h->lanes[0] = {h->ws_im, h->ws_pemb, h->ws_x, h->ws_h, h->ws_qkv, h->ws_att, h->ws_mlp, h->ws_pixels, h->ws_feats, h->ws_part};
+        h->lanes[0] = {h->ws_im, h->ws_pemb, h->ws_x, h->ws_h, h->ws_qkv, h->ws_att, h->ws_mlp, h->ws_pixels, h->ws_feats, h->ws_part, Bm, Bm};
         for (int ln = 1; ln < kMaxLanes; ++ln) {
             sm_handle::VitWs& w = h->lanes[ln];
+            // lanes 1..3 can also hold a chunk of kTowerBatch single-frame tickets (tower-batch mode of the pipelined path)
+            const int capf = (ln <= 3 && Bm < kTowerBatch) ? kTowerBatch : Bm;
+            const size_t lrows = static_cast<size_t>(capf) * h->S;
+            w.cap_frames = capf; w.part_frames = Bm;
             w.ws_pixels = A(static_cast<size_t>(Bm) * 3 * c.vit_image * c.vit_image * e);
-            w.ws_im = A(static_cast<size_t>(Bm) * h->P * h->kpad * e);
-            w.ws_pemb = A(static_cast<size_t>(Bm) * h->P * C * e);
-            w.ws_x = A(rows * C * e);
-            w.ws_h = A(rows * C * e);
-            w.ws_qkv = A(rows * 3 * C * e);
-            w.ws_att = A(rows * C * e);
-            w.ws_mlp = A(rows * F * e);
-            w.ws_feats = A(static_cast<size_t>(Bm) * h->P * C * e);
+            w.ws_im = A(static_cast<size_t>(capf) * h->P * h->kpad * e);
+            w.ws_pemb = A(static_cast<size_t>(capf) * h->P * C * e);
+            w.ws_x = A(lrows * C * e);
+            w.ws_h = A(lrows * C * e);
+            w.ws_qkv = A(lrows * 3 * C * e);
+            w.ws_att = A(lrows * C * e);
+            w.ws_mlp = A(lrows * F * e);
+            w.ws_feats = A(static_cast<size_t>(capf) * h->P * C * e);
             w.ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
         }
+        h->px_ring = A(static_cast<size_t>(kTicketRing) * 3 * c.vit_image * c.vit_image * e);
         h->mega_sync = static_cast<unsigned int*>(A(256));
         h->mega_mode = getenv("SMB_MEGA") ? atoi(getenv("SMB_MEGA")) : 0;
     }
@@ -1337,7 +1395,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->pj_y = A(NB * Di * e); h->pj_r2 = A(NB * Dm * e);
         h->pj_conv_state = A(static_cast<size_t>(Di) * W * e);
         h->pj_ssm_state = static_cast<float*>(A(static_cast<size_t>(Di) * N * sizeof(float)));
-        h->pj_toks = A(static_cast<size_t>(std::max(Bm, 4)) * Dm * e);
+        h->pj_toks = A(static_cast<size_t>(std::max(Bm, kTowerBatch)) * Dm * e);
     }
     // ---------------- gate
     if (c.gate_layers > 0) {
@@ -1363,7 +1421,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->gt_norm = A(H * e); add_slot(h, p + "model.norm.weight", h->gt_norm, 1, H);
         h->gt_head = A(static_cast<size_t>(2) * H * e); add_slot(h, p + "lm_head.weight", h->gt_head, 2, H);
         h->gt_h = A(4 * H * e); h->gt_v = A(static_cast<size_t>(4) * Hk * D * e); h->gt_m = A(static_cast<size_t>(4) * F * e);
-        h->gt_logits = static_cast<float*>(A(static_cast<size_t>(std::max(Bm, 4)) * 2 * sizeof(float)));
+        h->gt_logits = static_cast<float*>(A(static_cast<size_t>(std::max(Bm, kTowerBatch)) * 2 * sizeof(float)));
     }
     // ---------------- LLM
     if (c.llm_layers > 0) {
@@ -1425,6 +1483,8 @@ void sm_destroy(sm_handle* h) {
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (auto st : h->vit_streams) if (st) cudaStreamDestroy(st);
     if (h->gate_stream) cudaStreamDestroy(h->gate_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto e : h->ev_px) if (e) cudaEventDestroy(e);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto e : h->ev_vit) if (e) cudaEventDestroy(e);
     for (auto e : h->ev_gate) if (e) cudaEventDestroy(e);
@@ -1495,7 +1555,7 @@ int sm_stream_reset(sm_handle* h) {
     if (!h) return 1;
     cudaSetDevice(h->device);
     if (h->pipe_init) {
-        if (pipe_flush_gate(h)) return 1;
+        if (pipe_flush(h)) return 1;
         for (auto st : h->vit_streams) CUDA_OK(h, cudaStreamSynchronize(st));
         CUDA_OK(h, cudaStreamSynchronize(h->gate_stream));
     }
@@ -1611,82 +1671,74 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         int lo = 0, hi = 0;
         CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest priority
         for (auto& vst : h->vit_streams) CUDA_OK(h, cudaStreamCreateWithPriority(&vst, cudaStreamNonBlocking, hi));
-        h->n_lanes = std::max(1, std::min(kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : 8));
-        h->gate_batch = std::max(1, std::min(kGemvBatch, getenv("SMB_GATE_BATCH") ? atoi(getenv("SMB_GATE_BATCH")) : kGemvBatch));
-        if (h->gate_batch == 3) h->gate_batch = 2;   // groups must tile the ticket ring (8)
+        CUDA_OK(h, cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi));
         CUDA_OK(h, cudaStreamCreateWithPriority(&h->gate_stream, cudaStreamNonBlocking, lo));
         CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         for (auto& e : h->ev_vit) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : h->ev_gate) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : h->ev_px) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // streaming engines (max_frames == 1): the towers of tower_batch consecutive tickets run as one chunk on one of
+        // (up to 4) lanes; otherwise every ticket runs its own tower on one of (up to 8) lanes
+        h->tower_batch = c.max_frames == 1 ? std::max(1, std::min(kTowerBatch, getenv("SMB_TOWER_BATCH") ? atoi(getenv("SMB_TOWER_BATCH")) : kTowerBatch)) : 1;
+        if (h->tower_batch == 3 || (h->tower_batch > 4 && h->tower_batch < 8)) h->tower_batch = 4;   // groups must tile the ticket ring
+        if (h->mega_mode > 0) h->tower_batch = 1;                        // the persistent tower stages pixels per lane
+        const int lanes_default = h->tower_batch > 1 ? 2 : 8;
+        h->n_lanes = std::max(1, std::min(h->tower_batch > 1 ? 3 : kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : lanes_default));
+        h->gate_batch = std::max(1, std::min(kGemvBatch, getenv("SMB_GATE_BATCH") ? atoi(getenv("SMB_GATE_BATCH")) : kGemvBatch));
+        if (h->gate_batch == 3) h->gate_batch = 2;   // groups must tile the ticket ring
         h->bg_grid = getenv("SMB_BG_GRID") ? atoi(getenv("SMB_BG_GRID")) : 0;
         h->pipe_init = true;
     }
     const long long tk = h->ticket;
-    const int lane = static_cast<int>(tk % h->n_lanes), ring = static_cast<int>(tk % kTicketRing);
-    cudaStream_t st = static_cast<cudaStream_t>(stream), vs = h->vit_streams[lane];
-    struct LaneGuard {   // every exit path leaves lane 0 and the serial tile planner selected for the other entry points
-        sm_handle* h; int div, ssm, msp, pre, pg;
-        ~LaneGuard() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; h->pgemm = pg; }
-    } lane_guard{h, h->plan_div, h->split_sms, h->max_split, h->gemm_pre, h->pgemm};
-    select_lane(h, lane);
-    // With several towers in flight the SMs are kept busy by the other frames, so a GEMM is planned for bytes per
-    // flop (wide tiles, fewer CTAs, less split-K) instead of for its own latency (measured: +6 % at 2 lanes).
-    if (h->n_lanes > 1) {
-        // Measured at 4 lanes + gate batching (frames/s): split-K 4 -> 894, 2 -> 955, none -> 1025 (fp32 partials and
-        // their reduction cost more bytes than the idle SMs are worth once other frames fill them).
-        static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 8;
-        static const int ssm = getenv("SMB_SPLIT_SMS") ? atoi(getenv("SMB_SPLIT_SMS")) : 0;
-        static const int msp = getenv("SMB_PIPE_SPLITK") ? std::max(1, atoi(getenv("SMB_PIPE_SPLITK"))) : 1;
-        static const int pre = getenv("SMB_PIPE_PRE") ? atoi(getenv("SMB_PIPE_PRE")) : 0;
-        h->plan_div = pdiv;
-        h->split_sms = ssm;
-        h->max_split = msp;
-        h->gemm_pre = pre;
-        static const int pgm = getenv("SMB_PGEMM") ? std::max(0, atoi(getenv("SMB_PGEMM"))) : 0;
-        h->pgemm = pgm;
-    }
-    // the ring slot (events, pooled vector) of ticket tk - kTicketRing is reused: its gate must have been enqueued and finished
+    const int ring = static_cast<int>(tk % kTicketRing);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the ring slot (events, pooled vector, staged pixels) of ticket tk - kTicketRing is reused: its gate must be done
     if (tk >= kTicketRing) {
-        if (h->first_pending <= tk - kTicketRing && pipe_flush_gate(h)) return 1;
+        if (h->n_pending > 0 && h->first_pending <= tk - kTicketRing && pipe_flush(h)) return 1;
         CUDA_OK(h, cudaEventSynchronize(h->ev_gate[ring]));
     }
     CUDA_OK(h, cudaEventRecord(h->ev_in, st));
-    CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
-    if (h->n_pending == 0) CUDA_OK(h, cudaStreamWaitEvent(h->gate_stream, h->ev_in, 0));   // ... and earlier serial calls on it are ordered before this gate batch
+    if (h->n_pending == 0) CUDA_OK(h, cudaStreamWaitEvent(h->gate_stream, h->ev_in, 0));   // earlier serial calls on `stream` precede this batch
     const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
-    CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, vs));
-    const bool want_feats = feats_out != nullptr;
-    void* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(ring) * c.max_frames * c.vit_hidden * h->esz;
-    auto vit_body = [&](cudaStream_t s) -> int { return run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, pooled, s); };
-    if (!c.use_graphs) {
-        if (vit_body(vs)) return 1;
-    } else {
-        const int key = B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (lane << 28) | (ring << 24) | static_cast<int>((h->kfilter & 0xFFFu) << 12);
-        auto it = h->frame_graphs.find(key);
-        if (it == h->frame_graphs.end()) {
-            if (vit_body(vs)) return 1;                      // real run: produces this call's outputs
-            CUDA_OK(h, cudaStreamSynchronize(vs));
-            cudaGraphExec_t ge;
-            long long n = 0;
-            if (capture_graph(h, vit_body, &ge, &n, "sm_frame_submit(tower)")) return 1;
-            h->frame_graphs[key] = ge;
-            h->frame_graph_launches[key] = n;
-        } else {
-            CUDA_OK(h, cudaGraphLaunch(it->second, vs));
-            h->launches += h->frame_graph_launches[key];
-        }
+    const cudaMemcpyKind kind = pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (h->n_pending == 0) h->first_pending = tk;
+
+    if (h->tower_batch > 1) {
+        // ---- tower-batch mode: stage the pixels; the tower runs when the batch closes (pipe_flush)
+        CUDA_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_in, 0));
+        CUDA_OK(h, cudaMemcpyAsync(static_cast<char*>(h->px_ring) + static_cast<size_t>(ring) * px_bytes, pixels, px_bytes, kind, h->copy_stream));
+        CUDA_OK(h, cudaEventRecord(h->ev_px[ring], h->copy_stream));
+        h->pend[h->n_pending++] = {feats_out, toks_out, logits_out, logits_host, B};
+        if (ticket_out) *ticket_out = tk;
+        h->ticket = tk + 1;
+        if (h->n_pending >= h->tower_batch || (tk + 1) % h->tower_batch == 0) return pipe_flush(h);
+        return 0;
     }
-    if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, vs));
-    CUDA_OK(h, cudaEventRecord(h->ev_vit[ring], vs));
+
+    // ---- one tower per ticket, on lane tk mod n_lanes
+    const int lane = static_cast<int>(tk % h->n_lanes);
+    cudaStream_t vs = h->vit_streams[lane];
+    {
+        PipePlanScope plan(h);
+        select_lane(h, lane);
+        CUDA_OK(h, cudaStreamWaitEvent(vs, h->ev_in, 0));                            // inputs are ready on the caller's stream
+        CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, kind, vs));
+        const bool want_feats = feats_out != nullptr;
+        void* pooled = static_cast<char*>(h->pooled_ring) + static_cast<size_t>(ring) * c.max_frames * c.vit_hidden * h->esz;
+        auto vit_body = [&](cudaStream_t s) -> int { return run_vit(h, h->ws_pixels, B, want_feats ? h->ws_feats : nullptr, pooled, s); };
+        const int key = B | (want_feats ? 1 << 8 : 0) | (1 << 9) | (lane << 28) | (ring << 24) | static_cast<int>((h->kfilter & 0xFFFu) << 12);
+        if (pipe_run_part(h, key, vs, vit_body, "sm_frame_submit(tower)")) return 1;
+        if (feats_out) CUDA_OK(h, cudaMemcpyAsync(feats_out, h->ws_feats, static_cast<size_t>(B) * h->P * c.vit_hidden * h->esz, cudaMemcpyDeviceToDevice, vs));
+        CUDA_OK(h, cudaEventRecord(h->ev_vit[ring], vs));
+    }
     // projector + gate: batched over up to gate_batch consecutive single-frame tickets (aligned groups, so a batch
     // never wraps around the ring); multi-frame tickets are batched inside the call
-    if (h->n_pending == 0) h->first_pending = tk;
-    h->pend[h->n_pending++] = {toks_out, logits_out, logits_host, B};
+    h->pend[h->n_pending++] = {nullptr, toks_out, logits_out, logits_host, B};
     if (ticket_out) *ticket_out = tk;
     h->ticket = tk + 1;
     const bool batchable = B == 1 && c.max_frames == 1 && h->gate_batch > 1;   // ring slots are then contiguous single vectors
     if (!batchable || h->n_pending >= h->gate_batch || (tk + 1) % h->gate_batch == 0) {
-        if (pipe_flush_gate(h)) return 1;
+        if (pipe_flush(h)) return 1;
     }
     return 0;
 }
@@ -1696,7 +1748,7 @@ int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host) 
     if (ticket < 0 || ticket >= h->ticket || ticket + kTicketRing < h->ticket)
         return fail(h, "sm_frame_wait: ticket %lld is not in flight (next ticket %lld, ring of %d)", ticket, h->ticket, kTicketRing);
     cudaSetDevice(h->device);
-    if (h->n_pending > 0 && ticket >= h->first_pending && pipe_flush_gate(h)) return 1;   // its gate batch is still open
+    if (h->n_pending > 0 && ticket >= h->first_pending && pipe_flush(h)) return 1;   // its gate batch is still open
     cudaEvent_t ev = h->ev_gate[ticket % kTicketRing];
     if (stream != nullptr || !block_host) CUDA_OK(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
     if (block_host) CUDA_OK(h, cudaEventSynchronize(ev));

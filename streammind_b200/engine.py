@@ -82,7 +82,7 @@ class Engine:
         if self.lib.sm_create(C.byref(self._h), device, C.byref(cc)) != 0:
             raise RuntimeError(self.lib.sm_last_error(None).decode())
         self._pinned_logits = torch.empty(cfg.max_frames, 2, dtype=torch.float32).pin_memory()
-        self._pinned_ring = torch.empty(8, cfg.max_frames, 2, dtype=torch.float32).pin_memory()   # frame_submit tickets (kTicketRing)
+        self._pinned_ring = torch.empty(16, cfg.max_frames, 2, dtype=torch.float32).pin_memory()   # frame_submit tickets (kTicketRing)
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int):
@@ -206,7 +206,7 @@ class Engine:
         logits = torch.empty(B, 2, dtype=torch.float32, device=self.device) if want_device_outputs else None
         tk = C.c_longlong(0)
         nxt = getattr(self, "_next_ticket", 0)
-        host = self._pinned_ring[nxt % 8]
+        host = self._pinned_ring[nxt % 16]
         self._check(self.lib.sm_frame_submit(
             self._h, px.data_ptr(), on_host, B, feats.data_ptr() if feats is not None else None,
             toks.data_ptr() if toks is not None else None, logits.data_ptr() if logits is not None else None,
