@@ -376,6 +376,10 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         a.dbg_mode = dm;
     }
     a.pre_weights = h->gemm_pre;
+    {
+        static const int tp = getenv("SMB_GEMM_2PROD") ? atoi(getenv("SMB_GEMM_2PROD")) : 1;
+        a.two_producers = tp;
+    }
     a.dbg = h->gemm_dbg;
     if (h->gemm_dbg) h->gemm_dbg += 8;   // one 8-slot record per launch
     const CUtensorMap* tc = ta;  // placeholder when unused
@@ -393,7 +397,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     const int smem = gemm_smem_bytes(p.bn, p.bm2);
     {
         ProfScope ps(h, KC_GEMM, st);
-        CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads), smem, st, CS, *ta, *tb, *tc, a));
+        CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());

@@ -42,6 +42,7 @@ struct GemmArgs {
     int w_tiled;    // the weight operand is stored pre-tiled in HBM: [n_tile][k_block][128 rows][64 cols], each
                     // 16 KiB operand tile contiguous (full-rate DRAM bursts instead of 128-byte strided reads)
     int w_kb;       // k-blocks per n_tile in that layout
+    int two_producers;   // second TMA producer warp (warp 10) takes the odd k-blocks
     int bm2;        // 1: the CTA owns a 256-row tile = two 128-row halves that share every B (weight) stage; two
                     // accumulators in TMEM (columns 0 and 256).  Halves the weight bytes an SM ingests per output
                     // element (the L2 -> SM rate, ~48 B/clk/SM measured, bounds the 128-row tile).  Non-swapped only.
@@ -58,7 +59,8 @@ __device__ __forceinline__ long long gtimer() {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (vit_mega.cuh)
+constexpr int kGemmThreads2 = 352;  // gemm_tc_kernel: + a second TMA producer warp (warp 10)
 constexpr int kGemmEpiThreads = 256;
 constexpr int kGemmMaxStages = 8;
 constexpr int kGemmSmemBudget = 200 * 1024;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& cx, int cbase, const uin
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
     const int BN = args.bn;
@@ -229,7 +231,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // Two producer warps share the ring: one stage costs a single issuing thread ~370 cycles of barrier round trips
+    // plus ~75 cycles per TMA box (tools/tma_bench.cu: 37 / 63 / 83 B/clk per SM with 1 / 2 / 3 boxes per stage,
+    // whatever the ring depth), i.e. ~520 cycles per K slab at BN = 128 against 256-300 cycles of MMA -- the "250 ns
+    // per slab whatever the tile width" of the first traces.  Warp 0 takes the even k-blocks, warp 10 the odd ones.
+    const bool two_prod = args.two_producers != 0 && CS == 1 && args.dbg_mode == 0;
+    if (warp == 0 || (warp == 10 && two_prod)) {
+        const int pid = warp == 0 ? 0 : 1, pstep = two_prod ? 2 : 1;
         // ---------------- TMA producer: the whole warp walks the ring, one elected lane issues
         // weights are streamed once; activations are re-read by every CTA column -> keep them in L2
         const uint64_t pol_a = args.swap ? kEvictFirst : kEvictLast;
@@ -257,8 +265,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // The weight operand never depends on the previous kernel: with programmatic dependent launch this CTA is
         // often resident while its predecessor still runs, so the first ring of WEIGHT tiles is requested before
         // griddepcontrol.wait and only the activation tiles wait for it (hides the cold-HBM ramp of every GEMM).
-        const bool can_pre = CS == 1 && args.dbg_mode == 0 && args.pre_weights != 0;
-        const int npre = can_pre ? min(NSTAGE, num_kb) : 0;
+        const bool can_pre = CS == 1 && args.dbg_mode == 0 && args.pre_weights != 0 && pid == 0;
+        const int npre_all = (CS == 1 && args.dbg_mode == 0 && args.pre_weights != 0) ? min(NSTAGE, num_kb) : 0;
+        const int npre = can_pre ? npre_all : 0;
         if (npre > 0 && elect_one_sync()) {
             for (int kb = 0; kb < npre; ++kb) {
                 mbar_arrive_expect_tx(&full_bar[kb], A_BYTES + B_BYTES);
@@ -274,9 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
         __syncwarp();
-        int stage = npre == NSTAGE ? 0 : npre;
-        uint32_t phase = npre == NSTAGE ? 1 : 0;
-        for (int kb = npre; kb < num_kb; ++kb) {
+        for (int kb = npre_all + pid; kb < num_kb; kb += pstep) {
+            const int stage = kb % NSTAGE;
+            const uint32_t phase = static_cast<uint32_t>(kb / NSTAGE) & 1u;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (args.dbg_mode == 2 || args.dbg_mode == 3) {
                 if (elect_one_sync()) mbar_arrive(&full_bar[stage]);
@@ -287,8 +296,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 load_b(stage, kg);
             }
             __syncwarp();
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
+    } else if (warp == 10) {
+        // second producer not in use for this launch
     } else if (warp == 1) {
         pdl_wait();
         // ---------------- MMA issuer: whole warp waits, one elected lane issues tcgen05.mma / commit
