@@ -150,7 +150,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -379,7 +379,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "gate_fire_rate": sum(preds) / max(1, len(preds)),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.barrier()
@@ -491,14 +491,35 @@ def run_decode_workload(args):
             "stream_roofline": {"seconds_at_peak": roof_s, "frac": roof_s / (ms / args.steps / 1e3)},
             "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.engine.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) print to stdout; the contract is ONE JSON line there.
+    Route fd 1 to stderr for the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -121,6 +121,9 @@ struct sm_handle {
     // ---- gate
     std::vector<MistralLayer> gate;
     void *gt_norm = nullptr, *gt_head = nullptr, *gt_h = nullptr, *gt_v = nullptr, *gt_m = nullptr;
+    void *gg_h = nullptr, *gg_hn = nullptr, *gg_v = nullptr, *gg_ve = nullptr, *gg_gu = nullptr, *gg_m = nullptr;   // batched gate as GEMMs
+    float* gg_part = nullptr;   // split-K partials [8][rows][H]
+    int gate_gemm_cap = 0;   // rows (frames) the gg_* buffers hold
     float* gt_logits = nullptr;
     // ---- llm
     std::vector<MistralLayer> llm;
@@ -968,16 +971,85 @@ int run_gate(sm_handle* h, const void* tok, float* logits_out, int nv, cudaStrea
     return launch_gemv(h, a, 1, st);
 }
 
+// The gate for n >= gate_gemm_min frames as tensor-core GEMMs (the gate at L = 1 is a token-wise MLP stack, so n
+// frames are n independent rows): weights on the 128 MMA lanes (swap plan), the n rows on the MMA N dimension, every
+// weight byte streamed once for all n frames by TMA.  Same rounding points as the GEMV chain (rmsnorm rows, T outputs,
+// T(silu) * up, in-place residual); the 2-row lm_head stays a GEMV.
+int run_gate_gemm(sm_handle* h, const void* toks, float* logits_out, int n, cudaStream_t st) {
+    const sm_config& c = h->cfg;
+    const int H = c.proj_d_model, Hq = c.gate_heads, Hk = c.gate_kv_heads, D = c.gate_head_dim, F = c.gate_ffn;
+    if (n > h->gate_gemm_cap) return fail(h, "run_gate_gemm: %d rows exceed capacity %d", n, h->gate_gemm_cap);
+    CUDA_OK(h, cudaMemcpyAsync(h->gg_h, toks, static_cast<size_t>(n) * H * h->esz, cudaMemcpyDeviceToDevice, st));
+    const int nb = (n + 7) / 8;
+    auto rms = [&](const void* nw) -> int {
+        DISPATCH_T(h, T, {
+            CUDA_OK(h, launch_pdl(h, rmsnorm_rows_kernel<T>, dim3(nb), dim3(256), 0, st, (const T*)h->gg_h, (const T*)nw, (T*)h->gg_hn, n, H, c.gate_eps));
+            count_launch(h);
+        })
+        return 0;
+    };
+    // out[n, N] (= or +=) x[n, K] . W[N, K]^T with weight rows on the MMA lanes (swap plan, 16-wide token tile).  N / 128
+    // CTAs alone cannot pull HBM bandwidth for the narrow outputs (v: 8 tiles, o / down: 32), so K is split until about
+    // one CTA per SM streams weights; the fp32 partials are summed in fixed order by splitk_rows_kernel.
+    auto mm = [&](const void* x, const void* W, int N, int K, void* out, bool residual) -> int {
+        const int tiles = (N + 127) / 128, kb = (K + 63) / 64;
+        int split = std::min({8, std::max(1, h->num_sms / tiles), std::max(1, kb / 8)});
+        if (split < 2) return launch_gemm(h, x, n, W, N, K, nullptr, out, N, residual ? EPI_RESIDUAL : EPI_STORE, st, 1, 16);
+        while (split > 1 && (split - 1) * ((kb + split - 1) / split) >= kb) --split;
+        if (launch_gemm(h, x, n, W, N, K, nullptr, h->gg_part, N, EPI_STORE_F32, st, 1, 16, false, split)) return 1;
+        DISPATCH_T(h, T, {
+            const long long tot = static_cast<long long>(n) * N;
+            CUDA_OK(h, launch_pdl(h, splitk_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((tot + 255) / 256, 1024))), dim3(256), 0, st,
+                                  (const float*)h->gg_part, split, tot, residual ? (const T*)out : (const T*)nullptr, (T*)out, tot));
+            count_launch(h);
+        })
+        return 0;
+    };
+    for (int l = 0; l < c.gate_layers; ++l) {
+        const MistralLayer& L = h->gate[l];
+        if (rms(L.in_ln)) return 1;
+        if (mm(h->gg_hn, L.wqkv, Hk * D, H, h->gg_v, false)) return 1;
+        DISPATCH_T(h, T, {
+            const long long tot = static_cast<long long>(n) * Hq * D / 8;
+            CUDA_OK(h, launch_pdl(h, gqa_expand_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((tot + 255) / 256, 1024))), dim3(256), 0, st,
+                                  (const T*)h->gg_v, (T*)h->gg_ve, n, Hq, Hk, D));
+            count_launch(h);
+        })
+        if (mm(h->gg_ve, L.wo, H, Hq * D, h->gg_h, true)) return 1;
+        if (rms(L.post_ln)) return 1;
+        if (mm(h->gg_hn, L.wgu, 2 * F, H, h->gg_gu, false)) return 1;
+        DISPATCH_T(h, T, {
+            const long long tot = static_cast<long long>(n) * F;
+            CUDA_OK(h, launch_pdl(h, swiglu_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((tot + 255) / 256, 4096))), dim3(256), 0, st,
+                                  (const T*)h->gg_gu, (T*)h->gg_m, n, F));
+            count_launch(h);
+        })
+        if (mm(h->gg_m, L.wd, H, F, h->gg_h, true)) return 1;
+    }
+    // final RMSNorm + lm_head [2, H]: GEMV over the rows, kGemvBatch at a time
+    for (int i = 0; i < n; i += kGemvBatch) {
+        const int nv = std::min(kGemvBatch, n - i);
+        GemvArgs a = gv(h->gt_head, 2, H, PRO_RMSNORM, static_cast<const char*>(h->gg_h) + static_cast<size_t>(i) * H * h->esz, GEPI_F32, logits_out + 2 * i);
+        a.nw = h->gt_norm; a.eps = c.gate_eps;
+        a.nv_host = nv; a.x_stride = H; a.y_stride = 2;
+        if (launch_gemv(h, a, 1, st)) return 1;
+    }
+    return 0;
+}
+
 // projector + gate for n frames: batches of <= kGemvBatch frames share every weight pass
 int run_proj_gate(sm_handle* h, const void* pooled, void* toks, float* logits, int n, cudaStream_t st) {
     const sm_config& c = h->cfg;
     static const int max_batch = getenv("SMB_GEMV_BATCH") ? std::max(1, std::min(kGemvBatch, atoi(getenv("SMB_GEMV_BATCH")))) : kGemvBatch;
+    static const int gemm_min = getenv("SMB_GATE_GEMM") ? atoi(getenv("SMB_GATE_GEMM")) : 5;   // frames from which the gate runs as GEMMs (0 = never)
+    const bool gate_gemm = gemm_min > 0 && n >= gemm_min && n <= h->gate_gemm_cap && c.proj_d_model % 64 == 0 && c.gate_ffn % 64 == 0;
     for (int i = 0; i < n; i += max_batch) {
         const int nv = std::min(max_batch, n - i);
         char* tok = static_cast<char*>(toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz;
         if (run_projector(h, static_cast<const char*>(pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz, tok, nv, st)) return 1;
-        if (run_gate(h, tok, logits + 2 * i, nv, st)) return 1;
+        if (!gate_gemm && run_gate(h, tok, logits + 2 * i, nv, st)) return 1;
     }
+    if (gate_gemm) return run_gate_gemm(h, toks, logits, n, st);
     return 0;
 }
 
@@ -1425,6 +1497,13 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->gt_norm = A(H * e); add_slot(h, p + "model.norm.weight", h->gt_norm, 1, H);
         h->gt_head = A(static_cast<size_t>(2) * H * e); add_slot(h, p + "lm_head.weight", h->gt_head, 2, H);
         h->gt_h = A(4 * H * e); h->gt_v = A(static_cast<size_t>(4) * Hk * D * e); h->gt_m = A(static_cast<size_t>(4) * F * e);
+        h->gate_gemm_cap = std::max(Bm, kTowerBatch);
+        {
+            const size_t R = h->gate_gemm_cap;
+            h->gg_h = A(R * H * e); h->gg_hn = A(R * H * e); h->gg_v = A(R * Hk * D * e); h->gg_ve = A(R * Hq * D * e);
+            h->gg_gu = A(R * 2 * F * e); h->gg_m = A(R * F * e);
+            h->gg_part = static_cast<float*>(A(static_cast<size_t>(8) * R * std::max(H, Hk * D) * sizeof(float)));
+        }
         h->gt_logits = static_cast<float*>(A(static_cast<size_t>(std::max(Bm, kTowerBatch)) * 2 * sizeof(float)));
     }
     // ---------------- LLM

@@ -521,6 +521,8 @@ __global__ void gather_rows_kernel(const T* __restrict__ table, const int* __res
 template <typename T>
 __global__ void rmsnorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ nw, T* __restrict__ h, int rows,
                                     int C, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const T* xr = x + static_cast<long long>(warp) * C;
@@ -553,6 +555,8 @@ __global__ void rmsnorm_rows_kernel(const T* __restrict__ x, const T* __restrict
 // SwiGLU rows (prefill path): m[r, j] = T(T(silu(gu[r, j])) * gu[r, F + j])
 template <typename T>
 __global__ void swiglu_rows_kernel(const T* __restrict__ gu, T* __restrict__ m, int rows, int F) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = static_cast<long long>(rows) * F;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -561,6 +565,37 @@ __global__ void swiglu_rows_kernel(const T* __restrict__ gu, T* __restrict__ m, 
         const float g = Cvt<T>::to_f(gu[r * 2 * F + j]), u = Cvt<T>::to_f(gu[r * 2 * F + F + j]);
         const float sg = g / (1.0f + __expf(-g));
         m[i] = Cvt<T>::from_f(rnd<T>(sg) * u);
+    }
+}
+
+// Consumer of a split-K GEMM on a few rows (batched gate): v = T(sum_z part[z][i]) in fixed order;
+// out[i] = resid ? T(resid[i] + v) : v      (resid may alias out: in-place residual stream)
+template <typename T>
+__global__ void splitk_rows_kernel(const float* __restrict__ part, int nsplit, long long split_stride, const T* resid, T* out,
+                                   long long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc = 0.f;
+        for (int z = 0; z < nsplit; ++z) acc += part[z * split_stride + i];
+        const float v = rnd<T>(acc);
+        out[i] = Cvt<T>::from_f(resid != nullptr ? Cvt<T>::to_f(resid[i]) + v : v);
+    }
+}
+
+// repeat_kv at L = 1 for a batch of rows: out[r, h*D + d] = v[r, (h / rep)*D + d]   (gate batched over frames)
+template <typename T>
+__global__ void gqa_expand_rows_kernel(const T* __restrict__ v, T* __restrict__ out, int rows, int Hq, int Hk, int D) {
+    pdl_trigger();
+    pdl_wait();
+    const int rep = Hq / Hk, per_row = Hq * D / 8;
+    const long long total = static_cast<long long>(rows) * per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / per_row;
+        const int c = static_cast<int>(i % per_row) * 8, hq = c / D, d = c % D;
+        *reinterpret_cast<uint4*>(out + r * Hq * D + c) = *reinterpret_cast<const uint4*>(v + r * Hk * D + (hq / rep) * D + d);
     }
 }
 
