@@ -301,20 +301,31 @@ def run_ours(args):
         tot_ms = sum(v[0] for v in prof.values())
         per_frame = {k: {"ms_per_frame": v[0], "share_of_class_sum": v[0] / tot_ms} for k, v in prof.items()}
         frame_ms = ms / args.steps / n_frames
-        gate_batch = (int(os.environ.get("SMB_GATE_BATCH", "4")) if (pipelined and chunk == 1) else min(4, chunk))
+        # frames sharing one pass over the weights: projector (GEMV, batches of <= 4), gate (GEMMs over the whole tower
+        # batch when it has >= 5 frames, else GEMV batches of <= 4)
+        tower_batch = int(os.environ.get("SMB_TOWER_BATCH", "8")) if (pipelined and chunk == 1) else chunk
+        proj_batch = min(4, tower_batch)
+        gate_as_gemm = tower_batch >= int(os.environ.get("SMB_GATE_GEMM", "5")) > 0
+        gate_batch = tower_batch if gate_as_gemm else min(4, tower_batch)
         gemm, gemv = prof.get("gemm_tc_kernel", (0, 1)), prof.get("gemv_kernel", (0, 1))
+        gate_gemm = prof.get("gate_gemm_kernel", (0.0, 0))
         gemm_gflop = VIT_GFLOP_PER_FRAME * (334.65 / 366.0)                     # GEMM share of the ViT flops
-        gemv_mb_streamed = (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) / gate_batch   # weights are streamed once per batch
+        # bytes actually streamed per frame by the weight-streaming kernels
+        gate_mb_streamed = GATE_MB_PER_FRAME / gate_batch
+        proj_mb_streamed = PROJ_MB_PER_FRAME / proj_batch
+        gemv_mb_streamed = proj_mb_streamed + (0.0 if gate_as_gemm else gate_mb_streamed)
         gemm_tf = gemm_gflop / gemm[0] if gemm[0] else 0.0
         gemv_gbs = gemv_mb_streamed / gemv[0] if gemv[0] else 0.0
+        gate_gbs = gate_mb_streamed / gate_gemm[0] if (gate_as_gemm and gate_gemm[0]) else None
         roof_gemv = {"kernel": "gemv_kernel", "bound": "hbm", "achieved": gemv_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": gemv_gbs / peaks["hbm"], "traffic": 234.99e6,
                      "traffic_note": "dram read bytes of the largest launch (gate|up of one gate layer, 2 x 14336 x 4096 x 2 B = "
                                      "234.9 MB algorithmic, shared by 4 frames) from ncu --set full, profiles/r01_ncu_pipelined.md: no re-reads",
                      "share_of_step": gemv[0] / frame_ms,
-                     "avg_launch_us": 1e3 * gemv[0] * gate_batch / 22.0,
-                     "launches_per_weight_pass": 22,
-                     "frames_per_weight_pass": gate_batch,
+                     "avg_launch_us": 1e3 * gemv[0] * (proj_batch / 5.0 if gate_as_gemm else gate_batch / 22.0),
+                     "launches_per_weight_pass": 5 if gate_as_gemm else 22,
+                     "frames_per_weight_pass": proj_batch if gate_as_gemm else gate_batch,
+                     "covers": "projector" if gate_as_gemm else "projector + gate",
                      "bytes_streamed_per_frame": gemv_mb_streamed * 1e6,
                      "algorithmic_bytes_per_frame_unbatched": (GATE_MB_PER_FRAME + PROJ_MB_PER_FRAME) * 1e6,
                      "serial_b1": {"ms_per_frame": prof_serial["gemv_kernel"][0],
@@ -332,11 +343,21 @@ def run_ours(args):
                              "flight; avg_launch_us is the latency of one launch in the serial B=1 pass",
                      "serial_b1": {"ms_per_frame": prof_serial["gemm_tc_kernel"][0],
                                    "achieved_TFLOPs": gemm_gflop / prof_serial["gemm_tc_kernel"][0]}}
+        roof_gate = None
+        if gate_as_gemm:
+            roof_gate = {"kernel": "gemm_tc_kernel (batched gate: weights on the MMA lanes, weight streaming)", "bound": "hbm",
+                         "achieved": gate_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gate_gbs / peaks["hbm"],
+                         "traffic": None, "share_of_step": gate_gemm[0] / frame_ms, "frames_per_weight_pass": gate_batch,
+                         "bytes_streamed_per_frame": gate_mb_streamed * 1e6,
+                         "algorithmic_bytes_per_frame_unbatched": GATE_MB_PER_FRAME * 1e6, "peak_source": peaks["source"],
+                         "note": "includes the row kernels between the GEMMs (RMSNorm, GQA expand, SwiGLU, split-K sums)"}
         dominant, secondary = (roof_gemm, roof_gemv) if gemm[0] >= gemv[0] else (roof_gemv, roof_gemm)
+        if roof_gate is not None and gate_gemm[0] > secondary["share_of_step"] * frame_ms:
+            secondary = roof_gate
         dominant["peak_source"] = secondary["peak_source"] = peaks["source"]
         # frame-level roofline (with the gate weights shared by gate_batch frames)
         t_tensor = VIT_GFLOP_PER_FRAME / peaks["tf_sustained"]
-        t_hbm = (578.8 + gemv_mb_streamed) / peaks["hbm"]
+        t_hbm = (578.8 / (tower_batch if (pipelined and chunk == 1) else chunk) + proj_mb_streamed + gate_mb_streamed) / peaks["hbm"]
         frame_roof_ms = max(t_tensor, t_hbm)
 
         # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
@@ -358,7 +379,7 @@ def run_ours(args):
                        "frames_per_step": n_frames, "chunk": chunk, "cuda_graphs": cfg.use_graphs,
                        "pipelined": pipelined, "frames_in_flight": (16 if pipelined else 1),
                        "tower_batch": (int(os.environ.get("SMB_TOWER_BATCH", "8")) if (pipelined and chunk == 1) else 1),
-                       "gate_batch": (int(os.environ.get("SMB_GATE_BATCH", "4")) if pipelined else min(4, chunk)),
+                       "gate_batch": gate_batch, "gate_as_gemm": gate_as_gemm,
                        "e2e_lookahead": (args.lookahead if pipelined else 0),
                        "l2_policy": "inputs larger than L2: 2.41 GB of weights are re-streamed per frame (L2 = 126 MB)",
                        "parallelism": f"{world} independent stream(s), one per GPU, no data-path collective"},
@@ -369,10 +390,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": dominant,
             "roofline_secondary": secondary,
+            "roofline_gemv": roof_gemv,
             "frame_roofline": {"ms_per_frame_at_peak": frame_roof_ms, "tensor_ms": t_tensor, "hbm_ms": t_hbm,
                                "frac": frame_roof_ms / frame_ms,
-                               "note": "per-frame bound max(tensor: 366 GFLOP of ViT, HBM: ViT weights once per frame + "
-                                       "projector/gate weights once per gate_batch frames) at the measured peaks"},
+                               "note": "per-frame bound max(tensor: 366 GFLOP of ViT, HBM: ViT weights once per tower batch, "
+                                       "projector / gate weights once per batch) at the measured peaks"},
             "serial_b1": {"value": world * n_frames / (serial_ms / 1e3), "unit": "frames/s", "measured_on": "rank 0",
                           "note": "same stream through the serial sm_frame_step (one frame in flight, no batching)"},
             "kernel_breakdown": per_frame,

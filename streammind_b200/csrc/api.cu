@@ -74,6 +74,7 @@ struct sm_handle {
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
     bool use_pdl = true;
+    int gemm_class = 0;               // kernel class of gemm_tc_kernel launches (KC_GEMM; run_gate_gemm: KC_GATE_GEMM)
     bool gemv_tma = false;            // weight-streaming GEMVs through the bulk-copy ring (gemv_tma.cuh, experimental)
     int gemv_grid_cap = 0;            // > 0: GEMVs use at most this many CTAs (background gate)
     bool vit_tiled = true;            // ViT GEMM weights are stored pre-tiled (gemm_tc.cuh GemmArgs::w_tiled)
@@ -156,8 +157,8 @@ struct sm_handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_px[kTicketRing] = {};
     // ---- graphs
-    std::map<int, cudaGraphExec_t> frame_graphs;   // key: B | flags<<8
-    std::map<int, long long> frame_graph_launches;
+    std::map<long long, cudaGraphExec_t> frame_graphs;   // key: gkey(h, int key) = kernel filter << 32 | key   // key: B | flags<<8
+    std::map<long long, long long> frame_graph_launches;
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot capture)
     cudaGraphExec_t decode_graph = nullptr;
     long long decode_graph_launches = 0;
@@ -217,6 +218,8 @@ inline void select_lane(sm_handle* h, int lane) {
     h->cur_lane = lane;
 }
 
+inline long long gkey(const sm_handle* h, int key) { return (static_cast<long long>(h->kfilter) << 32) | static_cast<unsigned int>(key); }
+
 inline void count_launch(sm_handle* h) {
     if (h->capturing) h->captured_launches++; else h->launches++;
 }
@@ -251,11 +254,12 @@ cudaError_t launch_pdl(sm_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 blo
 
 // per-kernel-class CUDA-event timing (bench.py's roofline pass; off on the timed path)
 enum KClass { KC_GEMM = 0, KC_GEMV, KC_ATTN, KC_LAYERNORM, KC_IM2COL, KC_VIT_FINALIZE, KC_MAMBA_SCAN, KC_ROPE_APPEND,
-              KC_DECODE_ATTN, KC_ARGMAX, KC_GATHER, KC_RMSNORM_ROWS, KC_SWIGLU_ROWS, KC_COUNT };
+              KC_DECODE_ATTN, KC_ARGMAX, KC_GATHER, KC_RMSNORM_ROWS, KC_SWIGLU_ROWS, KC_GATE_GEMM, KC_COUNT };
 const char* kKClassNames[KC_COUNT] = {"gemm_tc_kernel", "gemv_kernel", "attention_kernel", "layernorm_kernel",
                                       "im2col_kernel", "vit_finalize_kernel", "mamba_scan_step_kernel",
                                       "rope_append_kernel", "decode_attn_kernels", "argmax_kernel",
-                                      "gather_rows_kernel", "rmsnorm_rows_kernel", "swiglu_rows_kernel"};
+                                      "gather_rows_kernel", "rmsnorm_rows_kernel", "swiglu_rows_kernel",
+                                      "gate_gemm_kernel"};   // gemm_tc_kernel launches of the batched gate (weight streaming)
 inline bool kon(const sm_handle* h, int cls) { return (h->kfilter >> cls) & 1u; }
 struct ProfScope {
     sm_handle* h; cudaStream_t st; cudaEvent_t b = nullptr;
@@ -329,7 +333,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
                   int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false,
                   int split_k = 1) {
     if (K % 8 != 0) return fail(h, "gemm: K=%d must be a multiple of 8", K);
-    if (!kon(h, KC_GEMM)) return 0;
+    if (!kon(h, h->gemm_class)) return 0;
     GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div, split_k);
     if (force_swap == 2) {                 // forced 256 x 256 dual-accumulator tile
         if (feats % 256 != 0) return fail(h, "gemm: the 256-row tile needs features %% 256 == 0");
@@ -399,7 +403,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     }
     const int smem = gemm_smem_bytes(p.bn, p.bm2);
     {
-        ProfScope ps(h, KC_GEMM, st);
+        ProfScope ps(h, h->gemm_class, st);
         CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
     }
     count_launch(h);
@@ -979,6 +983,9 @@ int run_gate_gemm(sm_handle* h, const void* toks, float* logits_out, int n, cuda
     const sm_config& c = h->cfg;
     const int H = c.proj_d_model, Hq = c.gate_heads, Hk = c.gate_kv_heads, D = c.gate_head_dim, F = c.gate_ffn;
     if (n > h->gate_gemm_cap) return fail(h, "run_gate_gemm: %d rows exceed capacity %d", n, h->gate_gemm_cap);
+    struct ClassScope { sm_handle* h; ~ClassScope() { h->gemm_class = KC_GEMM; } } class_scope{h};
+    h->gemm_class = KC_GATE_GEMM;
+    if (!kon(h, KC_GATE_GEMM)) return 0;
     CUDA_OK(h, cudaMemcpyAsync(h->gg_h, toks, static_cast<size_t>(n) * H * h->esz, cudaMemcpyDeviceToDevice, st));
     const int nb = (n + 7) / 8;
     auto rms = [&](const void* nw) -> int {
@@ -1192,18 +1199,18 @@ struct PipePlanScope {
 template <typename F>
 int pipe_run_part(sm_handle* h, int key, cudaStream_t s, F&& body, const char* what) {
     if (!h->cfg.use_graphs) return body(s);
-    auto it = h->frame_graphs.find(key);
+    auto it = h->frame_graphs.find(gkey(h, key));
     if (it == h->frame_graphs.end()) {
         if (body(s)) return 1;                       // real run: produces this call's outputs
         CUDA_OK(h, cudaStreamSynchronize(s));
         cudaGraphExec_t ge;
         long long n = 0;
         if (capture_graph(h, body, &ge, &n, what)) return 1;
-        h->frame_graphs[key] = ge;
-        h->frame_graph_launches[key] = n;
+        h->frame_graphs[gkey(h, key)] = ge;
+        h->frame_graph_launches[gkey(h, key)] = n;
     } else {
         CUDA_OK(h, cudaGraphLaunch(it->second, s));
-        h->launches += h->frame_graph_launches[key];
+        h->launches += h->frame_graph_launches[gkey(h, key)];
     }
     return 0;
 }
@@ -1708,7 +1715,7 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
     };
     if (c.use_graphs) {
         const int key = B | (want_feats ? 1 << 8 : 0) | static_cast<int>((h->kfilter & 0xFFFFu) << 9);
-        auto it = h->frame_graphs.find(key);
+        auto it = h->frame_graphs.find(gkey(h, key));
         if (it == h->frame_graphs.end()) {
             // warm run outside capture: fills the tensor-map cache and sets function attributes
             if (body(st)) return 1;
@@ -1726,12 +1733,12 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
             cudaGraphExec_t ge;
             CUDA_OK(h, cudaGraphInstantiate(&ge, g, 0));
             cudaGraphDestroy(g);
-            h->frame_graphs[key] = ge;
-            h->frame_graph_launches[key] = h->captured_launches;
+            h->frame_graphs[gkey(h, key)] = ge;
+            h->frame_graph_launches[gkey(h, key)] = h->captured_launches;
             // the warm run already produced this call's outputs
         } else {
             CUDA_OK(h, cudaGraphLaunch(it->second, st));
-            h->launches += h->frame_graph_launches[key];
+            h->launches += h->frame_graph_launches[gkey(h, key)];
         }
     } else {
         if (body(st)) return 1;

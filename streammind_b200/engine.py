@@ -249,7 +249,7 @@ class Engine:
         return int(self.lib.sm_launch_count(self._h, 1 if reset else 0))
 
     KERNEL_CLASSES = ["gemm_tc_kernel", "gemv_kernel", "attention_kernel", "layernorm_kernel", "im2col_kernel",
-                      "vit_finalize_kernel", "mamba_scan_step_kernel"]
+                      "vit_finalize_kernel", "mamba_scan_step_kernel", "gate_gemm_kernel"]
 
     def kernel_filter(self, classes=None):
         """Launch only the named kernel classes (None = all).  Measurement aid, see sm_debug_kernel_filter."""
