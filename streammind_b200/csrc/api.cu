@@ -74,6 +74,7 @@ struct sm_handle {
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
     bool use_pdl = true;
+    int gemm_occ2 = 0;                // 1: multi-wave GEMMs run as two co-resident CTAs per SM (gemm_tc_kernel<T, 2>)
     int gemm_class = 0;               // kernel class of gemm_tc_kernel launches (KC_GEMM; run_gate_gemm: KC_GATE_GEMM)
     bool gemv_tma = false;            // weight-streaming GEMVs through the bulk-copy ring (gemv_tma.cuh, experimental)
     int gemv_grid_cap = 0;            // > 0: GEMVs use at most this many CTAs (background gate)
@@ -377,7 +378,10 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.bm2 = p.bm2;
-    a.nstage = gemm_num_stages(p.bn, p.bm2); a.epi = epi;
+    // two co-resident CTAs per SM: only when there is more than one wave of tiles to overlap and the ring still has >= 2 stages
+    const int occ2 = (h->gemm_occ2 && !p.bm2 && CS == 1 && static_cast<int>(grid.x * grid.y * std::max(1u, grid.z)) > h->num_sms &&
+                      gemm_num_stages(p.bn, 0, 1) >= 2) ? 1 : 0;
+    a.nstage = gemm_num_stages(p.bn, p.bm2, occ2); a.epi = epi;
     {
         static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
         a.dbg_mode = dm;
@@ -401,10 +405,11 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         static const int dbg_stages = getenv("SMB_GEMM_STAGES") ? atoi(getenv("SMB_GEMM_STAGES")) : 0;   // tuning knob
         if (dbg_stages > 0 && dbg_stages < a.nstage) a.nstage = dbg_stages;
     }
-    const int smem = gemm_smem_bytes(p.bn, p.bm2);
+    const int smem = gemm_smem_bytes(p.bn, p.bm2, occ2);
     {
         ProfScope ps(h, h->gemm_class, st);
-        CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
+        if (occ2) CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T, 2>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
+        else CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T, 1>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -591,7 +596,8 @@ int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cu
 
 template <typename T>
 int init_kernel_attrs_t(sm_handle* h) {
-    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(vit_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     {
@@ -613,7 +619,7 @@ int init_kernel_attrs_t(sm_handle* h) {
     if (getenv("SMB_CARVEOUT") != nullptr) {
         const int co = atoi(getenv("SMB_CARVEOUT")) > 0 ? atoi(getenv("SMB_CARVEOUT")) : cudaSharedmemCarveoutMaxShared;
         auto set = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, co); };
-        CUDA_OK(h, set((const void*)gemm_tc_kernel<T>));
+        CUDA_OK(h, set((const void*)gemm_tc_kernel<T, 1>));
         CUDA_OK(h, set((const void*)gemv_kernel<T, 1>));
         CUDA_OK(h, set((const void*)gemv_kernel<T, 2>));
         CUDA_OK(h, set((const void*)attention_kernel<T, 64>));
@@ -1327,6 +1333,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
+    h->gemm_occ2 = getenv("SMB_GEMM_OCC2") ? atoi(getenv("SMB_GEMM_OCC2")) : 0;
     if (getenv("SMB_DEC_SPLITS")) h->dec_splits = std::max(1, std::min(128, atoi(getenv("SMB_DEC_SPLITS"))));
     h->max_split = getenv("SMB_SPLITK") ? std::max(1, atoi(getenv("SMB_SPLITK"))) : 4;
     h->gemm_pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
