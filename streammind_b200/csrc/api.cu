@@ -133,7 +133,7 @@ struct sm_handle {
     std::vector<void*> kc, vc;
     int pmax = 0;
     void *lw_x = nullptr, *lw_hn = nullptr, *lw_qkv = nullptr, *lw_att = nullptr, *lw_gu = nullptr, *lw_m = nullptr;
-    float *lw_logits = nullptr, *lw_part = nullptr;
+    float *lw_logits = nullptr, *lw_part = nullptr, *lw_part2 = nullptr;   // lw_part2: split-K partials of the few-row prefill GEMMs
     int *d_pos = nullptr, *d_tok = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_done = nullptr, *d_stop = nullptr;
     int kv_len = 0;
     int dec_splits = 64;   // KV slices per kv head of the decode attention (SMB_DEC_SPLITS); measured at ctx 2k: 16 -> 280, 32 -> 302, 64 -> 305 tokens/s
@@ -981,6 +981,30 @@ int run_gate(sm_handle* h, const void* tok, float* logits_out, int nv, cudaStrea
     return launch_gemv(h, a, 1, st);
 }
 
+// out[n, N] (= or +=) x[n, K] . W[N, K]^T for a few rows (n <= 64) with the weight rows on the MMA lanes (swap plan).
+// N / 128 CTAs alone cannot pull HBM bandwidth for narrow outputs (32-48 tiles for the 4096 / 6144-wide projections), so
+// K is split until about one CTA per SM streams weights; the fp32 partials are summed in fixed order by
+// splitk_rows_kernel (T(resid + T(sum)) for the in-place residual stream).  part: [8][n][N] floats.
+int gemm_few_rows(sm_handle* h, const void* x, int n, const void* W, int N, int K, void* out, bool residual, float* part,
+                  cudaStream_t st) {
+    const int tiles = (N + 127) / 128, kb = (K + 63) / 64;
+    const int bn = std::max(16, (n + 15) / 16 * 16);
+    int split = std::min({8, std::max(1, h->num_sms / tiles), std::max(1, kb / 8)});
+    while (split > 1 && (split - 1) * ((kb + split - 1) / split) >= kb) --split;
+    if (split < 2 || part == nullptr)
+        return launch_gemm(h, x, n, W, N, K, nullptr, out, N, residual ? EPI_RESIDUAL : EPI_STORE, st, 1, bn);
+    if (launch_gemm(h, x, n, W, N, K, nullptr, part, N, EPI_STORE_F32, st, 1, bn, false, split)) return 1;
+    DISPATCH_T(h, T, {
+        const long long tot = static_cast<long long>(n) * N;
+        if (kon(h, h->gemm_class)) {
+        CUDA_OK(h, launch_pdl(h, splitk_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((tot + 255) / 256, 1024))), dim3(256), 0, st,
+                              (const float*)part, split, tot, residual ? (const T*)out : (const T*)nullptr, (T*)out, tot));
+        }
+        count_launch(h);
+    })
+    return 0;
+}
+
 // The gate for n >= gate_gemm_min frames as tensor-core GEMMs (the gate at L = 1 is a token-wise MLP stack, so n
 // frames are n independent rows): weights on the 128 MMA lanes (swap plan), the n rows on the MMA N dimension, every
 // weight byte streamed once for all n frames by TMA.  Same rounding points as the GEMV chain (rmsnorm rows, T outputs,
@@ -1001,22 +1025,8 @@ int run_gate_gemm(sm_handle* h, const void* toks, float* logits_out, int n, cuda
         })
         return 0;
     };
-    // out[n, N] (= or +=) x[n, K] . W[N, K]^T with weight rows on the MMA lanes (swap plan, 16-wide token tile).  N / 128
-    // CTAs alone cannot pull HBM bandwidth for the narrow outputs (v: 8 tiles, o / down: 32), so K is split until about
-    // one CTA per SM streams weights; the fp32 partials are summed in fixed order by splitk_rows_kernel.
     auto mm = [&](const void* x, const void* W, int N, int K, void* out, bool residual) -> int {
-        const int tiles = (N + 127) / 128, kb = (K + 63) / 64;
-        int split = std::min({8, std::max(1, h->num_sms / tiles), std::max(1, kb / 8)});
-        if (split < 2) return launch_gemm(h, x, n, W, N, K, nullptr, out, N, residual ? EPI_RESIDUAL : EPI_STORE, st, 1, 16);
-        while (split > 1 && (split - 1) * ((kb + split - 1) / split) >= kb) --split;
-        if (launch_gemm(h, x, n, W, N, K, nullptr, h->gg_part, N, EPI_STORE_F32, st, 1, 16, false, split)) return 1;
-        DISPATCH_T(h, T, {
-            const long long tot = static_cast<long long>(n) * N;
-            CUDA_OK(h, launch_pdl(h, splitk_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((tot + 255) / 256, 1024))), dim3(256), 0, st,
-                                  (const float*)h->gg_part, split, tot, residual ? (const T*)out : (const T*)nullptr, (T*)out, tot));
-            count_launch(h);
-        })
-        return 0;
+        return gemm_few_rows(h, x, n, W, N, K, out, residual, h->gg_part, st);
     };
     for (int l = 0; l < c.gate_layers; ++l) {
         const MistralLayer& L = h->gate[l];
@@ -1120,6 +1130,9 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     const int QKV = (Hq + 2 * Hk) * D;
     CUDA_OK(h, cudaMemcpyAsync(h->lw_x, embeds, static_cast<size_t>(P) * H * h->esz, cudaMemcpyDeviceToDevice, st));
     const int nb = (P + 7) / 8;
+    // short dialogue suffixes (a fire prefills 11-74 new tokens): the narrow projections are split along K
+    static const bool few_on = getenv("SMB_PREFILL_SPLITK") ? atoi(getenv("SMB_PREFILL_SPLITK")) != 0 : true;
+    const bool few = few_on && P <= 64 && h->lw_part2 != nullptr;
     for (int l = 0; l < c.llm_layers; ++l) {
         const MistralLayer& L = h->llm[l];
         DISPATCH_T(h, T, {
@@ -1129,7 +1142,8 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
             }
             count_launch(h);
         })
-        if (launch_gemm(h, h->lw_hn, P, L.wqkv, QKV, H, nullptr, h->lw_qkv, QKV, EPI_STORE, st)) return 1;
+        if (few) { if (gemm_few_rows(h, h->lw_hn, P, L.wqkv, QKV, H, h->lw_qkv, false, h->lw_part2, st)) return 1; }
+        else if (launch_gemm(h, h->lw_hn, P, L.wqkv, QKV, H, nullptr, h->lw_qkv, QKV, EPI_STORE, st)) return 1;
         DISPATCH_T(h, T, {
             const long long tot = static_cast<long long>(P) * ((Hq + Hk) * (D / 2) + Hk * D);
             rope_append_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 2048)), 256, 0, st>>>(
@@ -1144,7 +1158,8 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         a.q_len = P; a.kv_len = pos0 + P; a.q_pos0 = pos0; a.causal = 1; a.group = Hq / Hk;
         a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
         if (launch_attn(h, a, D, Hq, 1, st)) return 1;
-        if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
+        if (few) { if (gemm_few_rows(h, h->lw_att, P, L.wo, H, Hq * D, h->lw_x, true, h->lw_part2, st)) return 1; }
+        else if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             if (kon(h, KC_RMSNORM_ROWS)) {
@@ -1162,7 +1177,8 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
             }
             count_launch(h);
         })
-        if (launch_gemm(h, h->lw_m, P, L.wd, H, F, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
+        if (few) { if (gemm_few_rows(h, h->lw_m, P, L.wd, H, F, h->lw_x, true, h->lw_part2, st)) return 1; }
+        else if (launch_gemm(h, h->lw_m, P, L.wd, H, F, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
     }
     CUDA_OK(h, cudaGetLastError());
     return 0;
@@ -1557,6 +1573,7 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->lw_gu = A(Pm * 2 * F * e); h->lw_m = A(Pm * F * e);
         h->lw_logits = static_cast<float*>(A(static_cast<size_t>(V) * sizeof(float)));
         h->lw_part = static_cast<float*>(A(static_cast<size_t>(Hq) * h->dec_splits * (D + 2) * sizeof(float)));
+        h->lw_part2 = static_cast<float*>(A(static_cast<size_t>(8) * 64 * std::max(QKV, H) * sizeof(float)));
         int* ints = static_cast<int*>(A((8 + 4096 + 64) * sizeof(int)));
         h->d_pos = ints; h->d_tok = ints + 1; h->d_nout = ints + 2; h->d_done = ints + 3; h->d_out = ints + 8;
         h->d_stop = ints + 8 + 4096;
