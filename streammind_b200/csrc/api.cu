@@ -518,7 +518,7 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     static const bool use_seg = getenv("SMB_GEMV_SEG") ? atoi(getenv("SMB_GEMV_SEG")) != 0 : false;   // measured slower (latency-bound at 1 CTA/SM): opt-in
     const bool seg_kernel = nv > 1 && use_seg;      // segment-stationary batched kernel (gemv_seg_kernel)
     const int nvt = nv <= 1 ? 1 : (seg_kernel ? (nv <= 2 ? 2 : 4) : nv);
-    a.seg_len = nv == 1 ? 1024 : 2048;
+    a.seg_len = nv == 1 ? (nmat == 1 ? SMB_GEMV_UNR1 * 256 : 1024) : 2048;   // one batch of loads covers a segment
     static const int grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;   // experiment: background-sized grids
     int grid = std::min(a.N, grid_cap > 0 ? grid_cap : (nv == 1 ? 2 : 1) * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;

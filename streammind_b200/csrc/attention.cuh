@@ -68,6 +68,9 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2^-inf = +
     return y;
 }
 
+#ifndef SMB_ATTN_MINBLOCKS
+#define SMB_ATTN_MINBLOCKS 2   // 128 registers: two CTAs per SM (3 -> 80 registers + spills: measured slower)
+#endif
 constexpr int kAttnBQ = 64;   // query rows per CTA (4 warps x 16 per key group)
 constexpr int kAttnBK = 64;   // keys per pipeline stage
 constexpr int kAttnGroups = 2;  // key groups per CTA: group g walks key tiles g, g+2, ... (halves the serial chain)
@@ -299,7 +302,7 @@ __device__ __forceinline__ void attention_body(const AttnArgs& a, int qt, int h,
 }
 
 template <typename T, int D>
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kAttnThreads, D == 64 ? SMB_ATTN_MINBLOCKS : 1) attention_kernel(const AttnArgs a) {
     extern __shared__ __align__(128) uint8_t attn_smem[];
     pdl_trigger();
     pdl_wait();

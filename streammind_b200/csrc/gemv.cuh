@@ -59,6 +59,9 @@ struct GemvArgs {
     int nv_host;   // host-side copy of NV (selects the template instance)
 };
 
+#ifndef SMB_GEMV_UNR1
+#define SMB_GEMV_UNR1 4
+#endif
 constexpr int kGemvThreads = 512;
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kGemvMaxRowsPerCta = 256;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kGemvThreads, NV == 1 ? 2 : 1) gemv_kernel(con
     const T* W1 = reinterpret_cast<const T*>(a.W1);
 
     // ---- issue the first item's weight loads before touching the input vector
-    constexpr int UNR = NV == 1 ? 4 : 8;  // 16-byte chunks in flight per matrix per lane per batch (NV > 1: one CTA per SM)
+    constexpr int UNR = NV == 1 ? (NMAT == 1 ? SMB_GEMV_UNR1 : 4) : 8;  // 16-byte chunks in flight per matrix per lane per batch (NV > 1: one CTA per SM)
     uint4 wbuf[NMAT][UNR];
     int item = warp;
     auto issue = [&](int it, int batch) {

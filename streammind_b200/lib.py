@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstreammind_b200.so")
+LIB_PATH = os.environ.get("SMB_LIB_PATH") or os.path.join(_HERE, "libstreammind_b200.so")   # override: A/B builds
 
 SM_DTYPE_F16, SM_DTYPE_BF16, SM_DTYPE_F32 = 0, 1, 2
 

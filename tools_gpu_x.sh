@@ -1,11 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_llm_gpu.py tests/test_stream_api_gpu.py -m gpu -q -x --timeout 600 -p no:cacheprovider > gpurun_out/pytest_pf.log 2>&1
-echo "pytest exit $?"; tail -5 gpurun_out/pytest_pf.log
-timeout 900 python bench.py --workload dense_decode --frames 128 --steps 1 --warmup 3 > gpurun_out/bench_dd_a.json 2>gpurun_out/bench_dd_a.err
-SMB_PREFILL_SPLITK=0 timeout 900 python bench.py --workload dense_decode --frames 128 --steps 1 --warmup 3 > gpurun_out/bench_dd_b.json 2>gpurun_out/bench_dd_b.err
-python - <<PY
+run() {
+  name=$1; shift
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_$name.json 2>gpurun_out/bench_$name.err
+  python - <<PY
 import json
-for n in ("a","b"):
-    d=json.load(open(f"gpurun_out/bench_dd_{n}.json")); print("dense_decode 128f splitk", n, "fps", round(d["value"],2), d["decode"]["tokens_per_s"])
+try:
+    d=json.load(open("gpurun_out/bench_$name.json")); print("$name value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "serial", round(d["serial_b1"]["value"],1), "attn ms/frame", round(d["kernel_breakdown"]["attention_kernel"]["ms_per_frame"],3))
+except Exception as e: print("$name ERR", e); print(open("gpurun_out/bench_$name.err").read()[-2000:])
 PY
+}
+run base
+SMB_LIB_PATH=$PWD/streammind_b200/libsmb_a3.so run attn3
+SMB_LIB_PATH=$PWD/streammind_b200/libsmb_a3.so timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_frame_path_gpu.py -m gpu -q -x -p no:cacheprovider -k "attention or full_width" 2>&1 | tail -2
