@@ -1,15 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() {
-  name=$1; shift
-  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_$name.json 2>gpurun_out/bench_$name.err
-  python - <<PY
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 -p no:cacheprovider > gpurun_out/pytest_final3.log 2>&1
+echo "pytest exit $?"; tail -4 gpurun_out/pytest_final3.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+python - <<PY
 import json
-try:
-    d=json.load(open("gpurun_out/bench_$name.json")); print("$name value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "serial", round(d["serial_b1"]["value"],1), "attn ms/frame", round(d["kernel_breakdown"]["attention_kernel"]["ms_per_frame"],3))
-except Exception as e: print("$name ERR", e); print(open("gpurun_out/bench_$name.err").read()[-2000:])
+d=json.load(open("gpurun_out/bench_default.json"))
+print("value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "serial", round(d["serial_b1"]["value"],1), "cpu", d["cpu_baseline"]["value"])
+print("roofline", d["roofline"]["kernel"], round(d["roofline"]["achieved"],1), round(d["roofline"]["frac"],3))
+print("secondary", d["roofline_secondary"]["kernel"][:40], round(d["roofline_secondary"]["achieved"],1), round(d["roofline_secondary"]["frac"],3))
+print({k:round(v["ms_per_frame"],3) for k,v in d["kernel_breakdown"].items()})
 PY
-}
-run base
-SMB_LIB_PATH=$PWD/streammind_b200/libsmb_a3.so run attn3
-SMB_LIB_PATH=$PWD/streammind_b200/libsmb_a3.so timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_frame_path_gpu.py -m gpu -q -x -p no:cacheprovider -k "attention or full_width" 2>&1 | tail -2
+timeout 300 python bench.py --steps 3 --warmup 3 --chunk 8 --no-cpu-baseline > gpurun_out/bench_chunk8.json 2> gpurun_out/bench_chunk8.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_chunk8.json")); print("chunk8 value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1))
+PY
