@@ -362,7 +362,7 @@ def run_ours(args):
 
         # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # reported at N = 1 only (bounded sample on the host cores)
             threads = os.cpu_count() or 1
             sec = cpu_reference_frames(args.cpu_frames, threads)
             cpu = {"value": args.cpu_frames / sec, "unit": "frames/s", "cores": threads, "kind": "port",
