@@ -161,6 +161,12 @@ const char* sm_profile_class_name(int cls);
  * bench.py uses it to time one kernel class at a time inside the same captured step. */
 int sm_debug_kernel_filter(sm_handle* h, unsigned mask);
 
+/* Debug / test: which attention kernel serves d = 64 non-causal attention (the vision tower).  -1 = default
+ * (tcgen05 kernel csrc/attention_tc.cuh when the launch has >= 148 CTAs of 128 query rows, else the mma.sync
+ * kernel csrc/attention.cuh; SMB_ATTN_TC=0/2 in the environment overrides), 0 = mma.sync kernel always,
+ * 2 = tcgen05 kernel wherever its layout conditions hold. */
+int sm_debug_attention_mode(sm_handle* h, int mode);
+
 /* Debug / measurement: per-op trace of the persistent vision-tower kernel (csrc/vit_mega.cuh).  device_buf
  * (NULL = off) receives 4 int64 slots per op of the plan for chunk size B: max over CTAs of the globaltimer
  * when the op's grid barrier was passed, when its work was done, and when the CTA arrived.  n_ops / types

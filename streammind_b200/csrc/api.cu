@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "gemv_tma.cuh"
@@ -79,6 +80,7 @@ struct sm_handle {
     bool gemv_tma = false;            // weight-streaming GEMVs through the bulk-copy ring (gemv_tma.cuh, experimental)
     int gemv_grid_cap = 0;            // > 0: GEMVs use at most this many CTAs (background gate)
     bool vit_tiled = true;            // ViT GEMM weights are stored pre-tiled (gemm_tc.cuh GemmArgs::w_tiled)
+    int attn_mode = -1;               // debug (sm_debug_attention_mode): -1 = SMB_ATTN_TC / auto, 0 = mma.sync kernel, 2 = tcgen05 wherever supported
     unsigned kfilter = 0xFFFFFFFFu;   // debug: kernel classes that are actually launched (bench.py per-class timing)
     long long* gemm_dbg = nullptr;   // device buffer for sm_test_gemm_trace
     bool profiling = false;
@@ -587,7 +589,39 @@ int launch_attn_t(sm_handle* h, const AttnArgs& a, int q_tiles, int heads, int b
     CUDA_OK(h, cudaGetLastError());
     return 0;
 }
+// tcgen05 attention (attention_tc.cuh): d = 64, non-causal, q / k / v packed in one row-major matrix, batch items
+// contiguous (the vision tower's qkv activation)
+template <typename T>
+int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cudaStream_t st) {
+    if (!kon(h, KC_ATTN)) return 0;
+    const int pitch = static_cast<int>(a.q_ss);                 // elements per packed row (3C)
+    const CUtensorMap* tm = get_tmap(h, a.q, batch * a.q_len, pitch, kAtcTile);
+    if (!tm) return 1;
+    AttnTcArgs t{};
+    t.o = a.o; t.o_ss = a.o_ss; t.S = a.q_len; t.col_q = 0;
+    t.col_k = static_cast<int>((static_cast<const char*>(a.k) - static_cast<const char*>(a.q)) / 2);
+    t.col_v = static_cast<int>((static_cast<const char*>(a.v) - static_cast<const char*>(a.q)) / 2);
+    t.scale_log2e = a.scale_log2e;
+    {
+        ProfScope ps(h, KC_ATTN, st);
+        CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, dim3((a.q_len + kAtcTile - 1) / kAtcTile, heads, batch), dim3(kAtcThreads),
+                              static_cast<size_t>(attn_tc_smem_bytes()), st, *tm, t));
+    }
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cudaStream_t st) {
+    // one frame alone is only 80 CTAs of 128 query rows: the 64-row mma.sync kernel (160 CTAs) fills the machine better
+    static const int env_tc = getenv("SMB_ATTN_TC") ? atoi(getenv("SMB_ATTN_TC")) : 1;
+    const int use_tc = h->attn_mode >= 0 ? h->attn_mode : env_tc;
+    static const int tc_min_ctas = getenv("SMB_ATTN_TC_MINCTAS") ? atoi(getenv("SMB_ATTN_TC_MINCTAS")) : 148;
+    if (use_tc && ((a.q_len + kAtcTile - 1) / kAtcTile) * heads * batch >= (use_tc == 2 ? 0 : tc_min_ctas) && D == 64 && !a.causal && a.group == 1 && a.q_len == a.kv_len && a.q_ss == a.k_ss && a.q_ss == a.v_ss &&
+        a.k_hs == 64 && a.v_hs == 64 && a.q_bs == static_cast<long long>(a.q_len) * a.q_ss && a.k_bs == a.q_bs && a.v_bs == a.q_bs &&
+        a.o_bs == static_cast<long long>(a.q_len) * a.o_ss && (a.q_ss * 2) % 16 == 0) {
+        DISPATCH_T(h, T, return launch_attn_tc_t<T>(h, a, heads, batch, st);)
+    }
     const int q_tiles = (a.q_len + kAttnBQ - 1) / kAttnBQ;
     if (D == 64) { DISPATCH_T(h, T, return launch_attn_t<T, 64>(h, a, q_tiles, heads, batch, st);) }
     if (D == 128) { DISPATCH_T(h, T, return launch_attn_t<T, 128>(h, a, q_tiles, heads, batch, st);) }
@@ -612,6 +646,7 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
+    CUDA_OK(h, cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
     // One shared-memory carve-out for every kernel of the per-frame chain: an SM has to drain before it can
     // change its L1/shared split, which serialises back-to-back launches (and defeats PDL overlap) when
@@ -2007,6 +2042,12 @@ int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, in
     a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
     a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
     return launch_attn(h, a, D, H, B, static_cast<cudaStream_t>(stream));
+}
+
+int sm_debug_attention_mode(sm_handle* h, int mode) {
+    if (!h) return 1;
+    h->attn_mode = mode;
+    return 0;
 }
 
 int sm_test_gemm_trace(sm_handle* h, long long* device_buf) {

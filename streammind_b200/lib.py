@@ -58,6 +58,7 @@ SYMBOLS = {
     "sm_profile_read": (_I, [_VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sm_profile_class_name": (C.c_char_p, [_I]),
     "sm_debug_kernel_filter": (_I, [_VP, C.c_uint]),
+    "sm_debug_attention_mode": (_I, [_VP, _I]),
     "sm_debug_mega_trace": (_I, [_VP, _VP, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I]),
     "sm_launch_count": (_LL, [_VP, _I]),
 }

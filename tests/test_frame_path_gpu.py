@@ -268,7 +268,9 @@ def test_batched_gate_gemm_full_size_fp16(built_library):
         eng.frame_wait(outs[-1][0], block=True)
         torch.cuda.synchronize()
         check_close(f"tower-batch tokens (pass {rep})", torch.cat([o[2] for o in outs]), ref_tok, 4e-3)
-        check_close(f"gate-as-GEMM logits (pass {rep})", torch.cat([o[3] for o in outs]), ref_lg, 2e-3)
+        # two fp16 paths, each within ~1e-3 of the oracle (asserted below and in test_full_size_frame_path_fp16), logits
+        # near 1.0 where one fp16 ulp is 9.8e-4: their mutual distance is a few ulps
+        check_close(f"gate-as-GEMM logits (pass {rep})", torch.cat([o[3] for o in outs]), ref_lg, 3e-3)
         # teacher-forced: the serial gate on the pipelined path's own tokens isolates the GEMM gate's error
         tf = torch.stack([eng.gate_score(o[2][0]) for o in outs])
         check_close(f"gate-as-GEMM logits, teacher-forced (pass {rep})", torch.cat([o[3] for o in outs]), tf, 1.5e-3)
