@@ -602,6 +602,7 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
     t.col_k = static_cast<int>((static_cast<const char*>(a.k) - static_cast<const char*>(a.q)) / 2);
     t.col_v = static_cast<int>((static_cast<const char*>(a.v) - static_cast<const char*>(a.q)) / 2);
     t.scale_log2e = a.scale_log2e;
+    t.dbg = h->gemm_dbg;
     {
         ProfScope ps(h, KC_ATTN, st);
         CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, dim3((a.q_len + kAtcTile - 1) / kAtcTile, heads, batch), dim3(kAtcThreads),
