@@ -29,6 +29,10 @@ struct AttnTcArgs {
 constexpr int kAtcThreads = 192;
 constexpr int kAtcTile = 128;                 // query rows per CTA and keys per TMA box
 constexpr int kAtcTileBytes = kAtcTile * 128; // 128 rows x 64 halfs
+#ifndef SMB_ATC_POLY_EVERY
+#define SMB_ATC_POLY_EVERY 4
+#endif
+constexpr int kAtcPolyEvery = SMB_ATC_POLY_EVERY;   // every n-th key pair takes its exp2 on the FMA pipe (0x7fffffff = none)
 constexpr float kAtcLazy = 8.f;               // rescale O only when the row maximum grew by more than 2^8 (log2 domain)
 inline int attn_tc_smem_bytes() { return 7 * kAtcTileBytes + 256; }   // Q, 2 K, 2 V, 2 P buffers + barriers (base 1024-aligned)
 
@@ -68,6 +72,26 @@ __device__ __forceinline__ uint64_t atc_add2(uint64_t a, uint64_t b) {
     uint64_t r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
+}
+
+// 2^x on the FMA pipe for a share of the elements (the MUFU unit, 16 exp2 / clk / SM, is this kernel's bound):
+// x = floor(x) + fr, 2^fr by a degree-4 polynomial (max relative error 2.7e-6 on [0, 1), fitted for this kernel), the
+// integer part added into the exponent field.  x is clamped at -126 (the result then rounds to 0 in T).
+__device__ __forceinline__ void atc_exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    const uint64_t x = atc_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    uint64_t t;                                       // 1.5 * 2^23 + floor(x): the low mantissa bits hold floor(x)
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(atc_pack(12582912.f, 12582912.f)));
+    const uint64_t j = atc_add2(t, atc_pack(-12582912.f, -12582912.f));
+    const uint64_t fr = atc_fma2(j, atc_pack(-1.f, -1.f), x);
+    uint64_t p = atc_fma2(fr, atc_pack(0x1.bb7cd4p-7f, 0x1.bb7cd4p-7f), atc_pack(0x1.aa13f0p-5f, 0x1.aa13f0p-5f));
+    p = atc_fma2(p, fr, atc_pack(0x1.ee798ap-3f, 0x1.ee798ap-3f));
+    p = atc_fma2(p, fr, atc_pack(0x1.62d166p-1f, 0x1.62d166p-1f));
+    p = atc_fma2(p, fr, atc_pack(0x1.00002cp+0f, 0x1.00002cp+0f));
+    float t0, t1, q0, q1;
+    atc_unpack(t, t0, t1);
+    atc_unpack(p, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 template <typename T>
@@ -201,12 +225,13 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
             tmem_ld_x32(tS + sb * 64 + lane_addr, ra);
             tmem_ld_x32(tS + sb * 64 + lane_addr + 32, rb);
             tmem_wait_ld();
-            float mh = -INFINITY;
+            float mh4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // four chains: the scan is latency-, not issue-bound
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                if (!partial || key0 + i < a.S) mh = fmaxf(mh, __uint_as_float(ra[i]));
-                if (!partial || key0 + 32 + i < a.S) mh = fmaxf(mh, __uint_as_float(rb[i]));
+                if (!partial || key0 + i < a.S) mh4[i & 3] = fmaxf(mh4[i & 3], __uint_as_float(ra[i]));
+                if (!partial || key0 + 32 + i < a.S) mh4[i & 3] = fmaxf(mh4[i & 3], __uint_as_float(rb[i]));
             }
+            const float mh = fmaxf(fmaxf(mh4[0], mh4[1]), fmaxf(mh4[2], mh4[3]));
             // Lazy online softmax: the reference maximum moves only when the row maximum outgrew it by more than 2^kAtcLazy,
             // so P stays <= 2^kAtcLazy (exact in T and in the fp32 sums) and O is rescaled a few times per row at most.
             float f = 1.f;
@@ -247,8 +272,9 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
                     const float s1 = __uint_as_float(ci == 0 ? ra[2 * i + 1] : rb[2 * i + 1]);
                     float x0, x1;
                     atc_unpack(atc_fma2(atc_pack(s0, s1), c2, nmc2), x0, x1);
-                    float p0 = atc_ex2(x0);
-                    float p1 = atc_ex2(x1);
+                    float p0, p1;
+                    if ((i % kAtcPolyEvery) == kAtcPolyEvery - 1) atc_exp2_poly2(x0, x1, p0, p1);
+                    else { p0 = atc_ex2(x0); p1 = atc_ex2(x1); }
                     if (partial) {
                         if (key0 + ci * 32 + 2 * i >= a.S) p0 = 0.f;
                         if (key0 + ci * 32 + 2 * i + 1 >= a.S) p1 = 0.f;
