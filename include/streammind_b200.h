@@ -142,7 +142,8 @@ int sm_kv_set_len(sm_handle* h, int len);   /* truncate to a common prefix; len 
 int sm_test_gemm(sm_handle* h, const void* x /*[M,K]*/, const void* w /*[N,K]*/, const void* bias /*[N]|NULL*/,
                  void* out /*[M,N]*/, int M, int N, int K, int epi, int force_swap /*-1 auto*/, int force_bn /*0 auto*/,
                  void* stream);
-/* Debug: while device_buf != NULL every GEMM CTA writes 8 phase timestamps (globaltimer, ns). */
+/* Debug: while device_buf != NULL every GEMM CTA writes 8 phase timestamps (globaltimer, ns); the tcgen05 attention
+ * kernel writes the clock64 trace of one mid-grid CTA (8 rows of 64 slots, tools/attn_trace.py) into the same buffer. */
 int sm_test_gemm_trace(sm_handle* h, long long* device_buf);
 int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out /*[B*S, H*D]*/, int B, int S, int H,
                       int D, void* stream);
