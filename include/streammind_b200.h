@@ -165,7 +165,7 @@ int sm_debug_kernel_filter(sm_handle* h, unsigned mask);
 /* Debug / test: which attention kernel serves d = 64 non-causal attention (the vision tower).  -1 = default
  * (tcgen05 kernel csrc/attention_tc.cuh when the launch has >= 148 CTAs of 128 query rows, else the mma.sync
  * kernel csrc/attention.cuh; SMB_ATTN_TC=0/2 in the environment overrides), 0 = mma.sync kernel always,
- * 2 = tcgen05 kernel wherever its layout conditions hold. */
+ * 2 = tcgen05 kernel wherever its layout conditions hold, 3 = its three-CTA-per-SM variant (attention_tc3_kernel). */
 int sm_debug_attention_mode(sm_handle* h, int mode);
 
 /* Debug / measurement: per-op trace of the persistent vision-tower kernel (csrc/vit_mega.cuh).  device_buf

@@ -595,7 +595,10 @@ template <typename T>
 int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cudaStream_t st) {
     if (!kon(h, KC_ATTN)) return 0;
     const int pitch = static_cast<int>(a.q_ss);                 // elements per packed row (3C)
-    const CUtensorMap* tm = get_tmap(h, a.q, batch * a.q_len, pitch, kAtcTile);
+    // three lean CTAs per SM (attention_tc3_kernel, 64-row TMA boxes) or two with double-buffered S (attention_tc_kernel)
+    static const int env_lean = getenv("SMB_ATTN_TC3") ? atoi(getenv("SMB_ATTN_TC3")) : 0;
+    const bool lean = h->attn_mode == 3 || (h->attn_mode != 2 && env_lean != 0);
+    const CUtensorMap* tm = get_tmap(h, a.q, batch * a.q_len, pitch, lean ? 64 : kAtcTile);
     if (!tm) return 1;
     AttnTcArgs t{};
     t.o = a.o; t.o_ss = a.o_ss; t.S = a.q_len; t.col_q = 0;
@@ -605,8 +608,9 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
     t.dbg = h->gemm_dbg;
     {
         ProfScope ps(h, KC_ATTN, st);
-        CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, dim3((a.q_len + kAtcTile - 1) / kAtcTile, heads, batch), dim3(kAtcThreads),
-                              static_cast<size_t>(attn_tc_smem_bytes()), st, *tm, t));
+        const dim3 grid((a.q_len + kAtcTile - 1) / kAtcTile, heads, batch);
+        if (lean) CUDA_OK(h, launch_pdl(h, attention_tc3_kernel<T>, grid, dim3(kAtcThreads), static_cast<size_t>(attn_tc3_smem_bytes()), st, *tm, t));
+        else CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, grid, dim3(kAtcThreads), static_cast<size_t>(attn_tc_smem_bytes()), st, *tm, t));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -616,7 +620,7 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
 int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cudaStream_t st) {
     // one frame alone is only 80 CTAs of 128 query rows: the 64-row mma.sync kernel (160 CTAs) fills the machine better
     static const int env_tc = getenv("SMB_ATTN_TC") ? atoi(getenv("SMB_ATTN_TC")) : 1;
-    const int use_tc = h->attn_mode >= 0 ? h->attn_mode : env_tc;
+    const int use_tc = h->attn_mode >= 0 ? (h->attn_mode == 3 ? 2 : h->attn_mode) : env_tc;
     static const int tc_min_ctas = getenv("SMB_ATTN_TC_MINCTAS") ? atoi(getenv("SMB_ATTN_TC_MINCTAS")) : 148;
     if (use_tc && ((a.q_len + kAtcTile - 1) / kAtcTile) * heads * batch >= (use_tc == 2 ? 0 : tc_min_ctas) && D == 64 && !a.causal && a.group == 1 && a.q_len == a.kv_len && a.q_ss == a.k_ss && a.q_ss == a.v_ss &&
         a.k_hs == 64 && a.v_hs == 64 && a.q_bs == static_cast<long long>(a.q_len) * a.q_ss && a.k_bs == a.q_bs && a.v_bs == a.q_bs &&
@@ -648,6 +652,7 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes()));
+    CUDA_OK(h, cudaFuncSetAttribute(attention_tc3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
     // One shared-memory carve-out for every kernel of the per-frame chain: an SM has to drain before it can
     // change its L1/shared split, which serialises back-to-back launches (and defeats PDL overlap) when

@@ -284,7 +284,7 @@ class Engine:
         return out
 
     def test_attention(self, qkv: torch.Tensor, B: int, S: int, H: int, D: int, mode: int = -1) -> torch.Tensor:
-        """mode: -1 default kernel choice, 0 mma.sync kernel, 2 tcgen05 kernel (sm_debug_attention_mode)."""
+        """mode: -1 default kernel choice, 0 mma.sync kernel, 2 / 3 tcgen05 kernels (sm_debug_attention_mode)."""
         self._check(self.lib.sm_debug_attention_mode(self._h, mode))
         out = torch.empty(B * S, H * D, dtype=qkv.dtype, device=qkv.device)
         self._check(self.lib.sm_test_attention(self._h, qkv.data_ptr(), out.data_ptr(), B, S, H, D, self._stream()))
