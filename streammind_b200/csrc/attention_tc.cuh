@@ -30,9 +30,17 @@ constexpr int kAtcThreads = 192;
 constexpr int kAtcTile = 128;                 // query rows per CTA and keys per TMA box
 constexpr int kAtcTileBytes = kAtcTile * 128; // 128 rows x 64 halfs
 #ifndef SMB_ATC_POLY_EVERY
-#define SMB_ATC_POLY_EVERY 4
+#define SMB_ATC_POLY_EVERY 0x7fffffff
 #endif
-constexpr int kAtcPolyEvery = SMB_ATC_POLY_EVERY;   // every n-th key pair takes its exp2 on the FMA pipe (0x7fffffff = none)
+// every n-th key pair takes its exp2 on the FMA pipe (atc_exp2_poly2).  Measured: n = 2, 3, 4 and "none" give the same
+// class time (the kernel is not MUFU-bound) and the polynomial costs ~95 extra instructions per warp and half: off.
+constexpr int kAtcPolyEvery = SMB_ATC_POLY_EVERY;
+// -DSMB_ATC_TRACE compiles the clock64 trace (AttnTcArgs::dbg, tools/attn_trace.py) into attention_tc_kernel
+#ifdef SMB_ATC_TRACE
+#define ATC_STAMP(cond, slot) do { if (dbg && (cond)) dbg[slot] = clock64(); } while (0)
+#else
+#define ATC_STAMP(cond, slot) do { } while (0)
+#endif
 constexpr float kAtcLazy = 8.f;               // rescale O only when the row maximum grew by more than 2^8 (log2 domain)
 inline int attn_tc_smem_bytes() { return 7 * kAtcTileBytes + 256; }   // Q, 2 K, 2 V, 2 P buffers + barriers (base 1024-aligned)
 
@@ -132,9 +140,11 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tS = tmem_base, tO = tmem_base + 128u;    // S buffers at columns 0 and 64, O at 128
     pdl_wait();
+#ifdef SMB_ATC_TRACE
     long long* dbg = (a.dbg != nullptr && blockIdx.x == min(2u, gridDim.x - 1) && blockIdx.y == gridDim.y / 2 && blockIdx.z == gridDim.z / 2)
                          ? a.dbg : nullptr;
-    if (dbg && threadIdx.x == 0) dbg[7 * 64] = clock64();
+#endif
+    ATC_STAMP(threadIdx.x == 0, 7 * 64);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
             const int st = it & 1;
             const uint32_t par = (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u;
             mbar_wait(&k_empty[st], par);
-            if (dbg && lane == 0) dbg[6 * 64 + it] = clock64();
+            ATC_STAMP(lane == 0, 6 * 64 + it);
             if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&k_full[st], kAtcTileBytes);
                 tma_load_2d(sK + st * kAtcTileBytes, &tmap, &k_full[st], a.col_k + h * 64, row_base + it * kAtcTile, kEvictLast);
@@ -166,12 +176,12 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
         const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64, Cvt<T>::kBf16);
         auto issue_s = [&](int g) {
             const int it = g >> 1, hh = g & 1, st = it & 1, sb = g & 1;
-            if (dbg && lane == 0) dbg[3 * 64 + g] = clock64();
+            ATC_STAMP(lane == 0, 3 * 64 + g);
             if (hh == 0) mbar_wait(&k_full[st], static_cast<uint32_t>(it >> 1) & 1u);
-            if (dbg && lane == 0) dbg[4 * 64 + g] = clock64();
+            ATC_STAMP(lane == 0, 4 * 64 + g);
             mbar_wait(&s_empty[sb], (static_cast<uint32_t>(g >> 1) & 1u) ^ 1u);    // softmax has read S of half g - 2
             tc_fence_after();
-            if (dbg && lane == 0) dbg[5 * 64 + g] = clock64();
+            ATC_STAMP(lane == 0, 5 * 64 + g);
             if (elect_one_sync()) {
                 const uint64_t qd = umma_desc_sw128_kmajor(smem_u32(sQ));
                 const uint64_t kd = umma_desc_sw128_kmajor(smem_u32(sK + st * kAtcTileBytes + hh * 8192));
@@ -187,11 +197,11 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
         for (int g = 0; g < G; ++g) {
             if (g + 1 < G) issue_s(g + 1);
             const int it = g >> 1, hh = g & 1, st = it & 1, pb = g & 1;
-            if (dbg && lane == 0) dbg[7 * 64 + 1 + g] = clock64();
+            ATC_STAMP(lane == 0, 7 * 64 + 1 + g);
             mbar_wait(&p_full[pb], static_cast<uint32_t>(g >> 1) & 1u);     // P of half g written, O rescaled if it had to be
             if (hh == 0) mbar_wait(&v_full[st], static_cast<uint32_t>(it >> 1) & 1u);
             tc_fence_after();
-            if (dbg && lane == 0) dbg[7 * 64 + 24 + g] = clock64();
+            ATC_STAMP(lane == 0, 7 * 64 + 24 + g);
             if (elect_one_sync()) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {    // 16 keys per MMA: P buffer pb (K-major), V rows 64 hh + 16 t .. (MN-major)
@@ -217,10 +227,10 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
         for (int g = 0; g < G; ++g) {
             const int sb = g & 1, key0 = g * 64;
             const bool partial = key0 + 64 > a.S;
-            if (dbg && threadIdx.x == 64) dbg[g] = clock64();
+            ATC_STAMP(threadIdx.x == 64, g);
             mbar_wait(&s_full[sb], static_cast<uint32_t>(g >> 1) & 1u);
             tc_fence_after();
-            if (dbg && threadIdx.x == 64) dbg[64 + g] = clock64();
+            ATC_STAMP(threadIdx.x == 64, 64 + g);
             uint32_t ra[32], rb[32];
             tmem_ld_x32(tS + sb * 64 + lane_addr, ra);
             tmem_ld_x32(tS + sb * 64 + lane_addr + 32, rb);
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
             fence_proxy_async_smem();      // P (generic-proxy stores) -> tensor-core reads (async proxy)
             mbar_arrive(&p_full[sb]);
             mbar_arrive(&s_empty[sb]);
-            if (dbg && threadIdx.x == 64) dbg[2 * 64 + g] = clock64();
+            ATC_STAMP(threadIdx.x == 64, 2 * 64 + g);
         }
         // ---- O / l -> global
         mbar_wait(o_full, 0);
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
             }
         }
         tc_fence_before();
-        if (dbg && threadIdx.x == 64) dbg[7 * 64 + 60] = clock64();
+        ATC_STAMP(threadIdx.x == 64, 7 * 64 + 60);
     }
     __syncthreads();
     if (warp == 1) {

@@ -1,4 +1,5 @@
-"""clock64 trace of one mid-grid CTA of the tcgen05 attention kernel (AttnTcArgs::dbg), batch 8 of the ViT shape."""
+"""clock64 trace of one mid-grid CTA of the tcgen05 attention kernel (AttnTcArgs::dbg), batch 8 of the ViT shape.
+Needs a library built with -DSMB_ATC_TRACE (the stamps are compiled out of the product build)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
