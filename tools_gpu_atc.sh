@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_attention_gpu.py -m gpu -x -q 2>&1 | tail -3
-rc=${PIPESTATUS[0]}
-if [ $rc -ne 0 ]; then echo "ATTENTION TEST FAILED rc=$rc"; exit 0; fi
-timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/nopoly.json 2> gpurun_out/nopoly.err
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/nopoly.json").read().strip().splitlines()[-1])
-print("no poly, no stamps:", d["value"], d["e2e"]["value"], d["kernel_breakdown"]["attention_kernel"]["ms_per_frame"])
-PY
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
+timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 200 gpurun_out/bench_final.json
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 300 gpurun_out/bench_ref.json
