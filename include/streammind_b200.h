@@ -73,6 +73,18 @@ int sm_finalize_weights(sm_handle* h);
  * state on the model object and never resets it (videollama2_mistral.py:159-165). */
 int sm_stream_reset(sm_handle* h);
 
+/* Frame preprocessing: mm_utils.process_video / process_image with aspect_ratio 'pad'
+ * (streammind/mm_utils.py:446-464) = expand2square(frame, background) (mm_utils.py:257-268) ->
+ * CLIPImageProcessor.preprocess (transformers 4.44.2: bicubic resize through PIL.Image.resize of Pillow 9.4.0 ->
+ * centre crop -> rescale 1/255 -> normalize -> channels first) -> cast to the model dtype (.half() in
+ * video_score_stream_demo.py:285-287).  frames [n, H, W, 3] uint8 RGB (host memory unless frames_on_device) ->
+ * pixels_out [n, 3, vit_image, vit_image] model dtype on the device: the input of sm_vit_encode / sm_frame_submit.
+ * mean / std: the processor's image_mean / image_std as float32; background: tuple(int(x*255) for x in image_mean).
+ * Bit-exact with the reference's PIL + numpy arithmetic (tests/test_preprocess_gpu.py). */
+int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H, int W, int frames_on_device,
+                         const float* mean /*[3]*/, const float* std /*[3]*/, const int* background /*[3]*/,
+                         void* pixels_out, void* stream);
+
 /* CLIPVisionTower.forward + feature_select (multimodal_encoder/clip_encoder.py:41-53,31-39).
  * pixels [B,3,H,W] model dtype, contiguous NCHW -> feats_out [B, P, C] (may be NULL) and
  * pooled_out [B, C] = mean over patches (multimodal_projector/builder.py:405; may be NULL). */

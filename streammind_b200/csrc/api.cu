@@ -21,6 +21,7 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "preprocess.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "gemv_tma.cuh"
@@ -70,6 +71,12 @@ struct sm_handle {
     int esz = 2;
     std::string err;
     std::vector<void*> allocs;
+    // frame preprocessing (sm_preprocess_frames): resample tables per padded side, grow-only staging / intermediate buffers
+    struct PreTable { int ksize; int* bounds; int* kk; };
+    std::map<int, PreTable> pre_tables;
+    void* pre_src = nullptr; size_t pre_src_bytes = 0;
+    void* pre_tmp = nullptr; size_t pre_tmp_bytes = 0;
+    void* pre_lut = nullptr; float pre_lut_key[6] = {0, 0, 0, 0, 0, 0};
     std::unordered_map<std::string, Slot> slots;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
     PFN_encodeTiled encode = nullptr;
@@ -1729,6 +1736,78 @@ int sm_vit_encode(sm_handle* h, const void* pixels, int B, void* feats_out, void
     cudaSetDevice(h->device);
     if (pipe_join(h, static_cast<cudaStream_t>(stream))) return 1;
     return run_vit(h, pixels, B, feats_out, pooled_out, static_cast<cudaStream_t>(stream));
+}
+
+int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H, int W, int frames_on_device, const float* mean,
+                         const float* std_, const int* background, void* pixels_out, void* stream) {
+    if (!h || !frames || !mean || !std_ || !background || !pixels_out) return fail(h, "sm_preprocess_frames: null argument");
+    if (n < 1 || H < 1 || W < 1) return fail(h, "sm_preprocess_frames: n=%d H=%d W=%d", n, H, W);
+    const int out = h->cfg.vit_image;
+    if (out <= 0) return fail(h, "sm_preprocess_frames: vision tower not configured");
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = std::max(H, W);
+    // buffers grow only; a grown buffer is replaced after the stream has drained (earlier calls may still read it)
+    auto grow = [&](void*& p, size_t& have, size_t need) -> int {
+        if (need <= have) return 0;
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        if (p) { CUDA_OK(h, cudaFree(p)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), p)); }
+        CUDA_OK(h, cudaMalloc(&p, need));
+        h->allocs.push_back(p);
+        have = need;
+        return 0;
+    };
+    auto tab = h->pre_tables.find(S);
+    if (tab == h->pre_tables.end()) {
+        std::vector<int> bounds, kk;
+        sm_handle::PreTable t{};
+        t.ksize = pre_build_table(S, out, bounds, kk);
+        CUDA_OK(h, cudaMalloc(reinterpret_cast<void**>(&t.bounds), bounds.size() * sizeof(int)));
+        CUDA_OK(h, cudaMalloc(reinterpret_cast<void**>(&t.kk), kk.size() * sizeof(int)));
+        h->allocs.push_back(t.bounds); h->allocs.push_back(t.kk);
+        CUDA_OK(h, cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_OK(h, cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        tab = h->pre_tables.emplace(S, t).first;
+    }
+    // rescale (uint8 * (1/255) in double -> float) + normalize ((x - mean) / std in float) + rounding to the model dtype,
+    // as transformers' image_transforms.rescale / normalize and the caller's .half() do: 3 x 256 possible results
+    const float key[6] = {mean[0], mean[1], mean[2], std_[0], std_[1], std_[2]};
+    if (!h->pre_lut || memcmp(key, h->pre_lut_key, sizeof key) != 0) {
+        std::vector<uint16_t> lut(3 * 256);
+        for (int c = 0; c < 3; ++c)
+            for (int v = 0; v < 256; ++v) {
+                const float x = static_cast<float>(static_cast<double>(v) * (1.0 / 255));
+                const float y = (x - mean[c]) / std_[c];
+                if (h->cfg.dtype == SM_DTYPE_BF16) { const __nv_bfloat16 t = __float2bfloat16_rn(y); memcpy(&lut[c * 256 + v], &t, 2); }
+                else { const __half t = __float2half_rn(y); memcpy(&lut[c * 256 + v], &t, 2); }
+            }
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        if (!h->pre_lut) { CUDA_OK(h, cudaMalloc(&h->pre_lut, lut.size() * 2)); h->allocs.push_back(h->pre_lut); }
+        CUDA_OK(h, cudaMemcpy(h->pre_lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
+        memcpy(h->pre_lut_key, key, sizeof key);
+    }
+    const size_t src_bytes = static_cast<size_t>(n) * H * W * 3;
+    const uint8_t* src = frames;
+    if (!frames_on_device) {
+        if (grow(h->pre_src, h->pre_src_bytes, src_bytes)) return 1;
+        CUDA_OK(h, cudaMemcpyAsync(h->pre_src, frames, src_bytes, cudaMemcpyHostToDevice, st));
+        src = static_cast<const uint8_t*>(h->pre_src);
+    }
+    if (grow(h->pre_tmp, h->pre_tmp_bytes, static_cast<size_t>(n) * S * out * 3)) return 1;
+    PreArgs a{};
+    a.src = src; a.tmp = static_cast<uint8_t*>(h->pre_tmp); a.bounds = tab->second.bounds; a.kk = tab->second.kk;
+    a.H = H; a.W = W; a.S = S; a.out = out; a.ksize = tab->second.ksize;
+    a.pad_x = H > W ? (H - W) / 2 : 0;       // expand2square: paste at ((height - width) // 2, 0) / (0, (width - height) // 2)
+    a.pad_y = W > H ? (W - H) / 2 : 0;
+    a.bg0 = background[0]; a.bg1 = background[1]; a.bg2 = background[2];
+    preprocess_h_kernel<<<dim3((out + 127) / 128, S, n), 128, 0, st>>>(a);
+    count_launch(h);
+    DISPATCH_T(h, T, {
+        preprocess_v_kernel<T><<<dim3((out + 127) / 128, out, n), 128, 0, st>>>(a, static_cast<const T*>(h->pre_lut), static_cast<T*>(pixels_out));
+        count_launch(h);
+    })
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
 }
 
 int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, void* stream) {

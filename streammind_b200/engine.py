@@ -15,6 +15,10 @@ import torch
 
 from . import lib as _lib
 
+# openai/clip-vit-large-patch14-336 preprocessor_config.json (CLIPImageProcessor image_mean / image_std)
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
 _DT = {torch.float16: _lib.SM_DTYPE_F16, torch.bfloat16: _lib.SM_DTYPE_BF16}
 
 
@@ -136,6 +140,29 @@ class Engine:
 
     def reset_stream(self):
         self._check(self.lib.sm_stream_reset(self._h))
+
+    # ------------------------------------------------------------------ frame preprocessing
+    def preprocess_frames(self, frames, image_mean=OPENAI_CLIP_MEAN, image_std=OPENAI_CLIP_STD) -> torch.Tensor:
+        """uint8 RGB frames [n, H, W, 3] (numpy / CPU tensor / CUDA tensor) -> pixels [n, 3, image, image] in the model
+        dtype on the device: expand2square + CLIPImageProcessor.preprocess + .half() of the reference
+        (mm_utils.py:446-464, 257-268), computed by sm_preprocess_frames."""
+        import numpy as np
+        t = torch.from_numpy(np.ascontiguousarray(frames)) if isinstance(frames, np.ndarray) else frames.contiguous()
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise ValueError(f"frames must be uint8 [n, H, W, 3], got {t.dtype} {tuple(t.shape)}")
+        if t.is_cuda and t.device != self.device:
+            raise ValueError(f"frames are on {t.device}, the engine is on {self.device}")
+        n, H, W, _ = t.shape
+        img = self.cfg.vit_image
+        out = torch.empty(n, 3, img, img, dtype=self.cfg.dtype, device=self.device)
+        mean = (C.c_float * 3)(*[float(x) for x in image_mean])
+        std = (C.c_float * 3)(*[float(x) for x in image_std])
+        bg = (C.c_int * 3)(*[int(x * 255) for x in image_mean])      # the reference's background colour expression
+        self._check(self.lib.sm_preprocess_frames(self._h, t.data_ptr(), n, H, W, 1 if t.is_cuda else 0, mean, std, bg,
+                                                  out.data_ptr(), self._stream()))
+        if not t.is_cuda:
+            torch.cuda.current_stream(self.device).synchronize()          # the pageable host buffer may go away with `t`
+        return out
 
     # ------------------------------------------------------------------ sub-model calls
     def vit_encode(self, pixels: torch.Tensor, want_feats: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:

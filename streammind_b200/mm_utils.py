@@ -1,6 +1,6 @@
 """Host-side helpers of the streaming call, same names and argument meaning as the reference's
 /root/reference/streammind/mm_utils.py (tokenizer_MMODAL_token :567-604, KeywordsStoppingCriteria
-:616-647)."""
+:616-647, process_video / process_image with aspect_ratio 'pad' :446-464, expand2square :257-268)."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -70,3 +70,27 @@ class KeywordsStoppingCriteria:
 
     def __call__(self, output_ids: torch.Tensor, scores=None, **kw) -> bool:
         return all(self.call_for_batch(output_ids[i].unsqueeze(0), scores) for i in range(output_ids.shape[0]))
+
+
+def process_video(frames, processor=None, aspect_ratio: str = "pad", *, engine) -> torch.Tensor:
+    """mm_utils.process_video (:446-464) for frames that are already decoded: uint8 RGB [n, H, W, 3] (numpy array, list
+    of arrays, CPU or CUDA tensor) -> pixel_values [n, 3, 336, 336] in the tower's dtype, on the engine's device.
+    The reference pads every frame to a square of the processor's mean colour (expand2square), runs
+    CLIPImageProcessor.preprocess on PIL images and casts to half; here the whole chain is one C-ABI call
+    (sm_preprocess_frames, bit-exact with PIL 8-bit bicubic + the processor's float32 arithmetic).
+    processor: anything with image_mean / image_std (e.g. the reference's CLIPImageProcessor); None = CLIP defaults."""
+    if aspect_ratio != "pad":
+        raise NotImplementedError("only aspect_ratio='pad' (the streaming demo's setting) is on the device path")
+    import numpy as np
+    if isinstance(frames, (list, tuple)):
+        frames = np.stack([np.asarray(f) for f in frames])
+    from .engine import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
+    mean = tuple(processor.image_mean) if processor is not None else OPENAI_CLIP_MEAN
+    std = tuple(processor.image_std) if processor is not None else OPENAI_CLIP_STD
+    return engine.preprocess_frames(frames, mean, std)
+
+
+def process_image(image, processor=None, aspect_ratio: str = "pad", *, engine) -> torch.Tensor:
+    """mm_utils.process_image: one RGB image [H, W, 3] -> [1, 3, 336, 336]."""
+    import numpy as np
+    return process_video(np.asarray(image)[None], processor, aspect_ratio, engine=engine)
