@@ -72,7 +72,7 @@ struct sm_handle {
     std::string err;
     std::vector<void*> allocs;
     // frame preprocessing (sm_preprocess_frames): resample tables per padded side, grow-only staging / intermediate buffers
-    struct PreTable { int ksize; int* bounds; int* kk; };
+    struct PreTable { int ksize; int* bounds; int* kk; int* kk_t; };
     std::map<int, PreTable> pre_tables;
     void* pre_src = nullptr; size_t pre_src_bytes = 0;
     void* pre_tmp = nullptr; size_t pre_tmp_bytes = 0;
@@ -1764,7 +1764,12 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
         t.ksize = pre_build_table(S, out, bounds, kk);
         CUDA_OK(h, cudaMalloc(reinterpret_cast<void**>(&t.bounds), bounds.size() * sizeof(int)));
         CUDA_OK(h, cudaMalloc(reinterpret_cast<void**>(&t.kk), kk.size() * sizeof(int)));
-        h->allocs.push_back(t.bounds); h->allocs.push_back(t.kk);
+        CUDA_OK(h, cudaMalloc(reinterpret_cast<void**>(&t.kk_t), kk.size() * sizeof(int)));
+        h->allocs.push_back(t.bounds); h->allocs.push_back(t.kk); h->allocs.push_back(t.kk_t);
+        std::vector<int> kk_t(kk.size());
+        for (int xx = 0; xx < out; ++xx)
+            for (int x = 0; x < t.ksize; ++x) kk_t[static_cast<size_t>(x) * out + xx] = kk[static_cast<size_t>(xx) * t.ksize + x];
+        CUDA_OK(h, cudaMemcpy(t.kk_t, kk_t.data(), kk_t.size() * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_OK(h, cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_OK(h, cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
         tab = h->pre_tables.emplace(S, t).first;
@@ -1795,7 +1800,7 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
     }
     if (grow(h->pre_tmp, h->pre_tmp_bytes, static_cast<size_t>(n) * S * out * 3)) return 1;
     PreArgs a{};
-    a.src = src; a.tmp = static_cast<uint8_t*>(h->pre_tmp); a.bounds = tab->second.bounds; a.kk = tab->second.kk;
+    a.src = src; a.tmp = static_cast<uint8_t*>(h->pre_tmp); a.bounds = tab->second.bounds; a.kk = tab->second.kk; a.kk_t = tab->second.kk_t;
     a.H = H; a.W = W; a.S = S; a.out = out; a.ksize = tab->second.ksize;
     a.pad_x = H > W ? (H - W) / 2 : 0;       // expand2square: paste at ((height - width) // 2, 0) / (0, (width - height) // 2)
     a.pad_y = W > H ? (W - H) / 2 : 0;

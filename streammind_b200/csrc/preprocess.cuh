@@ -17,7 +17,8 @@ struct PreArgs {
     const uint8_t* src;      // [n, H, W, 3]
     uint8_t* tmp;            // [n, S, out, 3]: the padded square after the horizontal pass
     const int* bounds;       // [out, 2] first tap, tap count (same table for both passes: the padded image is square)
-    const int* kk;           // [out, ksize] fixed-point taps
+    const int* kk;           // [out, ksize] fixed-point taps (vertical pass: one row per block, broadcast reads)
+    const int* kk_t;         // [ksize, out] the same taps transposed (horizontal pass: neighbouring threads, neighbouring ints)
     int H, W, S, pad_x, pad_y, out, ksize;
     int bg0, bg1, bg2;       // background colour of expand2square
 };
@@ -31,20 +32,23 @@ __device__ __forceinline__ int pre_clip8(int ss) {
 __global__ void __launch_bounds__(128) preprocess_h_kernel(const PreArgs a) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
     if (xx >= a.out) return;
-    const int xmin = a.bounds[2 * xx], n = a.bounds[2 * xx + 1];
-    const int* k = a.kk + static_cast<size_t>(xx) * a.ksize;
-    int s0 = 1 << (kPreBits - 1), s1 = s0, s2 = s0;
+    uint8_t* o = a.tmp + ((static_cast<size_t>(f) * a.S + y) * a.out + xx) * 3;
     const int sy = y - a.pad_y;
-    const bool row_in = sy >= 0 && sy < a.H;
-    const uint8_t* row = a.src + (static_cast<size_t>(f) * a.H + (row_in ? sy : 0)) * a.W * 3;
+    if (sy < 0 || sy >= a.H) {       // a padding row: every tap sees the background colour, and taps that sum to 1 +- ksize * 2^-23 return it
+        o[0] = static_cast<uint8_t>(a.bg0); o[1] = static_cast<uint8_t>(a.bg1); o[2] = static_cast<uint8_t>(a.bg2);
+        return;
+    }
+    const int xmin = a.bounds[2 * xx], n = a.bounds[2 * xx + 1];
+    const int* k = a.kk_t + xx;
+    int s0 = 1 << (kPreBits - 1), s1 = s0, s2 = s0;
+    const uint8_t* row = a.src + (static_cast<size_t>(f) * a.H + sy) * a.W * 3;
     for (int x = 0; x < n; ++x) {
         const int sx = xmin + x - a.pad_x;
         int v0 = a.bg0, v1 = a.bg1, v2 = a.bg2;
-        if (row_in && sx >= 0 && sx < a.W) { v0 = row[sx * 3]; v1 = row[sx * 3 + 1]; v2 = row[sx * 3 + 2]; }
-        const int w = k[x];
+        if (sx >= 0 && sx < a.W) { v0 = row[sx * 3]; v1 = row[sx * 3 + 1]; v2 = row[sx * 3 + 2]; }
+        const int w = k[static_cast<size_t>(x) * a.out];
         s0 += v0 * w; s1 += v1 * w; s2 += v2 * w;
     }
-    uint8_t* o = a.tmp + ((static_cast<size_t>(f) * a.S + y) * a.out + xx) * 3;
     o[0] = static_cast<uint8_t>(pre_clip8(s0)); o[1] = static_cast<uint8_t>(pre_clip8(s1)); o[2] = static_cast<uint8_t>(pre_clip8(s2));
 }
 
