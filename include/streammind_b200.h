@@ -85,6 +85,12 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
                          const float* mean /*[3]*/, const float* std /*[3]*/, const int* background /*[3]*/,
                          void* pixels_out, void* stream);
 
+/* Host-only (no GPU needed): the fixed-point bicubic tap table sm_preprocess_frames uses for an axis of in_size ->
+ * out_size pixels = Pillow's precompute_coeffs + normalize_coeffs_8bpc (Resample.c).  ksize_out: taps per output pixel;
+ * bounds_out [out_size, 2] (first source pixel, tap count) and kk_out [out_size, ksize] may be NULL; returns 2 when
+ * kk_capacity (ints) is too small.  Exported so the table can be checked against the oracle on a CPU-only box. */
+int sm_resample_table(int in_size, int out_size, int* ksize_out, int* bounds_out, int* kk_out, long long kk_capacity);
+
 /* CLIPVisionTower.forward + feature_select (multimodal_encoder/clip_encoder.py:41-53,31-39).
  * pixels [B,3,H,W] model dtype, contiguous NCHW -> feats_out [B, P, C] (may be NULL) and
  * pooled_out [B, C] = mean over patches (multimodal_projector/builder.py:405; may be NULL). */

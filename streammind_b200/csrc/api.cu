@@ -1815,6 +1815,18 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
     return 0;
 }
 
+int sm_resample_table(int in_size, int out_size, int* ksize_out, int* bounds_out, int* kk_out, long long kk_capacity) {
+    if (in_size < 1 || out_size < 1 || !ksize_out) return 1;
+    std::vector<int> bounds, kk;
+    *ksize_out = pre_build_table(in_size, out_size, bounds, kk);
+    if (bounds_out) memcpy(bounds_out, bounds.data(), bounds.size() * sizeof(int));
+    if (kk_out) {
+        if (kk_capacity < static_cast<long long>(kk.size())) return 2;
+        memcpy(kk_out, kk.data(), kk.size() * sizeof(int));
+    }
+    return 0;
+}
+
 int sm_pool_features(sm_handle* h, const void* feats, int n, void* pooled_out, void* stream) {
     if (!h || h->cfg.vit_hidden <= 0) return fail(h, "sm_pool_features: not configured");
     cudaSetDevice(h->device);

@@ -59,6 +59,7 @@ SYMBOLS = {
     "sm_profile_class_name": (C.c_char_p, [_I]),
     "sm_debug_kernel_filter": (_I, [_VP, C.c_uint]),
     "sm_debug_attention_mode": (_I, [_VP, _I]),
+    "sm_resample_table": (_I, [_I, _I, C.POINTER(C.c_int), _VP, _VP, _LL]),
     "sm_preprocess_frames": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), _VP, _VP]),
     "sm_debug_mega_trace": (_I, [_VP, _VP, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I]),
     "sm_launch_count": (_LL, [_VP, _I]),

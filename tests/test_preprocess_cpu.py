@@ -41,3 +41,21 @@ def test_coefficients_shape_and_normalisation():
     assert np.all(np.abs(kk.sum(axis=1) - (1 << P.PRECISION_BITS)) <= ksize)      # fixed-point rows sum to ~1.0
     ksize, bounds, kk = P.precompute_coeffs(336, 336)                              # same size: identity taps
     assert np.all(kk.max(axis=1) == 1 << P.PRECISION_BITS)
+
+
+def test_library_tap_tables_match_oracle(built_library):
+    """The C++ table builder inside the library (host code, no GPU) against the oracle's precompute_coeffs for many
+    geometries: down- and up-scaling, odd sizes, the identity."""
+    import ctypes as C
+    from streammind_b200 import lib as L
+    lib = L.load()
+    sizes = [(s, 336) for s in (20, 30, 61, 97, 335, 336, 337, 480, 500, 640, 720, 1080, 1280, 1920, 2160, 3840, 4001)]
+    sizes += [(640, 112), (97, 40), (1000, 224), (224, 448)]
+    for in_size, out_size in sizes:
+        ksize, bounds, kk = P.precompute_coeffs(in_size, out_size)
+        k = C.c_int(0)
+        b = np.zeros((out_size, 2), dtype=np.int32)
+        t = np.zeros((out_size, ksize), dtype=np.int32)
+        rc = lib.sm_resample_table(in_size, out_size, C.byref(k), b.ctypes.data, t.ctypes.data, t.size)
+        assert rc == 0 and k.value == ksize, (in_size, out_size, rc, k.value, ksize)
+        assert np.array_equal(b, bounds) and np.array_equal(t, kk), (in_size, out_size)
