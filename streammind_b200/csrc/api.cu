@@ -1805,10 +1805,16 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
     a.pad_x = H > W ? (H - W) / 2 : 0;       // expand2square: paste at ((height - width) // 2, 0) / (0, (width - height) // 2)
     a.pad_y = W > H ? (W - H) / 2 : 0;
     a.bg0 = background[0]; a.bg1 = background[1]; a.bg2 = background[2];
-    preprocess_h_kernel<<<dim3((out + 127) / 128, S, n), 128, 0, st>>>(a);
+    const size_t row_smem = (static_cast<size_t>(W) * 3 + 15) & ~size_t(15);
+    if (row_smem > 48 * 1024) return fail(h, "sm_preprocess_frames: frames wider than 16384 pixels are not supported (W=%d)", W);
+    preprocess_h_kernel<<<dim3(S, n), 128, row_smem, st>>>(a);
     count_launch(h);
     DISPATCH_T(h, T, {
-        preprocess_v_kernel<T><<<dim3((out + 127) / 128, out, n), 128, 0, st>>>(a, static_cast<const T*>(h->pre_lut), static_cast<T*>(pixels_out));
+        if (out % 4 == 0) {
+            preprocess_v4_kernel<T><<<dim3((out * 3 / 4 + 127) / 128, out, n), 128, 0, st>>>(a, static_cast<const T*>(h->pre_lut), static_cast<T*>(pixels_out));
+        } else {
+            preprocess_v_kernel<T><<<dim3((out + 127) / 128, out, n), 128, 0, st>>>(a, static_cast<const T*>(h->pre_lut), static_cast<T*>(pixels_out));
+        }
         count_launch(h);
     })
     CUDA_OK(h, cudaGetLastError());

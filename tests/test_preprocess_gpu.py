@@ -77,3 +77,15 @@ def test_process_video_mirror_and_timing(engines):
     mb = (1080 * 1920 * 3 + 2 * 1920 * 336 * 3 + 3 * 336 * 336 * 2) / 1e6
     print(f"\npreprocess 1080p -> 336: {us:.1f} us per frame on the device ({mb / us * 1e3:.0f} GB/s of {mb:.1f} MB algorithmic traffic); "
           f"numpy oracle {cpu_ms:.0f} ms per frame")
+
+
+@pytest.mark.parametrize("image", [70, 56])      # 70: byte-wise vertical pass (70 * 3 not a multiple of 4); 56: the 32-bit one
+def test_preprocess_other_tower_sizes(built_library, image):
+    from streammind_b200.engine import Engine
+    eng = Engine(engine_config(torch.float16, vit_image=image, vit_layers=0, proj_d_model=0, gate_layers=0, llm_layers=0))
+    frames = np.stack([make_frame(123, 211, 40), make_frame(123, 211, 41)])
+    out = eng.preprocess_frames(frames)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(P.preprocess_frames(frames, size=image)).half()
+    assert out.shape == (2, 3, image, image) and torch.equal(out.cpu(), ref)
+    eng.close()
