@@ -4,7 +4,8 @@
 // query row (TMEM lane) -- no shuffles.  Per 64-key half tile g:
 //   S_g = Q K_g^T (4 MMAs, N = 64)  ->  P_g = T(exp2(s c - m_ref c)) -> smem (K-major, swizzled)  ->  O += P_g V_g (4 MMAs)
 // S is double-buffered in TMEM (2 x 64 columns) and P in shared memory: the tensor core computes S of half g + 1 and
-// P V of half g - 1 while the softmax threads work on half g; the exp2 (MUFU, 16 / clk / SM) is the bound.
+// P V of half g - 1 while the softmax threads work on half g.  The exp2 rate (MUFU, 16 / clk / SM) is the theoretical
+// bound; measured, the kernel sits 4-5x above it, limited by the per-half dependency chain (profiles/r01_ncu_attention_tc.md).
 // Online softmax with a LAZY reference maximum: m_ref only moves when the row maximum outgrew it by more than 2^8, then
 // the row's O (TMEM) and sum are rescaled by the owning thread (tcgen05.ld / st) -- a handful of times per row at most.
 // V is consumed as the MN-major B operand (rows = keys = K, 64 contiguous d = N): exactly the tile TMA delivers.
