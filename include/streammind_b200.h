@@ -80,7 +80,8 @@ int sm_stream_reset(sm_handle* h);
  * video_score_stream_demo.py:285-287).  frames [n, H, W, 3] uint8 RGB (host memory unless frames_on_device) ->
  * pixels_out [n, 3, vit_image, vit_image] model dtype on the device: the input of sm_vit_encode / sm_frame_submit.
  * mean / std: the processor's image_mean / image_std as float32; background: tuple(int(x*255) for x in image_mean).
- * Bit-exact with the reference's PIL + numpy arithmetic (tests/test_preprocess_gpu.py). */
+ * Bit-exact with the reference's PIL + numpy arithmetic (tests/test_preprocess_gpu.py).  Calls on one handle share
+ * staging buffers: issue them on one stream (or synchronise between streams). */
 int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H, int W, int frames_on_device,
                          const float* mean /*[3]*/, const float* std /*[3]*/, const int* background /*[3]*/,
                          void* pixels_out, void* stream);

@@ -1751,7 +1751,12 @@ int sm_preprocess_frames(sm_handle* h, const unsigned char* frames, int n, int H
     auto grow = [&](void*& p, size_t& have, size_t need) -> int {
         if (need <= have) return 0;
         CUDA_OK(h, cudaStreamSynchronize(st));
-        if (p) { CUDA_OK(h, cudaFree(p)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), p)); }
+        if (p) {
+            CUDA_OK(h, cudaFree(p));
+            auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+            if (it != h->allocs.end()) h->allocs.erase(it);
+            p = nullptr; have = 0;
+        }
         CUDA_OK(h, cudaMalloc(&p, need));
         h->allocs.push_back(p);
         have = need;
