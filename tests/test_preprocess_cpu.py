@@ -59,3 +59,27 @@ def test_library_tap_tables_match_oracle(built_library):
         rc = lib.sm_resample_table(in_size, out_size, C.byref(k), b.ctypes.data, t.ctypes.data, t.size)
         assert rc == 0 and k.value == ksize, (in_size, out_size, rc, k.value, ksize)
         assert np.array_equal(b, bounds) and np.array_equal(t, kk), (in_size, out_size)
+
+
+def test_process_video_mirror_host_behaviour():
+    """mm_utils.process_video: list / array inputs are stacked, the processor's mean / std are forwarded, anything but
+    aspect_ratio='pad' is refused (the reference's other branch has no device path here)."""
+    from streammind_b200 import mm_utils
+
+    class FakeEngine:
+        def preprocess_frames(self, frames, mean, std):
+            self.seen = (np.asarray(frames).shape, tuple(mean), tuple(std))
+            return "pixels"
+
+    class Proc:
+        image_mean = [0.5, 0.4, 0.3]
+        image_std = [0.2, 0.2, 0.1]
+
+    eng = FakeEngine()
+    frames = [make_frame(20, 30, 1), make_frame(20, 30, 2)]
+    assert mm_utils.process_video(frames, Proc(), "pad", engine=eng) == "pixels"
+    assert eng.seen == ((2, 20, 30, 3), (0.5, 0.4, 0.3), (0.2, 0.2, 0.1))
+    mm_utils.process_image(frames[0], None, "pad", engine=eng)
+    assert eng.seen[0] == (1, 20, 30, 3) and eng.seen[1] == P.OPENAI_CLIP_MEAN and eng.seen[2] == P.OPENAI_CLIP_STD
+    with pytest.raises(NotImplementedError):
+        mm_utils.process_video(frames, Proc(), "resize", engine=eng)
