@@ -15,4 +15,12 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm
     python bench.py --steps 1 --warmup 3 --frames 1 --no-graphs --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 30 -c 2 -o gpurun_out/prof_attn -f \
     python bench.py --steps 1 --warmup 3 --frames 1 --no-graphs --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1
+# pipelined path (tower chunks of 8): launch list bounded to 16 frames, then the tcgen05 attention and the preprocessing kernels
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_pipelined.csv \
+    python bench.py --steps 1 --warmup 3 --frames 16 --no-graphs --no-cpu-baseline > gpurun_out/ncu_launch_pipe.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 30 -c 1 -o gpurun_out/prof_attn_tc -f \
+    python bench.py --steps 1 --warmup 3 --frames 16 --no-graphs --no-cpu-baseline > gpurun_out/ncu_attn_tc.log 2>&1
+timeout 120 python tools/preprocess_bench.py > gpurun_out/preprocess_bench.log 2>&1; tail -3 gpurun_out/preprocess_bench.log
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:preprocess -s 8 -c 2 -o gpurun_out/prof_preprocess -f \
+    python tools/preprocess_bench.py > gpurun_out/ncu_pre.log 2>&1
 ls -la gpurun_out
