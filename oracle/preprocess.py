@@ -20,8 +20,8 @@ The arithmetic lives in two third-party dependencies that are NOT vendored under
     away from zero), ImagingResampleHorizontal_8bpc then ImagingResampleVertical_8bpc, each accumulating from 1 << 21 in
     int32 and clipping (ss >> 22) to [0, 255] -- the intermediate image is uint8.
 
-Parity pin: resize_bicubic_u8 is checked bit-exactly against PIL.Image.resize of the Pillow in this image (12.2.0; the
-8bpc resampling code is unchanged since 9.x) in tests/test_preprocess_cpu.py, and against sha256 digests of Pillow's
+Parity pin: resize_bicubic_u8 is checked bit-exactly against PIL.Image.resize of the Pillow in this image (12.2.0 -- the reference pins 9.4.0, which
+cannot be installed here; the restated algorithm is the one documented for Resample.c's 8bpc path in both) in tests/test_preprocess_cpu.py, and against sha256 digests of Pillow's
 outputs committed in tests/golden/preprocess_digests.json (generator: oracle/make_preprocess_golden.py).
 """
 from __future__ import annotations
