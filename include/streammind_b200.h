@@ -47,7 +47,10 @@ typedef struct sm_config {
     /* LLM: MistralForCausalLM (language_model/videollama2_mistral.py:146). layers 0 = off */
     int llm_hidden, llm_layers, llm_heads, llm_kv_heads, llm_head_dim, llm_ffn, llm_vocab, llm_max_ctx;
     float llm_eps, llm_rope_theta;
-    int use_graphs;         /* capture the per-frame step and the decode step into CUDA graphs */
+    int use_graphs;         /* capture the per-frame step into CUDA graphs */
+    int n_streams;          /* video streams held by this handle (0 / 1 = one).  Each stream has its own Mamba conv / ssm state and
+                               KV cache; all share the weights, and sm_llm_decode_multi decodes several of them per pass over the
+                               weights (the reference keeps this state on the model object: videollama2_mistral.py:159-162) */
 } sm_config;
 
 /* Lifetime.  Replaces model construction in load_pretrained_model (streammind/model/builder.py:30). */
@@ -69,9 +72,16 @@ int sm_load_weight(sm_handle* h, const char* name, const void* data, int data_on
  * missing keys in sm_last_error otherwise. */
 int sm_finalize_weights(sm_handle* h);
 
-/* Per-stream state: zero the Mamba conv/ssm state, frame count and KV length.  The reference keeps this
- * state on the model object and never resets it (videollama2_mistral.py:159-165). */
-int sm_stream_reset(sm_handle* h);
+/* Per-stream state of the SELECTED stream: zero the Mamba conv/ssm state and the KV length, ordered on `stream` (frames
+ * still in flight in the pipelined path are joined first).  The reference keeps this state on the model object and
+ * never resets it (videollama2_mistral.py:159-165). */
+int sm_stream_reset(sm_handle* h, void* stream);
+
+/* Multi-stream handles (sm_config.n_streams > 1): the stream every single-stream entry point below acts on
+ * (sm_frame_step / submit, sm_projector_step, sm_llm_prefill, sm_llm_decode, sm_kv_len, sm_kv_set_len, sm_stream_reset).
+ * Default 0.  An open batch of pipelined tickets is closed first, so a batch never mixes streams. */
+int sm_stream_select(sm_handle* h, int stream_id);
+int sm_num_streams(const sm_handle* h);
 
 /* Frame preprocessing: mm_utils.process_video / process_image with aspect_ratio 'pad'
  * (streammind/mm_utils.py:446-464) = expand2square(frame, background) (mm_utils.py:257-268) ->
@@ -148,9 +158,36 @@ int sm_llm_prefill(sm_handle* h, const void* embeds, int P, float* last_logits, 
  * KeywordsStoppingCriteria, mm_utils.py:631-636): must follow sm_llm_prefill.  Produces up to max_new
  * tokens, stops after emitting any of stop_ids (host array).  ids_out_host [max_new] and n_out_host
  * are HOST pointers filled on return (the call synchronises `stream`).  The KV cache afterwards holds
- * every produced token except the last one (which was never fed back), as in HF. */
+ * every produced token except the last one (which was never fed back), as in HF.  A stream whose cache cannot hold
+ * max_new more tokens produces as many as fit (n_out_host < max_new) instead of failing.
+ * One token = ONE launch of the persistent weight-streaming kernel (csrc/decode_stream.cuh). */
 int sm_llm_decode(sm_handle* h, int max_new, const int32_t* stop_ids, int n_stop, int32_t* ids_out_host,
                   int32_t* n_out_host, void* stream);
+
+/* The same loop for n <= 4 streams of the handle at once (multi-stream batching): every pass over the
+ * 14.2 GB of LLM weights serves one new token of each listed stream (each with its own KV cache, position and stop
+ * state; a finished stream idles).  Every stream must have been prefilled (sm_stream_select + sm_llm_prefill).
+ * max_new [n]; ids_out_host [n][out_stride]; n_out_host [n].  Token ids are identical to n separate sm_llm_decode calls. */
+int sm_llm_decode_multi(sm_handle* h, int n, const int* stream_ids, const int* max_new, const int32_t* stop_ids, int n_stop,
+                        int32_t* ids_out_host, int out_stride, int32_t* n_out_host, void* stream);
+
+/* Device time of the decode steps (CUDA events around the token launches of every sm_llm_decode* call, on the call's
+ * stream) since the last reset: milliseconds, kernel launches (steps), tokens produced by those steps (sum over
+ * streams) and the sum over those tokens of the KV length each one attended to.  bench.py derives the achieved
+ * HBM GB/s of the decode kernel from it.  Blocks until the pending calls' events have completed. */
+int sm_decode_stats(sm_handle* h, double* ms, long long* steps, long long* tokens, long long* ctx_sum, int reset);
+
+/* Debug / measurement: while device_buf != NULL, CTA 0 of the decode kernel adds the nanoseconds (globaltimer) it spends in
+ * each phase to device_buf[0..5]: 0 vector staging (prologue), 1 weight ring, 2 epilogue, 3 grid barriers, 4 attention,
+ * 5 token selection (tools/decode_probe.py). */
+int sm_debug_decode_phases(sm_handle* h, long long* device_buf);
+
+/* Debug / test: activations the last decode step left behind (lane-major, model dtype): which = 0 residual stream x [hidden],
+ * 1 qkv of the last layer before RoPE [(Hq + 2 Hk) D], 2 attention output of the last layer [Hq D], 3 SwiGLU output [ffn]. */
+int sm_debug_decode_buffer(sm_handle* h, int which, void* out, long long bytes, void* stream);
+
+/* Debug / test: fp32 logits [vocab] of the LAST decode step of lane `lane` (0 for sm_llm_decode) -> logits_out (device). */
+int sm_debug_decode_logits(sm_handle* h, int lane, float* logits_out, void* stream);
 
 /* KV length bookkeeping (prefix reuse across fires; the reference re-prefills from scratch:
  * videollama2_mistral.py:413 past_key_values=None). */
@@ -184,14 +221,8 @@ int sm_debug_kernel_filter(sm_handle* h, unsigned mask);
 /* Debug / test: which attention kernel serves d = 64 non-causal attention (the vision tower).  -1 = default
  * (tcgen05 kernel csrc/attention_tc.cuh when the launch has >= 148 CTAs of 128 query rows, else the mma.sync
  * kernel csrc/attention.cuh; SMB_ATTN_TC=0/2 in the environment overrides), 0 = mma.sync kernel always,
- * 2 = tcgen05 kernel wherever its layout conditions hold, 3 = its three-CTA-per-SM variant (attention_tc3_kernel). */
+ * 2 = tcgen05 kernel wherever its layout conditions hold. */
 int sm_debug_attention_mode(sm_handle* h, int mode);
-
-/* Debug / measurement: per-op trace of the persistent vision-tower kernel (csrc/vit_mega.cuh).  device_buf
- * (NULL = off) receives 4 int64 slots per op of the plan for chunk size B: max over CTAs of the globaltimer
- * when the op's grid barrier was passed, when its work was done, and when the CTA arrived.  n_ops / types
- * (optional) return the op list of that plan (MegaOpType values). */
-int sm_debug_mega_trace(sm_handle* h, long long* device_buf, int B, int* n_ops, int* types, int max_ops);
 
 /* Launch accounting: number of this library's kernel launches (graph-replayed kernels included) since
  * the last call with reset != 0. */

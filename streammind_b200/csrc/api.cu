@@ -24,9 +24,8 @@
 #include "preprocess.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
-#include "gemv_tma.cuh"
+#include "decode_stream.cuh"
 #include "misc_kernels.cuh"
-#include "vit_mega.cuh"
 
 using namespace smb;
 
@@ -63,6 +62,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 constexpr int kMaxLanes = 8;      // concurrent vision towers of the pipelined path (SMB_LANES overrides)
 constexpr int kTicketRing = 16;   // frames in flight (sm_frame_submit tickets)
 constexpr int kTowerBatch = 8;    // single-frame tickets whose towers run as one chunk (pipelined path)
+constexpr int kMaxHandleStreams = 16;   // video streams one handle can hold (sm_config.n_streams)
+constexpr int kDsMaxNew = 4096;   // tokens one sm_llm_decode call can produce per stream
 
 struct sm_handle {
     sm_config cfg{};
@@ -82,10 +83,7 @@ struct sm_handle {
     PFN_encodeTiled encode = nullptr;
     long long launches = 0;
     bool use_pdl = true;
-    int gemm_occ2 = 0;                // 1: multi-wave GEMMs run as two co-resident CTAs per SM (gemm_tc_kernel<T, 2>)
     int gemm_class = 0;               // kernel class of gemm_tc_kernel launches (KC_GEMM; run_gate_gemm: KC_GATE_GEMM)
-    bool gemv_tma = false;            // weight-streaming GEMVs through the bulk-copy ring (gemv_tma.cuh, experimental)
-    int gemv_grid_cap = 0;            // > 0: GEMVs use at most this many CTAs (background gate)
     bool vit_tiled = true;            // ViT GEMM weights are stored pre-tiled (gemm_tc.cuh GemmArgs::w_tiled)
     int attn_mode = -1;               // debug (sm_debug_attention_mode): -1 = SMB_ATTN_TC / auto, 0 = mma.sync kernel, 2 = tcgen05 wherever supported
     unsigned kfilter = 0xFFFFFFFFu;   // debug: kernel classes that are actually launched (bench.py per-class timing)
@@ -110,16 +108,6 @@ struct sm_handle {
                    int cap_frames, part_frames; };   // frames the activation buffers / the split-K partial buffer hold
     VitWs lanes[kMaxLanes] = {};
     int cur_lane = 0;
-    // persistent vision-tower kernel (vit_mega.cuh): one op list + tensor-map array per chunk size B
-    struct MegaPlan { MegaOp* d_ops = nullptr; CUtensorMap* d_maps = nullptr; int n_ops = 0; std::vector<int> types; };
-    std::map<int, MegaPlan> mega_plans;
-    unsigned int* mega_sync = nullptr;
-    long long* mega_dbg = nullptr;
-    // persistent GEMM launches (one vit_mega_kernel op per launch: tile loop, double-buffered accumulator)
-    struct PGemm { MegaOp* d_op = nullptr; CUtensorMap* d_maps = nullptr; int tiles = 0; };
-    std::map<std::tuple<const void*, const void*, const void*, int, int, int>, PGemm> pgemms;
-    int pgemm = 0;        // > 0: tiles per CTA of the persistent GEMM (pipelined path), 0: one tile per CTA (gemm_tc_kernel)
-    int mega_mode = 2;   // 0 = one kernel per op (round-1 path), 1 = persistent kernel, attention as separate launches, 2 = one launch
     // ---- projector
     int d_inner = 0, dt_rank = 0;
     void *pj_pre_w = nullptr, *pj_pre_b = nullptr, *pj_norm_w = nullptr, *pj_norm_b = nullptr, *pj_in = nullptr,
@@ -142,10 +130,25 @@ struct sm_handle {
     std::vector<void*> kc, vc;
     int pmax = 0;
     void *lw_x = nullptr, *lw_hn = nullptr, *lw_qkv = nullptr, *lw_att = nullptr, *lw_gu = nullptr, *lw_m = nullptr;
-    float *lw_logits = nullptr, *lw_part = nullptr, *lw_part2 = nullptr;   // lw_part2: split-K partials of the few-row prefill GEMMs
-    int *d_pos = nullptr, *d_tok = nullptr, *d_out = nullptr, *d_nout = nullptr, *d_done = nullptr, *d_stop = nullptr;
-    int kv_len = 0;
-    int dec_splits = 64;   // KV slices per kv head of the decode attention (SMB_DEC_SPLITS); measured at ctx 2k: 16 -> 280, 32 -> 302, 64 -> 305 tokens/s
+    float *lw_logits = nullptr, *lw_part2 = nullptr;   // lw_logits [n_streams][V]: last-position logits of each stream's prefill; lw_part2: split-K partials of the few-row prefill GEMMs
+    // ---- per-stream state (multi-stream batching): the handle holds n_streams video streams that share
+    // its weights; `cur` is the stream the single-stream entry points act on (sm_stream_select)
+    int n_streams = 1, cur = 0;
+    std::vector<int> kv_lens;          // KV length per stream
+    long long kv_stream_stride = 0;    // elements between the caches of consecutive streams inside kc[l] / vc[l]
+    // ---- persistent decode kernel (decode_stream.cuh)
+    DsOp* ds_ops = nullptr;            // device op list of one decode step
+    int ds_n_ops = 0, ds_n_barriers = 0, ds_xcap = 0, ds_part_rows = 0 /* max over ops of nmat * rows-per-CTA * P */;
+    unsigned* ds_sync = nullptr;       // grid-barrier counter, epoch, all-done flag, per (lane, kv head) arrival counters
+    DsStreamState* ds_state = nullptr; // [kDsMaxStreams]
+    int *ds_out = nullptr, *ds_stop = nullptr, *ds_cand_idx = nullptr;   // ds_out [kDsMaxStreams][kDsMaxNew]
+    float *ds_att_part = nullptr, *ds_cand_val = nullptr, *ds_logits = nullptr;
+    void *ds_x = nullptr, *ds_qkv = nullptr, *ds_att = nullptr, *ds_m = nullptr;   // decode activations [kDsMaxStreams][...]
+    long long* ds_dbg = nullptr;       // sm_debug_decode_phases: per-phase ns of CTA 0
+    double ds_ms = 0.0;                // device time of the decode steps since the last sm_decode_stats reset (CUDA events)
+    long long ds_steps = 0, ds_tokens = 0, ds_ctx_sum = 0;
+    struct DsTiming { cudaEvent_t a, b; long long steps, tokens, ctx_sum; };
+    std::vector<DsTiming> ds_pending;
     // ---- pipelined frame path (sm_frame_submit): tower on vit_stream, projector + gate on gate_stream
     bool pipe_init = false;
     int n_lanes = 8;                   // towers of consecutive tickets run on this many streams / activation sets (<= kMaxLanes)
@@ -156,7 +159,6 @@ struct sm_handle {
     cudaStream_t vit_streams[kMaxLanes] = {}, gate_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_vit[kTicketRing] = {}, ev_gate[kTicketRing] = {};
     long long ticket = 0;
-    int bg_grid = 0;                   // > 0: projector/gate GEMVs of the pipelined path on this many CTAs (experiment; measured slower)
     void* pooled_ring = nullptr;       // [kTicketRing][max_frames][C]: pooled patch means, one slot per ticket in flight
     struct PendingTicket { void* feats_out; void* toks_out; float* logits_out; float* logits_host; int B; };
     PendingTicket pend[kTowerBatch] = {};   // tickets of the open batch (towers enqueued or, in tower-batch mode, only copied in)
@@ -170,8 +172,6 @@ struct sm_handle {
     std::map<long long, cudaGraphExec_t> frame_graphs;   // key: gkey(h, int key) = kernel filter << 32 | key   // key: B | flags<<8
     std::map<long long, long long> frame_graph_launches;
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot capture)
-    cudaGraphExec_t decode_graph = nullptr;
-    long long decode_graph_launches = 0;
 };
 
 namespace {
@@ -228,7 +228,10 @@ inline void select_lane(sm_handle* h, int lane) {
     h->cur_lane = lane;
 }
 
-inline long long gkey(const sm_handle* h, int key) { return (static_cast<long long>(h->kfilter) << 32) | static_cast<unsigned int>(key); }
+// graph cache key: captured graphs embed the kernel filter and the selected stream's state pointers
+inline long long gkey(const sm_handle* h, int key) {
+    return (static_cast<long long>(h->kfilter | (static_cast<unsigned>(h->cur) << 16)) << 32) | static_cast<unsigned int>(key);
+}
 
 inline void count_launch(sm_handle* h) {
     if (h->capturing) h->captured_launches++; else h->launches++;
@@ -387,10 +390,7 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
     if (!ta || !tb) return 1;
     a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.swap = p.swap; a.bn = p.bn;
     a.bm2 = p.bm2;
-    // two co-resident CTAs per SM: only when there is more than one wave of tiles to overlap and the ring still has >= 2 stages
-    const int occ2 = (h->gemm_occ2 && !p.bm2 && CS == 1 && static_cast<int>(grid.x * grid.y * std::max(1u, grid.z)) > h->num_sms &&
-                      gemm_num_stages(p.bn, 0, 1) >= 2) ? 1 : 0;
-    a.nstage = gemm_num_stages(p.bn, p.bm2, occ2); a.epi = epi;
+    a.nstage = gemm_num_stages(p.bn, p.bm2); a.epi = epi;
     {
         static const int dm = getenv("SMB_GEMM_DBG_MODE") ? atoi(getenv("SMB_GEMM_DBG_MODE")) : 0;
         a.dbg_mode = dm;
@@ -414,51 +414,10 @@ int launch_gemm_t(sm_handle* h, const void* x, int tokens, const void* w, int fe
         static const int dbg_stages = getenv("SMB_GEMM_STAGES") ? atoi(getenv("SMB_GEMM_STAGES")) : 0;   // tuning knob
         if (dbg_stages > 0 && dbg_stages < a.nstage) a.nstage = dbg_stages;
     }
-    const int smem = gemm_smem_bytes(p.bn, p.bm2, occ2);
+    const int smem = gemm_smem_bytes(p.bn, p.bm2);
     {
         ProfScope ps(h, h->gemm_class, st);
-        if (occ2) CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T, 2>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
-        else CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T, 1>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
-    }
-    count_launch(h);
-    CUDA_OK(h, cudaGetLastError());
-    return 0;
-}
-
-// One GEMM as a persistent launch of vit_mega_kernel (single op): G CTAs loop over the 128 x bn tiles, the epilogue
-// of tile i overlaps the mainloop of tile i+1 (two TMEM accumulators) and barriers / TMEM are set up once per CTA.
-template <typename T>
-int launch_gemm_persistent_t(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias,
-                             void* out, int ldo, int epi, int bn, cudaStream_t st) {
-    if (!kon(h, KC_GEMM)) return 0;
-    auto key = std::make_tuple(x, w, static_cast<const void*>(out), tokens, epi, bn);
-    auto it = h->pgemms.find(key);
-    if (it == h->pgemms.end()) {
-        if (h->capturing) return fail(h, "persistent gemm: plans must be built outside graph capture");
-        const int w_kb = (K + 63) / 64;
-        const CUtensorMap* ta = get_tmap(h, x, tokens, K, kGemmBM);
-        const CUtensorMap* tb = get_tmap(h, w, ((feats + 127) / 128) * w_kb * 128, kGemmBK, kGemmBM);
-        if (!ta || !tb) return 1;
-        CUtensorMap maps[2] = {*ta, *tb};
-        MegaOp o{};
-        o.type = MOP_GEMM; o.map_a = 0; o.map_b = 1; o.M = tokens; o.N = feats; o.K = K; o.bn = bn; o.split_k = 1; o.epi = epi;
-        o.w_kb = w_kb; o.w = w; o.bias = bias; o.out = out; o.ldo = ldo; o.split_stride = 0;
-        sm_handle::PGemm pg;
-        pg.d_op = static_cast<MegaOp*>(dalloc(h, sizeof(MegaOp)));
-        pg.d_maps = static_cast<CUtensorMap*>(dalloc(h, sizeof(maps)));
-        if (!pg.d_op || !pg.d_maps) return fail(h, "persistent gemm: out of device memory");
-        CUDA_OK(h, cudaMemcpy(pg.d_op, &o, sizeof o, cudaMemcpyHostToDevice));
-        CUDA_OK(h, cudaMemcpy(pg.d_maps, maps, sizeof maps, cudaMemcpyHostToDevice));
-        pg.tiles = ((tokens + 127) / 128) * (feats / bn);
-        it = h->pgemms.emplace(key, pg).first;
-    }
-    const sm_handle::PGemm& pg = it->second;
-    const int G = std::max(1, std::min(h->num_sms, (pg.tiles + h->pgemm - 1) / h->pgemm));
-    MegaParams p{};
-    p.ops = pg.d_op; p.op_begin = 0; p.op_end = 1; p.maps = pg.d_maps; p.sync = h->mega_sync; p.single = 1; p.dbg = nullptr;
-    {
-        ProfScope ps(h, KC_GEMM, st);
-        CUDA_OK(h, launch_ex(h, vit_mega_kernel<T>, dim3(G), dim3(kGemmThreads), mega_smem_bytes(), st, 1, p));
+        CUDA_OK(h, launch_ex(h, gemm_tc_kernel<T>, grid, dim3(kGemmThreads2), smem, st, CS, *ta, *tb, *tc, a));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -468,15 +427,6 @@ int launch_gemm_persistent_t(sm_handle* h, const void* x, int tokens, const void
 int launch_gemm(sm_handle* h, const void* x, int tokens, const void* w, int feats, int K, const void* bias, void* out,
                 int ldo, int epi, cudaStream_t st, int force_swap = -1, int force_bn = 0, bool w_tiled = false,
                 int split_k = 1) {
-    if (h->pgemm > 0 && w_tiled && split_k == 1 && force_swap < 0 && force_bn == 0 && feats % 128 == 0 && ldo == feats &&
-        h->mega_sync != nullptr && tokens > 64) {
-        const GemmPlan p = plan_gemm(tokens, feats, K, h->num_sms, epi, h->plan_div, 1);
-        if (!p.swap && !p.bm2 && (p.bn == 128 || p.bn == 256)) {
-            if (h->cfg.dtype == SM_DTYPE_BF16)
-                return launch_gemm_persistent_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, p.bn, st);
-            return launch_gemm_persistent_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, p.bn, st);
-        }
-    }
     if (h->cfg.dtype == SM_DTYPE_BF16)
         return launch_gemm_t<__nv_bfloat16>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
     return launch_gemm_t<__half>(h, x, tokens, w, feats, K, bias, out, ldo, epi, st, force_swap, force_bn, w_tiled, split_k);
@@ -497,42 +447,17 @@ int splitk_factor(const sm_handle* h, int tokens, int feats, int K, bool bm2 = f
 }
 
 // ------------------------------------------------------------------------------------------ GEMV
-// bulk-copy ring + tensor-pipe kernel (gemv_tma.cuh)
-template <typename T>
-int launch_gemv_tma_t(sm_handle* h, const GemvArgs& a, int nmat, cudaStream_t st) {
-    const int G = h->gemv_grid_cap > 0 ? std::min(h->gemv_grid_cap, h->num_sms) : h->num_sms;
-    const int R = kGtTileRows;
-    const int per_cta = (a.N + G * kGtMaxBlockRows - 1) / (G * kGtMaxBlockRows);          // row blocks per CTA
-    int rpb = ((a.N + G * per_cta - 1) / (G * per_cta) + R - 1) / R * R;
-    rpb = std::max(R, std::min(rpb, kGtMaxBlockRows));
-    const int nblocks = (a.N + rpb - 1) / rpb;
-    const int grid = std::min(nblocks, G);
-    const int smem = gemv_tma_smem_bytes(a.K, nmat);
-    {
-        ProfScope ps(h, KC_GEMV, st);
-        if (nmat == 2) CUDA_OK(h, launch_pdl(h, gemv_tma_kernel<T, 2>, dim3(grid), dim3(kGtThreads), smem, st, a, rpb, nblocks));
-        else CUDA_OK(h, launch_pdl(h, gemv_tma_kernel<T, 1>, dim3(grid), dim3(kGtThreads), smem, st, a, rpb, nblocks));
-    }
-    count_launch(h);
-    CUDA_OK(h, cudaGetLastError());
-    return 0;
-}
-
 template <typename T>
 int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
     if (a.K % 8 != 0) return fail(h, "gemv: K=%d must be a multiple of 8", a.K);
     if (!kon(h, KC_GEMV)) return 0;
-    if (h->gemv_tma && a.nv_host <= 1 && gemv_tma_supported(a.K)) return launch_gemv_tma_t<T>(h, a, nmat, st);
     const int nv = std::max(1, a.nv_host);
-    static const bool use_seg = getenv("SMB_GEMV_SEG") ? atoi(getenv("SMB_GEMV_SEG")) != 0 : false;   // measured slower (latency-bound at 1 CTA/SM): opt-in
-    const bool seg_kernel = nv > 1 && use_seg;      // segment-stationary batched kernel (gemv_seg_kernel)
-    const int nvt = nv <= 1 ? 1 : (seg_kernel ? (nv <= 2 ? 2 : 4) : nv);
+    const int nvt = nv;
     a.seg_len = nv == 1 ? (nmat == 1 ? SMB_GEMV_UNR1 * 256 : 1024) : 2048;   // one batch of loads covers a segment
-    static const int grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;   // experiment: background-sized grids
-    int grid = std::min(a.N, grid_cap > 0 ? grid_cap : (nv == 1 ? 2 : 1) * h->num_sms);
+    int grid = std::min(a.N, (nv == 1 ? 2 : 1) * h->num_sms);
     const int rows_per_cta = (a.N + grid - 1) / grid;
     grid = (a.N + rows_per_cta - 1) / rows_per_cta;
-    const int nseg = seg_kernel ? (a.K + kGemvSeg - 1) / kGemvSeg : (a.K + a.seg_len - 1) / a.seg_len;
+    const int nseg = (a.K + a.seg_len - 1) / a.seg_len;
     const int xpitch = (a.K + 7) & ~7;
     const size_t smem = ((static_cast<size_t>(nvt) * xpitch * 2 + 15) & ~size_t(15)) +
                         static_cast<size_t>(nmat) * nvt * rows_per_cta * nseg * sizeof(float);
@@ -541,8 +466,7 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
         ProfScope ps(h, KC_GEMV, st);
         const dim3 g(grid), b(kGemvThreads);
 #define SMB_GEMV_CASE(NM, NVV) CUDA_OK(h, launch_pdl(h, gemv_kernel<T, NM, NVV>, g, b, smem, st, a))
-#define SMB_GEMV_SEG_CASE(NM, NVV) CUDA_OK(h, launch_pdl(h, gemv_seg_kernel<T, NM, NVV>, g, b, smem, st, a, nv))
-        switch ((seg_kernel ? 100 : 0) + nmat * 10 + nvt) {
+        switch (nmat * 10 + nvt) {
             case 11: SMB_GEMV_CASE(1, 1); break;
             case 12: SMB_GEMV_CASE(1, 2); break;
             case 13: SMB_GEMV_CASE(1, 3); break;
@@ -551,14 +475,9 @@ int launch_gemv_t(sm_handle* h, GemvArgs a, int nmat, cudaStream_t st) {
             case 22: SMB_GEMV_CASE(2, 2); break;
             case 23: SMB_GEMV_CASE(2, 3); break;
             case 24: SMB_GEMV_CASE(2, 4); break;
-            case 112: SMB_GEMV_SEG_CASE(1, 2); break;
-            case 114: SMB_GEMV_SEG_CASE(1, 4); break;
-            case 122: SMB_GEMV_SEG_CASE(2, 2); break;
-            case 124: SMB_GEMV_SEG_CASE(2, 4); break;
             default: return fail(h, "gemv: %d matrices x %d vectors not instantiated", nmat, nv);
         }
 #undef SMB_GEMV_CASE
-#undef SMB_GEMV_SEG_CASE
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -602,10 +521,7 @@ template <typename T>
 int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cudaStream_t st) {
     if (!kon(h, KC_ATTN)) return 0;
     const int pitch = static_cast<int>(a.q_ss);                 // elements per packed row (3C)
-    // three lean CTAs per SM (attention_tc3_kernel, 64-row TMA boxes) or two with double-buffered S (attention_tc_kernel)
-    static const int env_lean = getenv("SMB_ATTN_TC3") ? atoi(getenv("SMB_ATTN_TC3")) : 0;
-    const bool lean = h->attn_mode == 3 || (h->attn_mode != 2 && env_lean != 0);
-    const CUtensorMap* tm = get_tmap(h, a.q, batch * a.q_len, pitch, lean ? 64 : kAtcTile);
+    const CUtensorMap* tm = get_tmap(h, a.q, batch * a.q_len, pitch, kAtcTile);
     if (!tm) return 1;
     AttnTcArgs t{};
     t.o = a.o; t.o_ss = a.o_ss; t.S = a.q_len; t.col_q = 0;
@@ -616,8 +532,7 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
     {
         ProfScope ps(h, KC_ATTN, st);
         const dim3 grid((a.q_len + kAtcTile - 1) / kAtcTile, heads, batch);
-        if (lean) CUDA_OK(h, launch_pdl(h, attention_tc3_kernel<T>, grid, dim3(kAtcThreads), static_cast<size_t>(attn_tc3_smem_bytes()), st, *tm, t));
-        else CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, grid, dim3(kAtcThreads), static_cast<size_t>(attn_tc_smem_bytes()), st, *tm, t));
+        CUDA_OK(h, launch_pdl(h, attention_tc_kernel<T>, grid, dim3(kAtcThreads), static_cast<size_t>(attn_tc_smem_bytes()), st, *tm, t));
     }
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -627,7 +542,7 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
 int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cudaStream_t st) {
     // one frame alone is only 80 CTAs of 128 query rows: the 64-row mma.sync kernel (160 CTAs) fills the machine better
     static const int env_tc = getenv("SMB_ATTN_TC") ? atoi(getenv("SMB_ATTN_TC")) : 1;
-    const int use_tc = h->attn_mode >= 0 ? (h->attn_mode == 3 ? 2 : h->attn_mode) : env_tc;
+    const int use_tc = h->attn_mode >= 0 ? h->attn_mode : env_tc;
     static const int tc_min_ctas = getenv("SMB_ATTN_TC_MINCTAS") ? atoi(getenv("SMB_ATTN_TC_MINCTAS")) : 148;
     if (use_tc && ((a.q_len + kAtcTile - 1) / kAtcTile) * heads * batch >= (use_tc == 2 ? 0 : tc_min_ctas) && D == 64 && !a.causal && a.group == 1 && a.q_len == a.kv_len && a.q_ss == a.k_ss && a.q_ss == a.v_ss &&
         a.k_hs == 64 && a.v_hs == 64 && a.q_bs == static_cast<long long>(a.q_len) * a.q_ss && a.k_bs == a.q_bs && a.v_bs == a.q_bs &&
@@ -642,223 +557,29 @@ int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cu
 
 template <typename T>
 int init_kernel_attrs_t(sm_handle* h) {
-    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    CUDA_OK(h, cudaFuncSetAttribute(vit_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega_smem_bytes()));
+    CUDA_OK(h, cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     {
         auto big = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); };
         CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 2>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 3>));
         CUDA_OK(h, big((const void*)gemv_kernel<T, 1, 4>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 2>));
         CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 3>)); CUDA_OK(h, big((const void*)gemv_kernel<T, 2, 4>));
-        CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 1, 2>)); CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 1, 4>));
-        CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 2, 2>)); CUDA_OK(h, big((const void*)gemv_seg_kernel<T, 2, 4>));
     }
-    CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CUDA_OK(h, cudaFuncSetAttribute(gemv_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(gemv_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes()));
-    CUDA_OK(h, cudaFuncSetAttribute(attention_tc3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc3_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
-    // One shared-memory carve-out for every kernel of the per-frame chain: an SM has to drain before it can
-    // change its L1/shared split, which serialises back-to-back launches (and defeats PDL overlap) when
-    // neighbouring kernels ask for different splits.
-    if (getenv("SMB_CARVEOUT") != nullptr) {
-        const int co = atoi(getenv("SMB_CARVEOUT")) > 0 ? atoi(getenv("SMB_CARVEOUT")) : cudaSharedmemCarveoutMaxShared;
-        auto set = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, co); };
-        CUDA_OK(h, set((const void*)gemm_tc_kernel<T, 1>));
-        CUDA_OK(h, set((const void*)gemv_kernel<T, 1>));
-        CUDA_OK(h, set((const void*)gemv_kernel<T, 2>));
-        CUDA_OK(h, set((const void*)attention_kernel<T, 64>));
-        CUDA_OK(h, set((const void*)attention_kernel<T, 128>));
-        CUDA_OK(h, set((const void*)layernorm_kernel<T>));
-        CUDA_OK(h, set((const void*)splitk_residual_ln_kernel<T>));
-        CUDA_OK(h, set((const void*)vit_embed_ln_kernel<T, 32>));
-        CUDA_OK(h, set((const void*)im2col_kernel<T>));
-        CUDA_OK(h, set((const void*)vit_finalize_kernel<T>));
-        CUDA_OK(h, set((const void*)mamba_scan_step_kernel<T>));
-    }
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------ persistent ViT
-bool mega_supported(const sm_handle* h) {
-    const sm_config& c = h->cfg;
-    return h->mega_mode > 0 && h->vit_tiled && (c.vit_hidden & 255) == 0 && c.vit_hidden <= 1024 && c.vit_ffn % 128 == 0 &&
-           c.vit_hidden / c.vit_heads == 64;
-}
-
-// tile width of a GEMM op: cost model from the issue-rate microbenchmark (profiles/r01_ncu_full_summary.md):
-// a K=64 slab costs ~150 ns at N=128 (4 MMAs + commit) and ~260 ns at N=256; the epilogue of the last tile is exposed.
-int mega_pick_bn(int rows, int feats, int K, int G) {
-    if (feats % 256 != 0) return 128;
-    const int mt = (rows + 127) / 128, kb = (K + 63) / 64;
-    const double c128 = std::ceil(double(mt) * (feats / 128) / G) * kb * 0.150 + 1.2;
-    const double c256 = std::ceil(double(mt) * (feats / 256) / G) * kb * 0.260 + 2.4;
-    static const int force = getenv("SMB_MEGA_BN") ? atoi(getenv("SMB_MEGA_BN")) : 0;
-    if (force == 128 || force == 256) return force;
-    return c256 < c128 ? 256 : 128;
-}
-
-int mega_build_plan(sm_handle* h, int B) {
-    const sm_config& c = h->cfg;
-    const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn, G = h->num_sms;
-    std::vector<CUtensorMap> maps;
-    std::vector<MegaOp> ops;
-    auto add_map = [&](const void* ptr, int nrows, int K) -> int {
-        const CUtensorMap* m = get_tmap(h, ptr, nrows, K, kGemmBM);
-        if (!m) return -1;
-        maps.push_back(*m);
-        return static_cast<int>(maps.size()) - 1;
-    };
-    auto tiled_rows = [](int feats, int K) { return ((feats + 127) / 128) * ((K + 63) / 64) * 128; };
-    const int m_im = add_map(h->ws_im, B * P, h->kpad), m_h = add_map(h->ws_h, rows, C), m_att = add_map(h->ws_att, rows, C),
-              m_mlp = add_map(h->ws_mlp, rows, F);
-    if (m_im < 0 || m_h < 0 || m_att < 0 || m_mlp < 0) return 1;
-    auto gemm = [&](int map_a, const void* w, int M, int N, int K, const void* bias, void* out, int ldo, int epi, int split) -> int {
-        MegaOp o{};
-        o.type = MOP_GEMM; o.map_a = map_a; o.map_b = add_map(w, tiled_rows(N, K), kGemmBK);
-        if (o.map_b < 0) return 1;
-        o.M = M; o.N = N; o.K = K; o.split_k = split; o.epi = epi; o.w_kb = (K + 63) / 64; o.w = w; o.bias = bias;
-        o.bn = split > 1 || epi == EPI_STORE_F32 ? 128 : mega_pick_bn(M, N, K, G);
-        o.out = out; o.ldo = ldo; o.split_stride = static_cast<long long>(M) * N;
-        ops.push_back(o);
-        return 0;
-    };
-    auto splitk_ln = [&](int nsplit, const void* bias, const void* ln_w, const void* ln_b) {
-        MegaOp o{};
-        o.type = MOP_SPLITK_LN; o.part = h->ws_part; o.nsplit = nsplit; o.part_stride = static_cast<long long>(rows) * C;
-        o.rbias = bias; o.x = h->ws_x; o.ln_w = ln_w; o.ln_b = ln_b; o.h = h->ws_h; o.rows = rows; o.C = C; o.eps = c.vit_eps;
-        ops.push_back(o);
-    };
-    {
-        MegaOp o{};
-        o.type = MOP_IM2COL; o.pixels = h->ws_pixels; o.im = h->ws_im; o.img = c.vit_image; o.patch = c.vit_patch;
-        o.kpad = h->kpad; o.batch = B;
-        ops.push_back(o);
-    }
-    if (gemm(m_im, h->vit_wpatch, B * P, C, h->kpad, nullptr, h->ws_pemb, C, EPI_STORE, 1)) return 1;
-    {
-        MegaOp o{};
-        o.type = MOP_EMBED_LN; o.pemb = h->ws_pemb; o.cls = h->vit_cls; o.pos = h->vit_pos; o.pre_w = h->vit_pre_w;
-        o.pre_b = h->vit_pre_b; o.ln_w = h->vit[0].ln1_w; o.ln_b = h->vit[0].ln1_b; o.x = h->ws_x; o.h = h->ws_h;
-        o.rows = rows; o.C = C; o.S = S; o.eps = c.vit_eps;
-        ops.push_back(o);
-    }
-    const int D = C / c.vit_heads;
-    for (int l = 0; l < c.vit_layers; ++l) {
-        const VitLayer& L = h->vit[l];
-        if (gemm(m_h, L.wqkv, rows, 3 * C, C, L.bqkv, h->ws_qkv, 3 * C, EPI_STORE, 1)) return 1;
-        {
-            MegaOp o{};
-            o.type = MOP_ATTN; o.heads = c.vit_heads; o.batch = B;
-            AttnArgs& a = o.attn;
-            a.q = h->ws_qkv;
-            a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
-            a.v = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(2 * C) * 2;
-            a.o = h->ws_att;
-            a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
-            a.q_ss = a.k_ss = a.v_ss = 3 * C;
-            a.k_hs = a.v_hs = D;
-            a.o_bs = static_cast<long long>(S) * C;
-            a.o_ss = C;
-            a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
-            a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
-            ops.push_back(o);
-        }
-        const int s1 = splitk_factor(h, rows, C, C), s2 = splitk_factor(h, rows, C, F);
-        if (gemm(m_att, L.wo, rows, C, C, nullptr, h->ws_part, C, EPI_STORE_F32, s1)) return 1;
-        splitk_ln(s1, L.bo, L.ln2_w, L.ln2_b);
-        if (gemm(m_h, L.w1, rows, F, C, L.b1, h->ws_mlp, F, EPI_QUICK_GELU, 1)) return 1;
-        if (gemm(m_mlp, L.w2, rows, C, F, nullptr, h->ws_part, C, EPI_STORE_F32, s2)) return 1;
-        const bool last = l + 1 == c.vit_layers;
-        splitk_ln(s2, L.b2, last ? nullptr : h->vit[l + 1].ln1_w, last ? nullptr : h->vit[l + 1].ln1_b);
-    }
-    {
-        MegaOp o{};
-        o.type = MOP_POOL; o.x = h->ws_x; o.pooled = h->ws_pooled; o.C = C; o.S = S; o.batch = B;
-        ops.push_back(o);
-    }
-    sm_handle::MegaPlan plan;
-    plan.n_ops = static_cast<int>(ops.size());
-    for (auto& o : ops) plan.types.push_back(o.type);
-    plan.d_ops = static_cast<MegaOp*>(dalloc(h, ops.size() * sizeof(MegaOp)));
-    plan.d_maps = static_cast<CUtensorMap*>(dalloc(h, maps.size() * sizeof(CUtensorMap)));
-    if (!plan.d_ops || !plan.d_maps) return fail(h, "mega_build_plan: out of device memory");
-    CUDA_OK(h, cudaMemcpy(plan.d_ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
-    CUDA_OK(h, cudaMemcpy(plan.d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    h->mega_plans[B | (h->cur_lane << 16)] = plan;
-    return 0;
-}
-
-template <typename T>
-int mega_launch_t(sm_handle* h, const sm_handle::MegaPlan& plan, int op_begin, int op_end, cudaStream_t st) {
-    MegaParams p{};
-    p.ops = plan.d_ops; p.op_begin = op_begin; p.op_end = op_end; p.maps = plan.d_maps; p.sync = h->mega_sync; p.dbg = h->mega_dbg;
-    CUDA_OK(h, launch_ex(h, vit_mega_kernel<T>, dim3(h->num_sms), dim3(kGemmThreads), mega_smem_bytes(), st, 1, p));
-    count_launch(h);
-    return 0;
-}
-
-int run_vit_mega(sm_handle* h, int B, cudaStream_t st) {
-    const int pkey = B | (h->cur_lane << 16);
-    auto it = h->mega_plans.find(pkey);
-    if (it == h->mega_plans.end()) {
-        if (h->capturing) return fail(h, "run_vit_mega: plan for B=%d must be built outside graph capture", B);
-        if (mega_build_plan(h, B)) return 1;
-        it = h->mega_plans.find(pkey);
-    }
-    const sm_handle::MegaPlan& plan = it->second;
-    auto launch = [&](int b, int e) -> int {
-        if (b >= e) return 0;
-        DISPATCH_T(h, T, return mega_launch_t<T>(h, plan, b, e, st);)
-    };
-    if (h->mega_mode >= 2) return launch(0, plan.n_ops);
-    // mode 1: attention ops run as the stand-alone kernel between persistent ranges
-    const sm_config& c = h->cfg;
-    const int C = c.vit_hidden, S = h->S, D = C / c.vit_heads;
-    int begin = 0;
-    for (int i = 0; i < plan.n_ops; ++i) {
-        if (plan.types[i] != MOP_ATTN) continue;
-        if (launch(begin, i)) return 1;
-        AttnArgs a{};
-        a.q = h->ws_qkv;
-        a.k = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(C) * 2;
-        a.v = reinterpret_cast<const char*>(h->ws_qkv) + static_cast<size_t>(2 * C) * 2;
-        a.o = h->ws_att;
-        a.q_bs = a.k_bs = a.v_bs = static_cast<long long>(S) * 3 * C;
-        a.q_ss = a.k_ss = a.v_ss = 3 * C;
-        a.k_hs = a.v_hs = D;
-        a.o_bs = static_cast<long long>(S) * C;
-        a.o_ss = C;
-        a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
-        a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
-        if (launch_attn(h, a, D, c.vit_heads, B, st)) return 1;
-        begin = i + 1;
-    }
-    return launch(begin, plan.n_ops);
 }
 
 // ------------------------------------------------------------------------------------------ sub-model runners
 int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, cudaStream_t st) {
     const sm_config& c = h->cfg;
     const int C = c.vit_hidden, S = h->S, P = h->P, rows = B * S, F = c.vit_ffn;
-    if (mega_supported(h) && h->kfilter == 0xFFFFFFFFu && !h->profiling) {
-        const size_t px_bytes = static_cast<size_t>(B) * 3 * c.vit_image * c.vit_image * h->esz;
-        if (pixels != h->ws_pixels) CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, cudaMemcpyDeviceToDevice, st));
-        if (run_vit_mega(h, B, st)) return 1;
-        if (feats_out != nullptr) {
-            DISPATCH_T(h, T, {
-                CUDA_OK(h, launch_pdl(h, vit_finalize_kernel<T>, dim3((C / 8 + 3) / 4, B), dim3(128), 0, st, (const T*)h->ws_x, (T*)feats_out, (T*)nullptr, S, C));
-                count_launch(h);
-            })
-        }
-        if (pooled_out != nullptr && pooled_out != h->ws_pooled)
-            CUDA_OK(h, cudaMemcpyAsync(pooled_out, h->ws_pooled, static_cast<size_t>(B) * C * h->esz, cudaMemcpyDeviceToDevice, st));
-        CUDA_OK(h, cudaGetLastError());
-        return 0;
-    }
     DISPATCH_T(h, T, {
         const long long n = static_cast<long long>(B) * P * (3 * c.vit_patch + 1);
         ProfScope ps_kc_im2col(h, KC_IM2COL, st);
@@ -966,7 +687,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaS
     if (launch_gemv(h, a, 1, st)) return 1;
     a = gv(h->pj_in, 2 * Di, Dm, PRO_LAYERNORM, h->pj_h0, GEPI_MAMBA_CONV, h->pj_xc);
     a.nw = h->pj_norm_w; a.nb = h->pj_norm_b; a.eps = c.proj_eps;
-    a.conv_state = h->pj_conv_state; a.conv_w = h->pj_conv_w; a.conv_b = h->pj_conv_b; a.z_out = h->pj_z;
+    a.conv_state = static_cast<char*>(h->pj_conv_state) + static_cast<size_t>(h->cur) * Di * c.proj_d_conv * h->esz; a.conv_w = h->pj_conv_w; a.conv_b = h->pj_conv_b; a.z_out = h->pj_z;
     a.d_inner = Di; a.d_conv = c.proj_d_conv;
     batched(a, Dm, Di, 0, Di);
     if (launch_gemv(h, a, 1, st)) return 1;
@@ -975,7 +696,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaS
     if (launch_gemv(h, a, 1, st)) return 1;
     ScanArgs s{};
     s.W_dt = h->pj_dt_w; s.b_dt = h->pj_dt_b; s.A_log = h->pj_alog; s.D = h->pj_D; s.xdb = h->pj_xdb; s.x = h->pj_xc;
-    s.z = h->pj_z; s.state = h->pj_ssm_state; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
+    s.z = h->pj_z; s.state = h->pj_ssm_state + static_cast<size_t>(h->cur) * Di * N; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
     s.nv = nv; s.xdb_stride = nxp; s.x_stride = Di; s.z_stride = Di; s.y_stride = Di;
     const int scan_smem = (nv * nxp * 2 + 15) & ~15;
     DISPATCH_T(h, T, {
@@ -1124,54 +845,6 @@ int run_proj_gate(sm_handle* h, const void* pooled, void* toks, float* logits, i
     return 0;
 }
 
-// one decode step: feeds the token in d_tok at position *d_pos, leaves the next token in d_tok
-int run_decode_step(sm_handle* h, cudaStream_t st) {
-    const sm_config& c = h->cfg;
-    const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn;
-    const int QKV = (Hq + 2 * Hk) * D;
-    if (D != 128) return fail(h, "llm decode: head_dim %d not supported (128)", D);
-    DISPATCH_T(h, T, {
-        CUDA_OK(h, launch_pdl(h, gather_rows_kernel<T>, dim3(1), dim3(256), 0, st, (const T*)h->lm_embed, (const int*)h->d_tok, (T*)h->lw_x, 1, H));
-        count_launch(h);
-    })
-    const float scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
-    for (int l = 0; l < c.llm_layers; ++l) {
-        const MistralLayer& L = h->llm[l];
-        GemvArgs a = gv(L.wqkv, QKV, H, PRO_RMSNORM, h->lw_x, GEPI_STORE, h->lw_qkv);
-        a.nw = L.in_ln; a.eps = c.llm_eps;
-        if (launch_gemv(h, a, 1, st)) return 1;
-        DISPATCH_T(h, T, {
-            CUDA_OK(h, launch_pdl(h, rope_append_kernel<T>, dim3(8), dim3(256), 0, st, (T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], 1, Hq, Hk, D,
-                                                     c.llm_max_ctx, (const int*)h->d_pos, 0, c.llm_rope_theta));
-            count_launch(h);
-            CUDA_OK(h, launch_pdl(h, decode_attn_partial_kernel<T, 128>, dim3(h->dec_splits, Hk), dim3(128), 0, st,
-                (const T*)h->lw_qkv, (const T*)h->kc[l], (const T*)h->vc[l], h->lw_part, Hq, Hk, c.llm_max_ctx,
-                (const int*)h->d_pos, 0, scale_log2e));
-            count_launch(h);
-            CUDA_OK(h, launch_pdl(h, decode_attn_combine_kernel<T, 128>, dim3(Hq), dim3(128), 0, st, (const float*)h->lw_part, (T*)h->lw_att, h->dec_splits));
-            count_launch(h);
-        })
-        a = gv(L.wo, H, Hq * D, PRO_PLAIN, h->lw_att, GEPI_RESID, nullptr);
-        a.resid = h->lw_x;
-        if (launch_gemv(h, a, 1, st)) return 1;
-        a = gv(L.wgu, F, H, PRO_RMSNORM, h->lw_x, GEPI_SWIGLU, h->lw_m);
-        a.W1 = reinterpret_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz;
-        a.nw = L.post_ln; a.eps = c.llm_eps;
-        if (launch_gemv(h, a, 2, st)) return 1;
-        a = gv(L.wd, H, F, PRO_PLAIN, h->lw_m, GEPI_RESID, nullptr);
-        a.resid = h->lw_x;
-        if (launch_gemv(h, a, 1, st)) return 1;
-    }
-    GemvArgs a = gv(h->lm_head, c.llm_vocab, H, PRO_RMSNORM, h->lw_x, GEPI_F32, h->lw_logits);
-    a.nw = h->lm_norm; a.eps = c.llm_eps;
-    if (launch_gemv(h, a, 1, st)) return 1;
-    argmax_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, h->d_tok, h->d_out, h->d_nout, h->d_pos, h->d_stop,
-                                      h->d_done);
-    count_launch(h);
-    CUDA_OK(h, cudaGetLastError());
-    return 0;
-}
-
 int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStream_t st) {
     const sm_config& c = h->cfg;
     const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn;
@@ -1195,11 +868,13 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         DISPATCH_T(h, T, {
             const long long tot = static_cast<long long>(P) * ((Hq + Hk) * (D / 2) + Hk * D);
             rope_append_kernel<T><<<static_cast<int>(std::min<long long>((tot + 255) / 256, 2048)), 256, 0, st>>>(
-                (T*)h->lw_qkv, (T*)h->kc[l], (T*)h->vc[l], P, Hq, Hk, D, c.llm_max_ctx, nullptr, pos0, c.llm_rope_theta);
+                (T*)h->lw_qkv, (T*)h->kc[l] + h->cur * h->kv_stream_stride, (T*)h->vc[l] + h->cur * h->kv_stream_stride, P, Hq, Hk, D, c.llm_max_ctx, nullptr, pos0, c.llm_rope_theta);
             count_launch(h);
         })
         AttnArgs a{};
-        a.q = h->lw_qkv; a.k = h->kc[l]; a.v = h->vc[l]; a.o = h->lw_att;
+        a.q = h->lw_qkv; a.o = h->lw_att;
+        a.k = static_cast<char*>(h->kc[l]) + h->cur * h->kv_stream_stride * h->esz;
+        a.v = static_cast<char*>(h->vc[l]) + h->cur * h->kv_stream_stride * h->esz;
         a.q_bs = 0; a.q_ss = QKV;
         a.k_bs = a.v_bs = 0; a.k_hs = a.v_hs = static_cast<long long>(c.llm_max_ctx) * D; a.k_ss = a.v_ss = D;
         a.o_bs = 0; a.o_ss = Hq * D;
@@ -1232,6 +907,137 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ persistent decode step
+// Slot geometry of a GEMV op (decode_stream.cuh): R rows of K elements per 32 KB ring slot (a power of two <= 8),
+// P = 8 / R parts per row, one (row, part) per consumer warp.
+int ds_geometry(sm_handle* h, int K, int nmat, int* R, int* P) {
+    const int fit = kDsSlotBytes / (K * 2);
+    if (fit < nmat) return fail(h, "decode kernel: a row of K = %d elements does not fit a %d-byte ring slot", K, kDsSlotBytes);
+    int r = kDsGroupWarps;
+    while (r > fit) r >>= 1;
+    const int p = kDsGroupWarps / r;
+    if (K % p != 0 || (K / p) % 256 != 0) return fail(h, "decode kernel: K = %d cannot be split into %d parts of 256-weight block pairs", K, p);
+    *R = r; *P = p;
+    return 0;
+}
+
+// The op list of ONE decode step (hf MistralForCausalLM.forward for one new token per lane + greedy argmax), built once:
+// per layer [qkv GEMV (RMSNorm prologue) | attention (RoPE, KV append, split-KV softmax, combine) | o_proj GEMV (+residual)
+// | gate/up GEMV (RMSNorm prologue, SwiGLU epilogue) | down GEMV (+residual)], then lm_head (RMSNorm prologue, fp32
+// logits, per-CTA argmax candidates) and the token selection.  embed_tokens is fused into the first layer.
+int build_decode_ops(sm_handle* h) {
+    const sm_config& c = h->cfg;
+    const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn, V = c.llm_vocab;
+    const int QKV = (Hq + 2 * Hk) * D, G = h->num_sms;
+    if (kDsMaxStreams * Hk > G) return fail(h, "decode kernel: %d lanes x %d kv heads exceed %d SMs", kDsMaxStreams, Hk, G);
+    std::vector<DsOp> ops;
+    int part_rows = 0, xcap = 0;
+    auto gemv = [&](const void* W0, const void* W1, int N, int K, int pro, int epi, const void* x, long long xs, const void* nw,
+                    void* y, long long ys, void* resid, long long rs) -> int {
+        DsOp o{};
+        o.type = DS_GEMV; o.W0 = W0; o.W1 = W1; o.nmat = W1 ? 2 : 1; o.N = N; o.K = K;
+        if (ds_geometry(h, K, o.nmat, &o.R, &o.P)) return 1;
+        o.pro = pro; o.epi = epi; o.x = x; o.x_stride = xs; o.nw = nw; o.eps = c.llm_eps; o.y = y; o.y_stride = ys;
+        o.resid = resid; o.resid_stride = rs;
+        ops.push_back(o);
+        part_rows = std::max(part_rows, o.nmat * ((N + G - 1) / G) * o.P);
+        xcap = std::max(xcap, (K + 7) & ~7);
+        return 0;
+    };
+    int n_bar = 0;
+    for (int l = 0; l < c.llm_layers; ++l) {
+        const MistralLayer& L = h->llm[l];
+        if (gemv(L.wqkv, nullptr, QKV, H, l == 0 ? DSP_EMBED_RMSNORM : DSP_RMSNORM, DSE_STORE, h->ds_x, H, L.in_ln, h->ds_qkv, QKV, nullptr, 0)) return 1;
+        DsOp a{};
+        a.type = DS_ATTN; a.qkv = h->ds_qkv; a.qkv_stride = QKV; a.kc = h->kc[l]; a.vc = h->vc[l];
+        a.kv_stream_stride = h->kv_stream_stride; a.att = h->ds_att; a.Hq = Hq; a.Hk = Hk; a.max_ctx = c.llm_max_ctx;
+        a.rope_theta = c.llm_rope_theta;
+        a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+        ops.push_back(a);
+        if (gemv(L.wo, nullptr, H, Hq * D, DSP_PLAIN, l == 0 ? DSE_RESID_EMBED : DSE_RESID, h->ds_att, Hq * D, nullptr, nullptr, 0, h->ds_x, H)) return 1;
+        if (gemv(L.wgu, static_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz, F, H, DSP_RMSNORM, DSE_SWIGLU, h->ds_x, H,
+                 L.post_ln, h->ds_m, F, nullptr, 0)) return 1;
+        if (gemv(L.wd, nullptr, H, F, DSP_PLAIN, DSE_RESID, h->ds_m, F, nullptr, nullptr, 0, h->ds_x, H)) return 1;
+        n_bar += 5;
+    }
+    if (gemv(h->lm_head, nullptr, V, H, DSP_RMSNORM, DSE_LOGITS, h->ds_x, H, h->lm_norm, h->ds_logits, V, nullptr, 0)) return 1;
+    n_bar += 1;
+    DsOp fin{};
+    fin.type = DS_FINAL;
+    ops.push_back(fin);
+    h->ds_ops = static_cast<DsOp*>(dalloc(h, ops.size() * sizeof(DsOp)));
+    if (!h->ds_ops) return fail(h, "decode kernel: out of device memory");
+    CUDA_OK(h, cudaMemcpy(h->ds_ops, ops.data(), ops.size() * sizeof(DsOp), cudaMemcpyHostToDevice));
+    h->ds_n_ops = static_cast<int>(ops.size());
+    h->ds_n_barriers = n_bar;
+    h->ds_xcap = xcap;
+    h->ds_part_rows = part_rows;
+    return 0;
+}
+
+// shared-memory plan of a launch with nv lanes: ring slots, staging region, partial sums
+struct DsSmem { int n_slots, x_bytes, part_cap; size_t total; };
+DsSmem ds_smem_plan(const sm_handle* h, int nv) {
+    DsSmem m{};
+    const int group = h->cfg.llm_heads / h->cfg.llm_kv_heads;
+    m.x_bytes = static_cast<int>(std::max<size_t>(static_cast<size_t>(nv) * h->ds_xcap * 2, decode_stream_attn_scratch_bytes(group)));
+    m.x_bytes = (m.x_bytes + 127) & ~127;
+    m.part_cap = (h->ds_part_rows * nv + 31) & ~31;
+    const long long budget = 227 * 1024 - 2048 /* static shared memory of the kernel */ - m.x_bytes - static_cast<long long>(m.part_cap) * 4;
+    static const int env_slots = getenv("SMB_DS_SLOTS") ? atoi(getenv("SMB_DS_SLOTS")) : kDsMaxSlots;
+    m.n_slots = static_cast<int>(std::max<long long>(0, std::min<long long>(std::min(env_slots, kDsMaxSlots), budget / kDsSlotBytes)));
+    m.total = decode_stream_smem_bytes(m.n_slots, m.x_bytes, m.part_cap);
+    return m;
+}
+
+template <typename T>
+int launch_decode_step_t(sm_handle* h, int nv, cudaStream_t st) {
+    const DsSmem m = ds_smem_plan(h, nv);
+    if (m.n_slots < 2) return fail(h, "decode kernel: %d lanes leave no room for the weight ring", nv);
+    DsParams p{};
+    p.ops = h->ds_ops; p.n_ops = h->ds_n_ops; p.n_slots = m.n_slots; p.xcap = h->ds_xcap; p.x_bytes = m.x_bytes; p.part_cap = m.part_cap;
+    p.sync = h->ds_sync; p.n_barriers = h->ds_n_barriers; p.st = h->ds_state; p.out_ids = h->ds_out; p.out_stride = kDsMaxNew;
+    p.stop = h->ds_stop; p.embed = h->lm_embed; p.H = h->cfg.llm_hidden; p.att_part = h->ds_att_part;
+    p.cand_val = h->ds_cand_val; p.cand_idx = h->ds_cand_idx; p.dbg = h->ds_dbg;
+    {
+        static const int ahead = getenv("SMB_DS_L2_AHEAD") ? atoi(getenv("SMB_DS_L2_AHEAD")) : 0;   // measured: an L2 prefetch cursor 8 / 16 chunks ahead is slower (3.65 / 5.4 vs 3.32 ms per step)
+        static const int flags = getenv("SMB_DS_DBG") ? atoi(getenv("SMB_DS_DBG")) : 0;
+        p.l2_ahead = std::max(0, ahead) & ~1;
+        p.dbg_flags = flags;
+    }
+    const dim3 grid(h->num_sms), block(kDsThreads);
+    switch (nv) {
+        case 1: decode_stream_kernel<T, 1><<<grid, block, m.total, st>>>(p); break;
+        case 2: decode_stream_kernel<T, 2><<<grid, block, m.total, st>>>(p); break;
+        case 3: decode_stream_kernel<T, 3><<<grid, block, m.total, st>>>(p); break;
+        case 4: decode_stream_kernel<T, 4><<<grid, block, m.total, st>>>(p); break;
+        default: return fail(h, "decode kernel: %d lanes not instantiated (1..%d)", nv, kDsMaxStreams);
+    }
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+int launch_decode_step(sm_handle* h, int nv, cudaStream_t st) {
+    DISPATCH_T(h, T, return launch_decode_step_t<T>(h, nv, st);)
+}
+
+// fold finished event pairs of earlier sm_llm_decode calls into the running totals (sm_decode_stats)
+void ds_collect_timings(sm_handle* h, bool wait) {
+    size_t k = 0;
+    for (auto& t : h->ds_pending) {
+        if (wait) cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        if (cudaEventQuery(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            h->ds_ms += ms; h->ds_steps += t.steps; h->ds_tokens += t.tokens; h->ds_ctx_sum += t.ctx_sum;
+            cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+        } else {
+            h->ds_pending[k++] = t;
+        }
+    }
+    h->ds_pending.resize(k);
+}
+
 // Captures `body` (which must already have run once on a real stream, so tensor maps / plans exist) into a graph.
 template <typename F>
 int capture_graph(sm_handle* h, F&& body, cudaGraphExec_t* out, long long* n_launches, const char* what) {
@@ -1253,16 +1059,15 @@ int capture_graph(sm_handle* h, F&& body, cudaGraphExec_t* out, long long* n_lau
 // work, so a GEMM is planned for bytes per flop (wide tiles, no split-K) instead of for its own latency.
 // Measured at 4 lanes + gate batching (frames/s): split-K 4 -> 894, 2 -> 955, none -> 1025.
 struct PipePlanScope {
-    sm_handle* h; int div, ssm, msp, pre, pg;
-    explicit PipePlanScope(sm_handle* h_) : h(h_), div(h_->plan_div), ssm(h_->split_sms), msp(h_->max_split), pre(h_->gemm_pre), pg(h_->pgemm) {
+    sm_handle* h; int div, ssm, msp, pre;
+    explicit PipePlanScope(sm_handle* h_) : h(h_), div(h_->plan_div), ssm(h_->split_sms), msp(h_->max_split), pre(h_->gemm_pre) {
         static const int pdiv = getenv("SMB_PLAN_DIV") ? std::max(1, atoi(getenv("SMB_PLAN_DIV"))) : 8;
         static const int s_sm = getenv("SMB_SPLIT_SMS") ? atoi(getenv("SMB_SPLIT_SMS")) : 0;
         static const int s_k = getenv("SMB_PIPE_SPLITK") ? std::max(1, atoi(getenv("SMB_PIPE_SPLITK"))) : 1;
         static const int s_pre = getenv("SMB_PIPE_PRE") ? atoi(getenv("SMB_PIPE_PRE")) : 0;
-        static const int s_pg = getenv("SMB_PGEMM") ? std::max(0, atoi(getenv("SMB_PGEMM"))) : 0;
-        if (h->n_lanes > 1 || h->tower_batch > 1) { h->plan_div = pdiv; h->split_sms = s_sm; h->max_split = s_k; h->gemm_pre = s_pre; h->pgemm = s_pg; }
+        if (h->n_lanes > 1 || h->tower_batch > 1) { h->plan_div = pdiv; h->split_sms = s_sm; h->max_split = s_k; h->gemm_pre = s_pre; }
     }
-    ~PipePlanScope() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; h->pgemm = pg; }
+    ~PipePlanScope() { select_lane(h, 0); h->plan_div = div; h->split_sms = ssm; h->max_split = msp; h->gemm_pre = pre; }
 };
 
 // run `body` on stream s: directly, or through a graph captured after the first (real) run
@@ -1330,13 +1135,7 @@ int pipe_flush(sm_handle* h) {
     }
 
     auto gate_body = [&](cudaStream_t s) -> int {
-        const int saved_cap = h->gemv_grid_cap;
-        const bool saved_tma = h->gemv_tma;
-        if (h->bg_grid > 0) { h->gemv_grid_cap = h->bg_grid; h->gemv_tma = true; }   // "background" gate experiment
-        const int rc = run_proj_gate(h, pooled, h->pj_toks, h->gt_logits, nframes, s);
-        h->gemv_grid_cap = saved_cap;
-        h->gemv_tma = saved_tma;
-        return rc;
+        return run_proj_gate(h, pooled, h->pj_toks, h->gt_logits, nframes, s);
     };
     if (pipe_run_part(h, nframes | (1 << 9) | (1 << 11) | (slot0 << 24) | kf, gs, gate_body, "sm_frame_submit(gate)")) return 1;
     int f0 = 0;
@@ -1389,6 +1188,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     h->num_sms = prop.multiProcessorCount;
     const sm_config& c = h->cfg;
     if (c.max_frames < 1) h->cfg.max_frames = 1;
+    h->n_streams = std::max(1, c.n_streams);
+    if (h->n_streams > kMaxHandleStreams) { delete h; return fail(nullptr, "sm_create: n_streams %d > %d", c.n_streams, kMaxHandleStreams); }
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
@@ -1397,14 +1198,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
     }
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     h->use_pdl = getenv("SMB_NO_PDL") == nullptr;
-    h->gemm_occ2 = getenv("SMB_GEMM_OCC2") ? atoi(getenv("SMB_GEMM_OCC2")) : 0;
-    if (getenv("SMB_DEC_SPLITS")) h->dec_splits = std::max(1, std::min(128, atoi(getenv("SMB_DEC_SPLITS"))));
     h->max_split = getenv("SMB_SPLITK") ? std::max(1, atoi(getenv("SMB_SPLITK"))) : 4;
     h->gemm_pre = getenv("SMB_GEMM_PRE") ? atoi(getenv("SMB_GEMM_PRE")) : 1;
-    // experimental bulk-copy + mma.sync GEMV (gemv_tma.cuh): not faster than gemv.cuh on B200 (both sit at the same
-    // ~48 GB/s-per-SM bulk/HBM limit) and 1 fp16 ulp off the oracle on the gate logits -> off unless asked for
-    h->gemv_tma = getenv("SMB_GEMV_TMA") ? atoi(getenv("SMB_GEMV_TMA")) != 0 : false;
-    h->gemv_grid_cap = getenv("SMB_GEMV_GRID") ? atoi(getenv("SMB_GEMV_GRID")) : 0;
     if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(nullptr, "sm_create: cudaStreamCreate failed");
@@ -1512,8 +1307,6 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
             w.ws_part = static_cast<float*>(A(static_cast<size_t>(4) * rows * C * sizeof(float)));
         }
         h->px_ring = A(static_cast<size_t>(kTicketRing) * 3 * c.vit_image * c.vit_image * e);
-        h->mega_sync = static_cast<unsigned int*>(A(256));
-        h->mega_mode = getenv("SMB_MEGA") ? atoi(getenv("SMB_MEGA")) : 0;
     }
     // ---------------- projector
     if (c.proj_d_model > 0) {
@@ -1547,8 +1340,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         if (N > 32) { delete h; return fail(nullptr, "sm_create: projector d_state %d > 32 not supported", N); }
         h->pj_h0 = A(NB * Dm * e); h->pj_xc = A(NB * Di * e); h->pj_z = A(NB * Di * e); h->pj_xdb = A(NB * ((R + 2 * N + 7) & ~7) * e + 64);
         h->pj_y = A(NB * Di * e); h->pj_r2 = A(NB * Dm * e);
-        h->pj_conv_state = A(static_cast<size_t>(Di) * W * e);
-        h->pj_ssm_state = static_cast<float*>(A(static_cast<size_t>(Di) * N * sizeof(float)));
+        h->pj_conv_state = A(static_cast<size_t>(h->n_streams) * Di * W * e);                           // per stream
+        h->pj_ssm_state = static_cast<float*>(A(static_cast<size_t>(h->n_streams) * Di * N * sizeof(float)));
         h->pj_toks = A(static_cast<size_t>(std::max(Bm, kTowerBatch)) * Dm * e);
     }
     // ---------------- gate
@@ -1610,8 +1403,8 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
             add_slot(h, lp + "mlp.gate_proj.weight", L.wgu, F, H);
             add_slot(h, lp + "mlp.up_proj.weight", (char*)L.wgu + static_cast<size_t>(F) * H * e, F, H);
             L.wd = A(static_cast<size_t>(H) * F * e); add_slot(h, lp + "mlp.down_proj.weight", L.wd, H, F);
-            h->kc[l] = A(static_cast<size_t>(Hk) * c.llm_max_ctx * D * e);
-            h->vc[l] = A(static_cast<size_t>(Hk) * c.llm_max_ctx * D * e);
+            h->kc[l] = A(static_cast<size_t>(h->n_streams) * Hk * c.llm_max_ctx * D * e);                // [stream][Hk][max_ctx][D]
+            h->vc[l] = A(static_cast<size_t>(h->n_streams) * Hk * c.llm_max_ctx * D * e);
         }
         h->lm_norm = A(H * e); add_slot(h, "model.norm.weight", h->lm_norm, 1, H);
         h->lm_head = A(static_cast<size_t>(V) * H * e); add_slot(h, "lm_head.weight", h->lm_head, V, H);
@@ -1619,17 +1412,31 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         const size_t Pm = h->pmax;
         h->lw_x = A(Pm * H * e); h->lw_hn = A(Pm * H * e); h->lw_qkv = A(Pm * QKV * e); h->lw_att = A(Pm * Hq * D * e);
         h->lw_gu = A(Pm * 2 * F * e); h->lw_m = A(Pm * F * e);
-        h->lw_logits = static_cast<float*>(A(static_cast<size_t>(V) * sizeof(float)));
-        h->lw_part = static_cast<float*>(A(static_cast<size_t>(Hq) * h->dec_splits * (D + 2) * sizeof(float)));
+        h->lw_logits = static_cast<float*>(A(static_cast<size_t>(h->n_streams) * V * sizeof(float)));
+        h->kv_stream_stride = static_cast<long long>(Hk) * c.llm_max_ctx * D;
         h->lw_part2 = static_cast<float*>(A(static_cast<size_t>(8) * 64 * std::max(QKV, H) * sizeof(float)));
-        int* ints = static_cast<int*>(A((8 + 4096 + 64) * sizeof(int)));
-        h->d_pos = ints; h->d_tok = ints + 1; h->d_nout = ints + 2; h->d_done = ints + 3; h->d_out = ints + 8;
-        h->d_stop = ints + 8 + 4096;
+        // persistent decode kernel: activations of up to kDsMaxStreams lanes, state, split-KV partials, argmax candidates
+        const size_t NL = kDsMaxStreams;
+        h->ds_x = A(NL * H * e); h->ds_qkv = A(NL * QKV * e); h->ds_att = A(NL * Hq * D * e); h->ds_m = A(NL * F * e);
+        h->ds_logits = static_cast<float*>(A(NL * V * sizeof(float)));
+        h->ds_sync = static_cast<unsigned*>(A((8 + 2 * NL * Hk) * sizeof(unsigned)));
+        h->ds_state = static_cast<DsStreamState*>(A(NL * sizeof(DsStreamState)));
+        h->ds_out = static_cast<int*>(A(NL * kDsMaxNew * sizeof(int)));
+        h->ds_stop = static_cast<int*>(A(64 * sizeof(int)));
+        h->ds_att_part = static_cast<float*>(A(NL * Hq * h->num_sms * (D + 2) * sizeof(float)));
+        h->ds_cand_val = static_cast<float*>(A(NL * h->num_sms * sizeof(float)));
+        h->ds_cand_idx = static_cast<int*>(A(NL * h->num_sms * sizeof(int)));
+        h->kv_lens.assign(h->n_streams, 0);
     }
     if (oom) {
         std::string msg = "sm_create: cudaMalloc failed (out of device memory)";
         sm_destroy(h);
         return fail(nullptr, "%s", msg.c_str());
+    }
+    if (c.llm_layers > 0 && build_decode_ops(h)) {
+        g_create_error = h->err;
+        sm_destroy(h);
+        return 1;
     }
     cudaDeviceSynchronize();
     *out = h;
@@ -1641,7 +1448,7 @@ void sm_destroy(sm_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto& g : h->frame_graphs) cudaGraphExecDestroy(g.second);
-    if (h->decode_graph) cudaGraphExecDestroy(h->decode_graph);
+    for (auto& t : h->ds_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (auto st : h->vit_streams) if (st) cudaStreamDestroy(st);
     if (h->gate_stream) cudaStreamDestroy(h->gate_stream);
@@ -1713,22 +1520,31 @@ int sm_finalize_weights(sm_handle* h) {
     return 0;
 }
 
-int sm_stream_reset(sm_handle* h) {
+int sm_stream_reset(sm_handle* h, void* stream) {
     if (!h) return 1;
     cudaSetDevice(h->device);
-    if (h->pipe_init) {
-        if (pipe_flush(h)) return 1;
-        for (auto st : h->vit_streams) CUDA_OK(h, cudaStreamSynchronize(st));
-        CUDA_OK(h, cudaStreamSynchronize(h->gate_stream));
-    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pipe_join(h, st)) return 1;            // frames still in flight on the internal streams belong to the old stream state
     if (h->pj_conv_state) {
-        CUDA_OK(h, cudaMemset(h->pj_conv_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_conv * h->esz));
-        CUDA_OK(h, cudaMemset(h->pj_ssm_state, 0, static_cast<size_t>(h->d_inner) * h->cfg.proj_d_state * sizeof(float)));
+        const size_t cb = static_cast<size_t>(h->d_inner) * h->cfg.proj_d_conv * h->esz, sb = static_cast<size_t>(h->d_inner) * h->cfg.proj_d_state * sizeof(float);
+        CUDA_OK(h, cudaMemsetAsync(static_cast<char*>(h->pj_conv_state) + h->cur * cb, 0, cb, st));
+        CUDA_OK(h, cudaMemsetAsync(reinterpret_cast<char*>(h->pj_ssm_state) + h->cur * sb, 0, sb, st));
     }
-    h->kv_len = 0;
-    if (h->d_pos) CUDA_OK(h, cudaMemset(h->d_pos, 0, 8 * sizeof(int)));
+    if (!h->kv_lens.empty()) h->kv_lens[h->cur] = 0;
     return 0;
 }
+
+int sm_stream_select(sm_handle* h, int stream_id) {
+    if (!h) return 1;
+    if (stream_id < 0 || stream_id >= h->n_streams) return fail(h, "sm_stream_select: stream %d outside [0, %d)", stream_id, h->n_streams);
+    if (stream_id == h->cur) return 0;
+    cudaSetDevice(h->device);
+    if (h->pipe_init && pipe_flush(h)) return 1;     // an open batch of tickets never mixes streams
+    h->cur = stream_id;
+    return 0;
+}
+
+int sm_num_streams(const sm_handle* h) { return h ? h->n_streams : -1; }
 
 int sm_vit_encode(sm_handle* h, const void* pixels, int B, void* feats_out, void* pooled_out, void* stream) {
     if (!h || h->cfg.vit_layers <= 0) return fail(h, "sm_vit_encode: vision tower not configured");
@@ -1943,12 +1759,10 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
         // (up to 4) lanes; otherwise every ticket runs its own tower on one of (up to 8) lanes
         h->tower_batch = c.max_frames == 1 ? std::max(1, std::min(kTowerBatch, getenv("SMB_TOWER_BATCH") ? atoi(getenv("SMB_TOWER_BATCH")) : kTowerBatch)) : 1;
         if (h->tower_batch == 3 || (h->tower_batch > 4 && h->tower_batch < 8)) h->tower_batch = 4;   // groups must tile the ticket ring
-        if (h->mega_mode > 0) h->tower_batch = 1;                        // the persistent tower stages pixels per lane
         const int lanes_default = h->tower_batch > 1 ? 2 : 8;
         h->n_lanes = std::max(1, std::min(h->tower_batch > 1 ? 3 : kMaxLanes, getenv("SMB_LANES") ? atoi(getenv("SMB_LANES")) : lanes_default));
         h->gate_batch = std::max(1, std::min(kGemvBatch, getenv("SMB_GATE_BATCH") ? atoi(getenv("SMB_GATE_BATCH")) : kGemvBatch));
         if (h->gate_batch == 3) h->gate_batch = 2;   // groups must tile the ticket ring
-        h->bg_grid = getenv("SMB_BG_GRID") ? atoi(getenv("SMB_BG_GRID")) : 0;
         h->pipe_init = true;
     }
     const long long tk = h->ticket;
@@ -2031,7 +1845,8 @@ int sm_embed_tokens(sm_handle* h, const int32_t* ids, int n, void* out, void* st
 int sm_llm_prefill(sm_handle* h, const void* embeds, int P, float* last_logits, void* stream) {
     if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_llm_prefill: LLM not configured");
     if (P < 1) return fail(h, "sm_llm_prefill: P must be >= 1");
-    if (h->kv_len + P > h->cfg.llm_max_ctx) return fail(h, "sm_llm_prefill: %d + %d exceeds llm_max_ctx %d", h->kv_len, P, h->cfg.llm_max_ctx);
+    int& kv_len = h->kv_lens[h->cur];
+    if (kv_len + P > h->cfg.llm_max_ctx) return fail(h, "sm_llm_prefill: %d + %d exceeds llm_max_ctx %d", kv_len, P, h->cfg.llm_max_ctx);
     cudaSetDevice(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const sm_config& c = h->cfg;
@@ -2039,95 +1854,144 @@ int sm_llm_prefill(sm_handle* h, const void* embeds, int P, float* last_logits, 
     while (done < P) {
         const int n = std::min(h->pmax, P - done);
         const char* src = static_cast<const char*>(embeds) + static_cast<size_t>(done) * c.llm_hidden * h->esz;
-        if (run_prefill_chunk(h, src, n, h->kv_len, st)) return 1;
-        h->kv_len += n;
+        if (run_prefill_chunk(h, src, n, kv_len, st)) return 1;
+        kv_len += n;
         done += n;
         last_chunk = n;
     }
     // final norm + lm_head on the last position only (generate() needs nothing else)
     const char* xlast = static_cast<const char*>(h->lw_x) + static_cast<size_t>(last_chunk - 1) * c.llm_hidden * h->esz;
-    GemvArgs a = gv(h->lm_head, c.llm_vocab, c.llm_hidden, PRO_RMSNORM, xlast, GEPI_F32, h->lw_logits);
+    float* logits = h->lw_logits + static_cast<size_t>(h->cur) * c.llm_vocab;      // kept per stream until its decode call
+    GemvArgs a = gv(h->lm_head, c.llm_vocab, c.llm_hidden, PRO_RMSNORM, xlast, GEPI_F32, logits);
     a.nw = h->lm_norm; a.eps = c.llm_eps;
     if (launch_gemv(h, a, 1, st)) return 1;
-    if (last_logits) CUDA_OK(h, cudaMemcpyAsync(last_logits, h->lw_logits, static_cast<size_t>(c.llm_vocab) * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    const int pos = h->kv_len;
-    CUDA_OK(h, cudaMemcpyAsync(h->d_pos, &pos, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (last_logits) CUDA_OK(h, cudaMemcpyAsync(last_logits, logits, static_cast<size_t>(c.llm_vocab) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int sm_llm_decode_multi(sm_handle* h, int n, const int* stream_ids, const int* max_new, const int32_t* stop_ids, int n_stop,
+                        int32_t* ids_out_host, int out_stride, int32_t* n_out_host, void* stream) {
+    if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_llm_decode: LLM not configured");
+    if (n < 1 || n > kDsMaxStreams) return fail(h, "sm_llm_decode: %d streams per pass outside [1, %d]", n, kDsMaxStreams);
+    if (!stream_ids || !max_new || !ids_out_host || !n_out_host) return fail(h, "sm_llm_decode: null argument");
+    if (n_stop < 0 || n_stop > 63) return fail(h, "sm_llm_decode: at most 63 stop ids");
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sm_config& c = h->cfg;
+    DsStreamState hs[kDsMaxStreams] = {};
+    int steps = 0;
+    long long ctx_sum = 0, tok_sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const int s = stream_ids[i];
+        if (s < 0 || s >= h->n_streams) return fail(h, "sm_llm_decode: stream %d outside [0, %d)", s, h->n_streams);
+        for (int j = 0; j < i; ++j)
+            if (stream_ids[j] == s) return fail(h, "sm_llm_decode: stream %d listed twice", s);
+        if (max_new[i] < 1) return fail(h, "sm_llm_decode: max_new must be >= 1");
+        if (h->kv_lens[s] < 1) return fail(h, "sm_llm_decode: stream %d has no prefilled context (call sm_llm_prefill first)", s);
+        // a stream at the end of its cache produces what still fits (the token fed at position p needs slot p)
+        const int room = c.llm_max_ctx - h->kv_lens[s] + 1;
+        const int mn = std::min({max_new[i], room, kDsMaxNew, out_stride});
+        if (mn < 1) return fail(h, "sm_llm_decode: KV cache of stream %d is full (%d of %d)", s, h->kv_lens[s], c.llm_max_ctx);
+        hs[i].pos = h->kv_lens[s]; hs[i].max_new = mn; hs[i].kv_slot = s;
+        steps = std::max(steps, mn - 1);
+    }
+    int stopbuf[64] = {};
+    stopbuf[0] = n_stop;
+    for (int i = 0; i < n_stop; ++i) stopbuf[1 + i] = stop_ids[i];
+    CUDA_OK(h, cudaMemcpyAsync(h->ds_stop, stopbuf, sizeof stopbuf, cudaMemcpyHostToDevice, st));
+    CUDA_OK(h, cudaMemcpyAsync(h->ds_state, hs, sizeof(DsStreamState) * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(h, cudaMemsetAsync(h->ds_sync, 0, (8 + 2 * static_cast<size_t>(kDsMaxStreams) * c.llm_kv_heads) * sizeof(unsigned), st));
+    ds_first_token_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, c.llm_vocab, n, h->ds_state, h->ds_out, kDsMaxNew, h->ds_stop, h->ds_sync);
+    count_launch(h);
+    CUDA_OK(h, cudaGetLastError());
+    // one launch per token; with stop ids the host looks at the all-done flag every 16 steps (a finished call turns the
+    // remaining launches into no-ops: the kernel returns at its first instruction)
+    sm_handle::DsTiming tm{};
+    CUDA_OK(h, cudaEventCreate(&tm.a));
+    CUDA_OK(h, cudaEventCreate(&tm.b));
+    CUDA_OK(h, cudaEventRecord(tm.a, st));
+    int launched = 0;
+    unsigned host_done = 0;
+    const int check_every = n_stop > 0 ? 16 : steps;
+    while (launched < steps && !host_done) {
+        const int burst = std::min(check_every, steps - launched);
+        for (int i = 0; i < burst; ++i)
+            if (launch_decode_step(h, n, st)) return 1;
+        launched += burst;
+        if (n_stop > 0 && launched < steps) {
+            CUDA_OK(h, cudaMemcpyAsync(&host_done, h->ds_sync + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CUDA_OK(h, cudaStreamSynchronize(st));
+        }
+    }
+    CUDA_OK(h, cudaEventRecord(tm.b, st));
+    CUDA_OK(h, cudaMemcpyAsync(hs, h->ds_state, sizeof(DsStreamState) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+        const int nout = std::min(hs[i].n_out, hs[i].max_new);
+        CUDA_OK(h, cudaMemcpy(ids_out_host + static_cast<size_t>(i) * out_stride, h->ds_out + static_cast<size_t>(i) * kDsMaxNew,
+                              static_cast<size_t>(nout) * sizeof(int), cudaMemcpyDeviceToHost));
+        n_out_host[i] = nout;
+        ctx_sum += static_cast<long long>(nout - 1) * (h->kv_lens[hs[i].kv_slot] + hs[i].pos + 1) / 2;   // sum over the nout - 1 steps of the KV length each one read
+        tok_sum += nout - 1;
+        h->kv_lens[hs[i].kv_slot] = hs[i].pos;
+    }
+    int steps_run = 0;
+    for (int i = 0; i < n; ++i) steps_run = std::max(steps_run, std::min(hs[i].n_out, hs[i].max_new) - 1);
+    tm.steps = steps_run; tm.tokens = tok_sum; tm.ctx_sum = ctx_sum;
+    h->ds_pending.push_back(tm);
+    ds_collect_timings(h, false);
     return 0;
 }
 
 int sm_llm_decode(sm_handle* h, int max_new, const int32_t* stop_ids, int n_stop, int32_t* ids_out_host,
                   int32_t* n_out_host, void* stream) {
-    if (!h || h->cfg.llm_layers <= 0) return fail(h, "sm_llm_decode: LLM not configured");
-    if (max_new < 1 || max_new > 4096) return fail(h, "sm_llm_decode: max_new must be in [1, 4096]");
-    if (n_stop > 63) return fail(h, "sm_llm_decode: at most 63 stop ids");
-    if (h->kv_len + max_new - 1 > h->cfg.llm_max_ctx) return fail(h, "sm_llm_decode: KV cache would overflow llm_max_ctx %d", h->cfg.llm_max_ctx);
+    if (!h) return 1;
+    if (max_new < 1 || max_new > kDsMaxNew) return fail(h, "sm_llm_decode: max_new must be in [1, %d]", kDsMaxNew);
+    const int sid = h->cur;
+    return sm_llm_decode_multi(h, 1, &sid, &max_new, stop_ids, n_stop, ids_out_host, max_new, n_out_host, stream);
+}
+
+int sm_decode_stats(sm_handle* h, double* ms, long long* steps, long long* tokens, long long* ctx_sum, int reset) {
+    if (!h) return 1;
     cudaSetDevice(h->device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const sm_config& c = h->cfg;
-    int zeros[2] = {0, 0};
-    CUDA_OK(h, cudaMemcpyAsync(h->d_nout, zeros, 2 * sizeof(int), cudaMemcpyHostToDevice, st));  // n_out, done
-    int stopbuf[64];
-    stopbuf[0] = n_stop;
-    for (int i = 0; i < n_stop; ++i) stopbuf[1 + i] = stop_ids[i];
-    CUDA_OK(h, cudaMemcpyAsync(h->d_stop, stopbuf, 64 * sizeof(int), cudaMemcpyHostToDevice, st));
-    // first token from the prefill logits (not fed back yet: position counter unchanged)
-    argmax_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, h->d_tok, h->d_out, h->d_nout, nullptr, h->d_stop,
-                                      h->d_done);
-    count_launch(h);
-    int produced = 1;
-    int host_done = 0;
-    const int check_every = n_stop > 0 ? 16 : max_new;
-    while (produced < max_new && !host_done) {
-        const int burst = std::min(check_every, max_new - produced);
-        for (int i = 0; i < burst; ++i) {
-            if (c.use_graphs) {
-                if (!h->decode_graph) {
-                    cudaGraph_t g;
-                    // make sure attributes / first-use state is set outside capture
-                    h->capturing = true;
-                    h->captured_launches = 0;
-                    CUDA_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-                    const int rc = run_decode_step(h, h->cap_stream);
-                    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
-                    h->capturing = false;
-                    if (rc || ce != cudaSuccess) return fail(h, "sm_llm_decode: graph capture failed: %s", cudaGetErrorString(ce));
-                    CUDA_OK(h, cudaGraphInstantiate(&h->decode_graph, g, 0));
-                    cudaGraphDestroy(g);
-                    h->decode_graph_launches = h->captured_launches;
-                }
-                CUDA_OK(h, cudaGraphLaunch(h->decode_graph, st));
-                h->launches += h->decode_graph_launches;
-            } else {
-                if (run_decode_step(h, st)) return 1;
-            }
-        }
-        produced += burst;
-        if (n_stop > 0) {
-            CUDA_OK(h, cudaMemcpyAsync(&host_done, h->d_done, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_OK(h, cudaStreamSynchronize(st));
-        }
-    }
-    int nout = 0, pos = 0;
-    CUDA_OK(h, cudaMemcpyAsync(&nout, h->d_nout, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(h, cudaMemcpyAsync(&pos, h->d_pos, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(h, cudaStreamSynchronize(st));
-    nout = std::min(nout, max_new);
-    CUDA_OK(h, cudaMemcpy(ids_out_host, h->d_out, static_cast<size_t>(nout) * sizeof(int), cudaMemcpyDeviceToHost));
-    *n_out_host = nout;
-    h->kv_len = pos;
+    ds_collect_timings(h, true);
+    if (ms) *ms = h->ds_ms;
+    if (steps) *steps = h->ds_steps;
+    if (tokens) *tokens = h->ds_tokens;
+    if (ctx_sum) *ctx_sum = h->ds_ctx_sum;
+    if (reset) { h->ds_ms = 0.0; h->ds_steps = h->ds_tokens = h->ds_ctx_sum = 0; }
     return 0;
 }
 
-int sm_kv_len(const sm_handle* h) { return h ? h->kv_len : -1; }
+int sm_debug_decode_phases(sm_handle* h, long long* device_buf) {
+    if (!h) return 1;
+    h->ds_dbg = device_buf;
+    return 0;
+}
+
+int sm_debug_decode_buffer(sm_handle* h, int which, void* out, long long bytes, void* stream) {
+    if (!h || !h->ds_x || !out) return fail(h, "sm_debug_decode_buffer: bad argument");
+    const void* src = which == 0 ? h->ds_x : which == 1 ? h->ds_qkv : which == 2 ? h->ds_att : which == 3 ? h->ds_m : nullptr;
+    if (!src) return fail(h, "sm_debug_decode_buffer: which = %d", which);
+    cudaSetDevice(h->device);
+    CUDA_OK(h, cudaMemcpyAsync(out, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int sm_debug_decode_logits(sm_handle* h, int lane, float* logits_out, void* stream) {
+    if (!h || !h->ds_logits || lane < 0 || lane >= kDsMaxStreams || !logits_out) return fail(h, "sm_debug_decode_logits: bad argument");
+    cudaSetDevice(h->device);
+    CUDA_OK(h, cudaMemcpyAsync(logits_out, h->ds_logits + static_cast<size_t>(lane) * h->cfg.llm_vocab,
+                               static_cast<size_t>(h->cfg.llm_vocab) * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int sm_kv_len(const sm_handle* h) { return (h && !h->kv_lens.empty()) ? h->kv_lens[h->cur] : -1; }
 
 int sm_kv_set_len(sm_handle* h, int len) {
-    if (!h) return 1;
-    if (len < 0 || len > h->kv_len) return fail(h, "sm_kv_set_len: %d outside [0, %d]", len, h->kv_len);
-    h->kv_len = len;
-    if (h->d_pos) {
-        cudaSetDevice(h->device);
-        CUDA_OK(h, cudaMemcpy(h->d_pos, &len, sizeof(int), cudaMemcpyHostToDevice));
-    }
+    if (!h || h->kv_lens.empty()) return 1;
+    if (len < 0 || len > h->kv_lens[h->cur]) return fail(h, "sm_kv_set_len: %d outside [0, %d]", len, h->kv_lens[h->cur]);
+    h->kv_lens[h->cur] = len;      // host-side bookkeeping only: positions >= len are simply overwritten by the next prefill / decode
     return 0;
 }
 
@@ -2166,16 +2030,6 @@ int sm_debug_attention_mode(sm_handle* h, int mode) {
 int sm_test_gemm_trace(sm_handle* h, long long* device_buf) {
     if (!h) return 1;
     h->gemm_dbg = device_buf;
-    return 0;
-}
-
-int sm_debug_mega_trace(sm_handle* h, long long* device_buf, int B, int* n_ops, int* types, int max_ops) {
-    if (!h) return 1;
-    h->mega_dbg = device_buf;
-    auto it = h->mega_plans.find(B);   // lane 0
-    if (n_ops) *n_ops = it == h->mega_plans.end() ? 0 : it->second.n_ops;
-    if (types && it != h->mega_plans.end())
-        for (int i = 0; i < it->second.n_ops && i < max_ops; ++i) types[i] = it->second.types[i];
     return 0;
 }
 

@@ -343,231 +343,4 @@ __global__ void __launch_bounds__(kAtcThreads, 2) attention_tc_kernel(const __gr
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Lean variant: three CTAs per SM.  The kernel above is latency-bound at two resident CTAs (profiles/r01_ncu_attention_tc.md),
-// and what limits residency is TMEM (256 columns) and shared memory (112 KB).  Here S is single-buffered (TMEM: S 64 + O 64
-// = 128 columns), K / V arrive as 64-key boxes in two 8 KB stages each and P has one buffer: 64 KB + 128 columns per CTA.
-// The softmax threads release S right after their tcgen05.ld (the 64 scores of the half live in registers), so the next
-// S still overlaps the exponentials; P V of half g - 1 has long completed when P of half g is written.
-constexpr int kAtc3HalfBytes = 64 * 128;      // 64 keys x 64 halfs
-inline int attn_tc3_smem_bytes() { return kAtcTileBytes + 4 * kAtc3HalfBytes + kAtcTileBytes + 256; }   // Q, 2 K, 2 V, P, barriers
-
-template <typename T>
-__global__ void __maxnreg__(112) attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap, const AttnTcArgs a) {
-    extern __shared__ __align__(1024) uint8_t atc_raw[];
-    uint8_t* smem = atc_raw;
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + kAtcTileBytes;          // 2 stages of 64 keys
-    uint8_t* sV = sK + 2 * kAtc3HalfBytes;     // 2 stages of 64 keys
-    uint8_t* sP = sV + 2 * kAtc3HalfBytes;     // 128 rows x 64 keys
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kAtcTileBytes);
-    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7,
-             *s_full = bars + 9, *s_empty = bars + 10, *p_full = bars + 11, *p_empty = bars + 12, *o_full = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * kAtcTile, h = blockIdx.y, b = blockIdx.z;
-    const int row_base = b * a.S;
-    const int G = (a.S + 63) / 64;             // 64-key halves
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 128); mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
-    pdl_trigger();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 64u;
-    pdl_wait();
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (boxes of 64 rows)
-        if (elect_one_sync()) {
-            mbar_arrive_expect_tx(q_full, kAtcTileBytes);
-            tma_load_2d(sQ, &tmap, q_full, a.col_q + h * 64, row_base + q0, kEvictNormal);
-            tma_load_2d(sQ + kAtc3HalfBytes, &tmap, q_full, a.col_q + h * 64, row_base + q0 + 64, kEvictNormal);
-        }
-        __syncwarp();
-        for (int g = 0; g < G; ++g) {
-            const int st = g & 1;
-            const uint32_t par = (static_cast<uint32_t>(g >> 1) & 1u) ^ 1u;
-            mbar_wait(&k_empty[st], par);
-            if (elect_one_sync()) {
-                mbar_arrive_expect_tx(&k_full[st], kAtc3HalfBytes);
-                tma_load_2d(sK + st * kAtc3HalfBytes, &tmap, &k_full[st], a.col_k + h * 64, row_base + g * 64, kEvictLast);
-            }
-            __syncwarp();
-            mbar_wait(&v_empty[st], par);
-            if (elect_one_sync()) {
-                mbar_arrive_expect_tx(&v_full[st], kAtc3HalfBytes);
-                tma_load_2d(sV + st * kAtc3HalfBytes, &tmap, &v_full[st], a.col_v + h * 64, row_base + g * 64, kEvictLast);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc_s = umma_idesc_f16(128, 64, Cvt<T>::kBf16);
-        const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64, Cvt<T>::kBf16);
-        auto issue_s = [&](int g) {
-            const int st = g & 1;
-            mbar_wait(&k_full[st], static_cast<uint32_t>(g >> 1) & 1u);
-            mbar_wait(s_empty, (static_cast<uint32_t>(g) & 1u) ^ 1u);       // the softmax threads hold S of half g - 1 in registers
-            tc_fence_after();
-            if (elect_one_sync()) {
-                const uint64_t qd = umma_desc_sw128_kmajor(smem_u32(sQ));
-                const uint64_t kd = umma_desc_sw128_kmajor(smem_u32(sK + st * kAtc3HalfBytes));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tS, qd + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-                umma_commit(&k_empty[st]);
-                umma_commit(s_full);
-            }
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0);
-        issue_s(0);
-        for (int g = 0; g < G; ++g) {
-            if (g + 1 < G) issue_s(g + 1);
-            const int st = g & 1;
-            mbar_wait(p_full, static_cast<uint32_t>(g) & 1u);               // P of half g written, O rescaled if it had to be
-            mbar_wait(&v_full[st], static_cast<uint32_t>(g >> 1) & 1u);
-            tc_fence_after();
-            if (elect_one_sync()) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint64_t pd = umma_desc_sw128_kmajor(smem_u32(sP)) + 2 * t;
-                    const uint64_t vd = umma_desc_sw128_mnmajor(smem_u32(sV + st * kAtc3HalfBytes + t * 2048));
-                    umma_f16(tO, pd, vd, idesc_o, (g | t) != 0 ? 1u : 0u);
-                }
-                umma_commit(p_empty);
-                umma_commit(&v_empty[st]);
-                if (g == G - 1) umma_commit(o_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ------------------------------------------------------------------ softmax: thread = query row = TMEM lane
-        const int lane_base = (warp & 3) * 32;
-        const int r = lane_base + lane;
-        const uint32_t lane_addr = static_cast<uint32_t>(lane_base) << 16;
-        const float c = a.scale_log2e;
-        float m_ref = -INFINITY, nmc = 0.f;
-        uint64_t l2 = atc_pack(0.f, 0.f);
-        const uint64_t c2 = atc_pack(c, c);
-        const uint32_t dst = smem_u32(sP) + r * 128;
-        for (int g = 0; g < G; ++g) {
-            const int key0 = g * 64;
-            const bool partial = key0 + 64 > a.S;
-            mbar_wait(s_full, static_cast<uint32_t>(g) & 1u);
-            tc_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld_x32(tS + lane_addr, ra);
-            tmem_ld_x32(tS + lane_addr + 32, rb);
-            tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive(s_empty);                       // S of this half now lives in registers: the next S may overwrite it
-            float mh4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (!partial || key0 + i < a.S) mh4[i & 3] = fmaxf(mh4[i & 3], __uint_as_float(ra[i]));
-                if (!partial || key0 + 32 + i < a.S) mh4[i & 3] = fmaxf(mh4[i & 3], __uint_as_float(rb[i]));
-            }
-            const float mh = fmaxf(fmaxf(mh4[0], mh4[1]), fmaxf(mh4[2], mh4[3]));
-            float f = 1.f;
-            bool resc = false;
-            if (m_ref == -INFINITY) {
-                if (mh != -INFINITY) { m_ref = mh; nmc = -mh * c; }
-            } else if ((mh - m_ref) * c > kAtcLazy) {
-                f = atc_ex2((m_ref - mh) * c);
-                m_ref = mh; nmc = -mh * c;
-                float l_lo, l_hi;
-                atc_unpack(l2, l_lo, l_hi);
-                l2 = atc_pack(l_lo * f, l_hi * f);
-                resc = true;
-            }
-            // P V of half g - 1 has completed: O may be rescaled and the P buffer rewritten
-            mbar_wait(p_empty, (static_cast<uint32_t>(g) & 1u) ^ 1u);
-            if (__any_sync(0xffffffffu, resc)) {
-                tc_fence_after();
-#pragma unroll 1
-                for (int oc = 0; oc < 2; ++oc) {
-                    uint32_t ob[32];
-                    tmem_ld_x32(tO + lane_addr + oc * 32, ob);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * f);
-                    tmem_st_x32(tO + lane_addr + oc * 32, ob);
-                }
-                tmem_wait_st();
-            }
-            const uint64_t nmc2 = atc_pack(nmc, nmc);
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float s0 = __uint_as_float(ci == 0 ? ra[2 * i] : rb[2 * i]);
-                    const float s1 = __uint_as_float(ci == 0 ? ra[2 * i + 1] : rb[2 * i + 1]);
-                    float x0, x1;
-                    atc_unpack(atc_fma2(atc_pack(s0, s1), c2, nmc2), x0, x1);
-                    float p0 = atc_ex2(x0), p1 = atc_ex2(x1);
-                    if (partial) {
-                        if (key0 + ci * 32 + 2 * i >= a.S) p0 = 0.f;
-                        if (key0 + ci * 32 + 2 * i + 1 >= a.S) p1 = 0.f;
-                    }
-                    pk[i] = Cvt<T>::pack2(p0, p1);
-                    l2 = atc_add2(l2, atc_pack(p0, p1));
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = ci * 4 + q;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((chunk ^ (r & 7)) << 4)),
-                                 "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            mbar_arrive(p_full);
-        }
-        // ---- O / l -> global
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        const int qrow = q0 + r;
-        float l_lo, l_hi;
-        atc_unpack(l2, l_lo, l_hi);
-        const float l = l_lo + l_hi;
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        T* orow = reinterpret_cast<T*>(a.o) + static_cast<long long>(row_base + qrow) * a.o_ss + h * 64;
-#pragma unroll 1
-        for (int ci = 0; ci < 2; ++ci) {
-            uint32_t rb[32];
-            tmem_ld_x32(tO + lane_addr + ci * 32, rb);
-            tmem_wait_ld();
-            if (qrow < a.S) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 o;
-                    o.x = Cvt<T>::pack2(__uint_as_float(rb[8 * q + 0]) * inv, __uint_as_float(rb[8 * q + 1]) * inv);
-                    o.y = Cvt<T>::pack2(__uint_as_float(rb[8 * q + 2]) * inv, __uint_as_float(rb[8 * q + 3]) * inv);
-                    o.z = Cvt<T>::pack2(__uint_as_float(rb[8 * q + 4]) * inv, __uint_as_float(rb[8 * q + 5]) * inv);
-                    o.w = Cvt<T>::pack2(__uint_as_float(rb[8 * q + 6]) * inv, __uint_as_float(rb[8 * q + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + ci * 32 + q * 8) = o;
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
-    }
-}
-
 }  // namespace smb

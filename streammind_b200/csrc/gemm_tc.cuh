@@ -59,19 +59,16 @@ __device__ __forceinline__ long long gtimer() {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (vit_mega.cuh)
 constexpr int kGemmThreads2 = 352;  // gemm_tc_kernel: + a second TMA producer warp (warp 10)
 constexpr int kGemmEpiThreads = 256;
 constexpr int kGemmMaxStages = 8;
 constexpr int kGemmSmemBudget = 200 * 1024;
-
-constexpr int kGemmSmemBudget2 = 108 * 1024;   // two co-resident CTAs per SM (gemm_tc_kernel<T, 2>)
 inline int gemm_stage_bytes(int bn, int bm2 = 0) { return (bm2 ? 2 : 1) * kGemmBM * kGemmBK * 2 + bn * kGemmBK * 2; }
-inline int gemm_num_stages(int bn, int bm2 = 0, int occ2 = 0) {
-    int s = (occ2 ? kGemmSmemBudget2 : kGemmSmemBudget) / gemm_stage_bytes(bn, bm2);
+inline int gemm_num_stages(int bn, int bm2 = 0) {
+    int s = kGemmSmemBudget / gemm_stage_bytes(bn, bm2);
     return s > kGemmMaxStages ? kGemmMaxStages : s;
 }
-inline int gemm_smem_bytes(int bn, int bm2 = 0, int occ2 = 0) { return gemm_num_stages(bn, bm2, occ2) * gemm_stage_bytes(bn, bm2) + 1024 + 256 + 1024; }
+inline int gemm_smem_bytes(int bn, int bm2 = 0) { return gemm_num_stages(bn, bm2) * gemm_stage_bytes(bn, bm2) + 1024 + 256 + 1024; }
 
 template <typename T> __device__ __forceinline__ float quick_gelu_t(float h) {
     // every intermediate is materialised in T by the reference: 1.702*x, sigmoid(.), x*(.)
@@ -174,10 +171,8 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& cx, int cbase, const uin
     }
 }
 
-// OCC = CTAs per SM the kernel is compiled for: 1 (the whole shared memory and register file: deep ring, 168
-// registers) or 2 (108 KB ring, <= 93 registers: the fill and the epilogue of one CTA overlap the mainloop of the other).
-template <typename T, int OCC = 1>
-__global__ void __launch_bounds__(kGemmThreads2, OCC)
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
     const int BN = args.bn;

@@ -295,181 +295,6 @@ __global__ void __launch_bounds__(kGemvThreads, NV == 1 ? 2 : 1) gemv_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batched GEMV, segment-stationary: NV input vectors share every weight byte.  A warp works on one 512-column
-// K segment at a time and keeps its slice of the NV staged vectors in REGISTERS as fp32 (NV x 16 values per
-// lane), so the inner loop is 16 weight conversions + NV x 16 FMAs per 32 weight bytes per lane and touches
-// no shared memory (the row-stationary loop above re-reads and re-converts x for every weight chunk and is
-// issue-bound at NV = 4: 2.5-3.7 TB/s, profiles/r01_ncu_pipelined.md).  Work items (segment, row) are dealt to the
-// 16 warps as contiguous ranges in segment-major order (a warp reloads its x registers only when its segment
-// changes).  RU rows are in flight per lane (8 x 16-byte loads); the RU x NMAT x NV partial sums of a row group are
-// reduced with one butterfly "transpose" (one value per lane pair) instead of one 5-step reduction each.
-// Per-row results are summed over the segments in a FIXED order by the epilogue thread (deterministic).
-// ---------------------------------------------------------------------------------------------
-constexpr int kGemvSeg = 512;
-
-template <typename T, int NMAT, int NV>
-__global__ void __launch_bounds__(kGemvThreads, 1) gemv_seg_kernel(const GemvArgs a, int nv_valid) {
-    static_assert(NV == 2 || NV == 4, "instantiated for 2 and 4 vectors");
-    constexpr int RU = NMAT == 1 ? 4 : 2;        // rows per group: 8 x 16-byte weight loads in flight per lane
-    constexpr int NVAL = RU * NMAT * NV;         // partial sums per group: 16 (NV = 4) or 8 (NV = 2)
-    extern __shared__ __align__(16) uint8_t gemv_smem[];
-    const int xpitch = (a.K + 7) & ~7;
-    T* xs = reinterpret_cast<T*>(gemv_smem);                                   // [NV][xpitch]
-    float* part = reinterpret_cast<float*>(gemv_smem + ((NV * xpitch * 2 + 15) & ~15));  // [NMAT][NV][rows][nseg]
-    __shared__ float red[kGemvWarps * 2];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rows_per_cta = (a.N + gridDim.x - 1) / gridDim.x;
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(a.N, r0 + rows_per_cta);
-    const int nrows = max(0, r1 - r0);
-    const int nseg = (a.K + kGemvSeg - 1) / kGemvSeg;
-    // Warp -> work mapping keeps HBM accesses sequential across the CTA: the warps of a "slab" (nsl = min(16, nseg)
-    // of them) read consecutive 1 KB segments of the same RU rows; with nseg < 16 the 16 / nsl slabs take alternate
-    // row groups, with nseg > 16 the segments are covered in passes (a warp reloads its x registers once per pass).
-    const int nsl = min(kGemvWarps, nseg), nsub = kGemvWarps / nsl;
-    const int sub = warp / nsl, wseg = warp % nsl;
-    const bool w_active = sub < nsub;
-    const int npass = (nseg + nsl - 1) / nsl, ngroups = (nrows + RU - 1) / RU;
-    const T* W0 = reinterpret_cast<const T*>(a.W0);
-    const T* W1 = reinterpret_cast<const T*>(a.W1);
-
-    uint4 wbuf[RU][NMAT][2];
-    auto issue = [&](int seg, int g) {       // loads of row group g of segment seg
-        const int row = r0 + g * RU;
-        const int k0 = seg * kGemvSeg + lane * 8;
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-            if (g * RU + r < nrows) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int k = k0 + c * 256;
-                    if (k < a.K) {
-                        wbuf[r][0][c] = ldg_stream(W0 + static_cast<size_t>(row + r) * a.K + k);
-                        if (NMAT == 2) wbuf[r][1][c] = ldg_stream(W1 + static_cast<size_t>(row + r) * a.K + k);
-                    }
-                }
-            }
-        }
-    };
-    // iteration state: (pass, group); a warp whose segment of the pass is beyond nseg skips the pass
-    int pass = 0, g = sub;
-    auto normalise = [&]() {                 // move (pass, g) to the next existing work item, false when done
-        while (pass < npass) {
-            if (pass * nsl + wseg < nseg && g < ngroups) return true;
-            ++pass; g = sub;
-        }
-        return false;
-    };
-    pdl_trigger();
-    bool have = w_active && normalise();
-    if (have) issue(pass * nsl + wseg, g);   // weights never depend on the previous kernel
-    pdl_wait();
-
-#pragma unroll 1
-    for (int v = 0; v < NV; ++v) gemv_stage_vector<T>(a, min(v, nv_valid - 1), xs + v * xpitch, red);
-    __syncthreads();
-
-    float xr[NV][2][8];
-    int cur_seg = -1;
-    while (have) {
-        const int seg = pass * nsl + wseg;
-        const int ngrp = min(RU, nrows - g * RU);
-        if (seg != cur_seg) {        // this warp's x slice of the new segment -> registers (fp32)
-            cur_seg = seg;
-#pragma unroll
-            for (int v = 0; v < NV; ++v)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int k = seg * kGemvSeg + c * 256 + lane * 8;
-                    if (k < a.K) {
-                        const uint4 xv = *reinterpret_cast<const uint4*>(xs + v * xpitch + k);
-                        const float2 f0 = Cvt<T>::unpack2(xv.x), f1 = Cvt<T>::unpack2(xv.y), f2 = Cvt<T>::unpack2(xv.z), f3 = Cvt<T>::unpack2(xv.w);
-                        xr[v][c][0] = f0.x; xr[v][c][1] = f0.y; xr[v][c][2] = f1.x; xr[v][c][3] = f1.y;
-                        xr[v][c][4] = f2.x; xr[v][c][5] = f2.y; xr[v][c][6] = f3.x; xr[v][c][7] = f3.y;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) xr[v][c][j] = 0.f;
-                    }
-                }
-        }
-        // ---- consume the group in flight
-        float val[NVAL];
-#pragma unroll
-        for (int q = 0; q < NVAL; ++q) val[q] = 0.f;
-        const int kq = seg * kGemvSeg + lane * 8;
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-            if (r < ngrp) {
-#pragma unroll
-                for (int m = 0; m < NMAT; ++m)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (kq + c * 256 < a.K) {
-                            const uint4 w = wbuf[r][m][c];
-                            const float2 w0 = Cvt<T>::unpack2(w.x), w1 = Cvt<T>::unpack2(w.y), w2 = Cvt<T>::unpack2(w.z), w3 = Cvt<T>::unpack2(w.w);
-#pragma unroll
-                            for (int v = 0; v < NV; ++v) {
-                                float t = val[(r * NMAT + m) * NV + v];
-                                t = fmaf(w0.x, xr[v][c][0], t); t = fmaf(w0.y, xr[v][c][1], t);
-                                t = fmaf(w1.x, xr[v][c][2], t); t = fmaf(w1.y, xr[v][c][3], t);
-                                t = fmaf(w2.x, xr[v][c][4], t); t = fmaf(w2.y, xr[v][c][5], t);
-                                t = fmaf(w3.x, xr[v][c][6], t); t = fmaf(w3.y, xr[v][c][7], t);
-                                val[(r * NMAT + m) * NV + v] = t;
-                            }
-                        }
-                    }
-            }
-        }
-        const int g_done = g;
-        g += nsub;
-        have = normalise();
-        if (have) issue(pass * nsl + wseg, g);   // next group's loads fly during the reduction
-        // ---- butterfly transpose-reduce: after the steps lane l holds the sum of value index
-        //      idx(l) = bits of l above bit 0 (MSB first) over NVAL values; lanes l and l^1 hold the same value
-#pragma unroll
-        for (int h = NVAL / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int q = 0; q < h; ++q) {
-                const float keep = up ? val[q + h] : val[q];
-                const float send = up ? val[q] : val[q + h];
-                val[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-        }
-        float total = val[0];
-        if (NVAL == 16) {
-            total += __shfl_xor_sync(0xffffffffu, total, 1);
-        } else {   // NVAL == 8: steps used offsets 16, 8, 4 -> reduce over offsets 2 and 1
-            total += __shfl_xor_sync(0xffffffffu, total, 2);
-            total += __shfl_xor_sync(0xffffffffu, total, 1);
-        }
-        const int idx = NVAL == 16 ? (lane >> 1) : (lane >> 2);          // value index held by this lane
-        const bool writer = NVAL == 16 ? (lane & 1) == 0 : (lane & 3) == 0;
-        const int r = idx / (NMAT * NV), m = (idx / NV) % NMAT, v = idx % NV;
-        if (writer && r < ngrp) {
-            const int row = g_done * RU + r;
-            part[((m * NV + v) * nrows + row) * nseg + seg] = total;
-        }
-    }
-    __syncthreads();
-
-    // ---- epilogue: one thread per row, fixed-order sum of the K-segment partials
-    for (int r = threadIdx.x; r < nrows; r += kGemvThreads) {
-        const int n = r0 + r;
-#pragma unroll 1
-        for (int v = 0; v < nv_valid; ++v) {       // vectors in order: the Mamba conv window rolls once per frame
-            float acc = 0.f, accb = 0.f;
-            for (int sg = 0; sg < nseg; ++sg) {
-                acc += part[((0 * NV + v) * nrows + r) * nseg + sg];
-                if (NMAT == 2) accb += part[((1 * NV + v) * nrows + r) * nseg + sg];
-            }
-            gemv_finish_row<T, NMAT>(a, n, v, acc, accb);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Mamba-1 single-step selective scan fused with dt_proj (K = dt_rank is one 16-byte chunk per lane
 // for dt_rank = 256): one warp per channel d.
 //   dt = softplus(T(W_dt[d,:] . xdb[:R]) + b_dt[d]);  h[d,n] = h[d,n]*exp(dt*A[d,n]) + dt*B[n]*x[d]

@@ -351,159 +351,6 @@ __global__ void rope_append_kernel(T* __restrict__ qkv, T* __restrict__ kc, T* _
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Decode attention (one query token), split over the KV length: grid (splits, Hk).  Each CTA handles
-// the `group` query heads of one kv head over its KV slice (K/V read once per group), writes
-// un-normalised partial (m, l, o[D]) per head; the combine kernel merges splits in fixed order.
-// ------------------------------------------------------------------------------------------
-template <typename T, int D>
-__global__ void __launch_bounds__(128) decode_attn_partial_kernel(const T* __restrict__ qkv, const T* __restrict__ kc,
-                                                                  const T* __restrict__ vc, float* __restrict__ part,
-                                                                  int Hq, int Hk, int max_ctx, const int* kv_len_ptr,
-                                                                  int kv_len_host, float scale_log2e) {
-    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
-    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
-    // 4 warps; each warp owns keys kbeg + warp, +4, ...; lane owns D/32 dims.  group <= 8.
-    constexpr int VPL = D / 32;
-    const int kv_len = kv_len_ptr ? (*kv_len_ptr + 1) : kv_len_host;  // device counter holds the position of the new token
-    const int nsplit = gridDim.x, split = blockIdx.x, hk = blockIdx.y;
-    const int group = Hq / Hk;
-    const int per = (kv_len + nsplit - 1) / nsplit;
-    const int kbeg = split * per, kend = min(kv_len, kbeg + per);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ float sm_m[4][8], sm_l[4][8];
-    __shared__ float sm_o[4][8][D];
-    float q[8][VPL];
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-#pragma unroll
-        for (int i = 0; i < VPL; ++i)
-            q[g][i] = g < group ? Cvt<T>::to_f(qkv[(hk * group + g) * D + lane * VPL + i]) : 0.f;
-    float m[8], l[8], o[8][VPL];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        m[g] = -INFINITY;
-        l[g] = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) o[g][i] = 0.f;
-    }
-    const T* kb = kc + static_cast<long long>(hk) * max_ctx * D;
-    const T* vb = vc + static_cast<long long>(hk) * max_ctx * D;
-    for (int key = kbeg + warp; key < kend; key += 4) {
-        float kv[VPL], vv[VPL];
-        if constexpr (VPL == 4) {
-            const uint2 ku = *reinterpret_cast<const uint2*>(kb + static_cast<long long>(key) * D + lane * 4);
-            const uint2 vu = *reinterpret_cast<const uint2*>(vb + static_cast<long long>(key) * D + lane * 4);
-            float2 a = Cvt<T>::unpack2(ku.x), b = Cvt<T>::unpack2(ku.y);
-            kv[0] = a.x; kv[1] = a.y; kv[2] = b.x; kv[3] = b.y;
-            a = Cvt<T>::unpack2(vu.x); b = Cvt<T>::unpack2(vu.y);
-            vv[0] = a.x; vv[1] = a.y; vv[2] = b.x; vv[3] = b.y;
-        } else {
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                kv[i] = Cvt<T>::to_f(kb[static_cast<long long>(key) * D + lane * VPL + i]);
-                vv[i] = Cvt<T>::to_f(vb[static_cast<long long>(key) * D + lane * VPL + i]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g < group) {
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) s = fmaf(q[g][i], kv[i], s);
-                s = warp_sum(s) * scale_log2e;
-                const float mn = fmaxf(m[g], s);
-                const float c = exp2f(m[g] - mn);
-                // P is rounded to T before it multiplies V, as in the fused reference kernels
-                const float p = rnd<T>(exp2f(s - mn));
-                l[g] = l[g] * c + p;
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(p, vv[i], o[g][i] * c);
-                m[g] = mn;
-            }
-        }
-    }
-    // merge the 4 warps (fixed order)
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        if (g < group) {
-            if (lane == 0) { sm_m[warp][g] = m[g]; sm_l[warp][g] = l[g]; }
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) sm_o[warp][g][lane * VPL + i] = o[g][i];
-        }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < group * D; idx += blockDim.x) {
-        const int g = idx / D, d = idx % D;
-        float mm = -INFINITY;
-        for (int w = 0; w < 4; ++w) mm = fmaxf(mm, sm_m[w][g]);
-        float ll = 0.f, oo = 0.f;
-        for (int w = 0; w < 4; ++w) {
-            const float c = sm_m[w][g] == -INFINITY ? 0.f : exp2f(sm_m[w][g] - mm);
-            ll += sm_l[w][g] * c;
-            oo += sm_o[w][g][d] * c;
-        }
-        float* dst = part + ((static_cast<long long>(hk * group + g) * nsplit + split) * (D + 2));
-        dst[2 + d] = oo;
-        if (d == 0) { dst[0] = mm; dst[1] = ll; }
-    }
-}
-
-template <typename T, int D>
-__global__ void decode_attn_combine_kernel(const float* __restrict__ part, T* __restrict__ out, int nsplit) {
-    pdl_trigger();   // programmatic dependent launch: the next kernel may start its prologue now ...
-    pdl_wait();      // ... and this one touches its predecessor's outputs only from here on
-    const int h = blockIdx.x, d = threadIdx.x;
-    const float* p = part + static_cast<long long>(h) * nsplit * (D + 2);
-    float mm = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, p[s * (D + 2)]);
-    float ll = 0.f, oo = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float ms = p[s * (D + 2)];
-        const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
-        ll += p[s * (D + 2) + 1] * c;
-        oo += p[s * (D + 2) + 2 + d] * c;
-    }
-    out[h * D + d] = Cvt<T>::from_f(oo / ll);
-}
-
-// argmax over fp32 logits (first index wins ties, like torch.argmax), single CTA; writes the token,
-// appends it to the output list and bumps the device-side position counter used by graph replays.
-__global__ void argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ token_out,
-                              int* __restrict__ out_list, int* __restrict__ n_out, int* __restrict__ pos_counter,
-                              const int* __restrict__ stop /* [0] = count, then ids */, int* __restrict__ done_flag) {
-    __shared__ float sv[32];
-    __shared__ int si[32];
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = logits[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int w = 1; w < nw; ++w)
-            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-        const bool already_done = done_flag && *done_flag;
-        if (!already_done) {
-            *token_out = bi;
-            if (out_list && n_out) { out_list[*n_out] = bi; *n_out += 1; }
-            if (pos_counter) *pos_counter += 1;
-            const int n_stop = stop ? stop[0] : 0;
-            for (int s = 0; s < n_stop; ++s)
-                if (stop[1 + s] == bi && done_flag) *done_flag = 1;
-        }
-    }
-}
-
 // rows[i, :] = table[ids[i], :]   (embed_tokens); ids may come from the device (decode loop)
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,

@@ -59,6 +59,7 @@ class EngineConfig:
     llm_eps: float = 1e-5
     llm_rope_theta: float = 1e6
     use_graphs: bool = True
+    n_streams: int = 1          # video streams per handle (multi-stream batching of the LLM decode)
 
     def to_c(self) -> _lib.SmConfig:
         c = _lib.SmConfig()
@@ -139,7 +140,12 @@ class Engine:
         self._check(self.lib.sm_finalize_weights(self._h))
 
     def reset_stream(self):
-        self._check(self.lib.sm_stream_reset(self._h))
+        """Zero the selected stream's Mamba state and KV length (ordered on the current CUDA stream)."""
+        self._check(self.lib.sm_stream_reset(self._h, self._stream()))
+
+    def select_stream(self, stream_id: int):
+        """Multi-stream handles: the stream the single-stream calls act on (sm_stream_select)."""
+        self._check(self.lib.sm_stream_select(self._h, int(stream_id)))
 
     # ------------------------------------------------------------------ frame preprocessing (SURVEY.md 8f-2)
     def preprocess_frames(self, frames, image_mean=OPENAI_CLIP_MEAN, image_std=OPENAI_CLIP_STD) -> torch.Tensor:
@@ -264,6 +270,31 @@ class Engine:
         stops = (C.c_int32 * max(1, len(stop_ids)))(*stop_ids)
         self._check(self.lib.sm_llm_decode(self._h, max_new, stops, len(stop_ids), out, C.byref(n), self._stream()))
         return list(out[: n.value])
+
+    def llm_decode_multi(self, stream_ids: Sequence[int], max_new: Sequence[int], stop_ids: Sequence[int] = ()) -> List[List[int]]:
+        """Greedy-decode several prefilled streams of the handle together: one pass over the LLM weights per step
+        serves every listed stream (sm_llm_decode_multi).  Returns the new ids per stream."""
+        n = len(stream_ids)
+        stride = max(int(m) for m in max_new)
+        out = (C.c_int32 * (n * stride))()
+        nout = (C.c_int32 * n)()
+        sids = (C.c_int * n)(*[int(s) for s in stream_ids])
+        mx = (C.c_int * n)(*[int(m) for m in max_new])
+        stops = (C.c_int32 * max(1, len(stop_ids)))(*stop_ids)
+        self._check(self.lib.sm_llm_decode_multi(self._h, n, sids, mx, stops, len(stop_ids), out, stride, nout, self._stream()))
+        return [list(out[i * stride: i * stride + nout[i]]) for i in range(n)]
+
+    def last_decode_logits(self, lane: int = 0) -> torch.Tensor:
+        """fp32 logits [vocab] of the last decode step of `lane` (test hook, sm_debug_decode_logits)."""
+        out = torch.empty(self.cfg.llm_vocab, dtype=torch.float32, device=self.device)
+        self._check(self.lib.sm_debug_decode_logits(self._h, lane, out.data_ptr(), self._stream()))
+        return out
+
+    def decode_stats(self, reset: bool = True) -> Dict[str, float]:
+        """Device time of the decode-step launches since the last reset (sm_decode_stats)."""
+        ms, steps, toks, ctx = C.c_double(0), C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self._check(self.lib.sm_decode_stats(self._h, C.byref(ms), C.byref(steps), C.byref(toks), C.byref(ctx), 1 if reset else 0))
+        return {"ms": ms.value, "steps": steps.value, "tokens": toks.value, "ctx_sum": ctx.value}
 
     @property
     def kv_len(self) -> int:

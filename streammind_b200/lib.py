@@ -26,7 +26,7 @@ class SmConfig(C.Structure):
         ("llm_hidden", C.c_int), ("llm_layers", C.c_int), ("llm_heads", C.c_int), ("llm_kv_heads", C.c_int),
         ("llm_head_dim", C.c_int), ("llm_ffn", C.c_int), ("llm_vocab", C.c_int), ("llm_max_ctx", C.c_int),
         ("llm_eps", C.c_float), ("llm_rope_theta", C.c_float),
-        ("use_graphs", C.c_int),
+        ("use_graphs", C.c_int), ("n_streams", C.c_int),
     ]
 
 
@@ -38,7 +38,9 @@ SYMBOLS = {
     "sm_last_error": (C.c_char_p, [_VP]),
     "sm_load_weight": (_I, [_VP, C.c_char_p, _VP, _I, _I, _I, C.POINTER(C.c_int64)]),
     "sm_finalize_weights": (_I, [_VP]),
-    "sm_stream_reset": (_I, [_VP]),
+    "sm_stream_reset": (_I, [_VP, _VP]),
+    "sm_stream_select": (_I, [_VP, _I]),
+    "sm_num_streams": (_I, [_VP]),
     "sm_vit_encode": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "sm_pool_features": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_projector_step": (_I, [_VP, _VP, _I, _VP, _VP]),
@@ -49,6 +51,11 @@ SYMBOLS = {
     "sm_embed_tokens": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_prefill": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_decode": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),
+    "sm_llm_decode_multi": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP]),
+    "sm_decode_stats": (_I, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _I]),
+    "sm_debug_decode_logits": (_I, [_VP, _I, _VP, _VP]),
+    "sm_debug_decode_buffer": (_I, [_VP, _I, _VP, _LL, _VP]),
+    "sm_debug_decode_phases": (_I, [_VP, _VP]),
     "sm_kv_len": (_I, [_VP]),
     "sm_kv_set_len": (_I, [_VP, _I]),
     "sm_test_gemm": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
@@ -61,7 +68,6 @@ SYMBOLS = {
     "sm_debug_attention_mode": (_I, [_VP, _I]),
     "sm_resample_table": (_I, [_I, _I, C.POINTER(C.c_int), _VP, _VP, _LL]),
     "sm_preprocess_frames": (_I, [_VP, _VP, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), _VP, _VP]),
-    "sm_debug_mega_trace": (_I, [_VP, _VP, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I]),
     "sm_launch_count": (_LL, [_VP, _I]),
 }
 
