@@ -129,6 +129,13 @@ int sm_gate_score(sm_handle* h, const void* tok, float* logits_out, void* stream
 int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, void* feats_out, void* toks_out,
                   float* logits_out, float* logits_host, void* stream);
 
+/* sm_frame_step for n DIFFERENT streams at once (multi-stream batching): frame i belongs to stream slot
+ * first_stream + i.  One tower batch, then every pass over the projector weights serves <= 4 streams (each with its own
+ * Mamba conv / ssm state) and every pass over the gate weights serves all n frames.  n <= max_frames.  Outputs as in
+ * sm_frame_step (row i = stream first_stream + i); results equal n separate sm_frame_step calls on the selected streams. */
+int sm_frame_step_multi(sm_handle* h, const void* pixels, int pixels_on_host, int n, int first_stream, void* toks_out,
+                        float* logits_out, float* logits_host, void* stream);
+
 /* Pipelined form of sm_frame_step for throughput streams.  The vision tower of the call runs on an internal
  * high-priority stream; projector + gate run on a second internal low-priority stream, so the gate of frame t
  * overlaps the tower of frame t+1 (the tower is tensor/latency-bound and leaves HBM mostly idle, the gate is

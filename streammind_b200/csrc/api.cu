@@ -674,7 +674,9 @@ int run_vit(sm_handle* h, const void* pixels, int B, void* feats_out, void* pool
 // sequential pieces (conv window in the in_proj epilogue, SSM state in the scan kernel) walk the frames in order.
 constexpr int kGemvBatch = 4;
 
-int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaStream_t st) {
+// multi = true: the nv frames belong to the nv consecutive stream slots starting at h->cur (one frame each) instead of being
+// nv consecutive frames of stream h->cur
+int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaStream_t st, bool multi = false) {
     const sm_config& c = h->cfg;
     const int Dm = c.proj_d_model, Di = h->d_inner, R = h->dt_rank, N = c.proj_d_state, C = c.vit_hidden;
     const int nxp = (R + 2 * N + 7) & ~7;
@@ -689,6 +691,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaS
     a.nw = h->pj_norm_w; a.nb = h->pj_norm_b; a.eps = c.proj_eps;
     a.conv_state = static_cast<char*>(h->pj_conv_state) + static_cast<size_t>(h->cur) * Di * c.proj_d_conv * h->esz; a.conv_w = h->pj_conv_w; a.conv_b = h->pj_conv_b; a.z_out = h->pj_z;
     a.d_inner = Di; a.d_conv = c.proj_d_conv;
+    a.conv_state_stride = multi ? static_cast<long long>(Di) * c.proj_d_conv : 0;
     batched(a, Dm, Di, 0, Di);
     if (launch_gemv(h, a, 1, st)) return 1;
     a = gv(h->pj_xproj, R + 2 * N, Di, PRO_PLAIN, h->pj_xc, GEPI_STORE, h->pj_xdb);
@@ -698,6 +701,7 @@ int run_projector(sm_handle* h, const void* pooled, void* tok_out, int nv, cudaS
     s.W_dt = h->pj_dt_w; s.b_dt = h->pj_dt_b; s.A_log = h->pj_alog; s.D = h->pj_D; s.xdb = h->pj_xdb; s.x = h->pj_xc;
     s.z = h->pj_z; s.state = h->pj_ssm_state + static_cast<size_t>(h->cur) * Di * N; s.y = h->pj_y; s.d_inner = Di; s.dt_rank = R; s.d_state = N;
     s.nv = nv; s.xdb_stride = nxp; s.x_stride = Di; s.z_stride = Di; s.y_stride = Di;
+    s.state_stride = multi ? static_cast<long long>(Di) * N : 0;
     const int scan_smem = (nv * nxp * 2 + 15) & ~15;
     DISPATCH_T(h, T, {
         ProfScope ps_kc_mamba_scan(h, KC_MAMBA_SCAN, st);
@@ -1735,6 +1739,44 @@ int sm_frame_step(sm_handle* h, const void* pixels, int pixels_on_host, int B, v
     if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(B) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, st));
     if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int sm_frame_step_multi(sm_handle* h, const void* pixels, int pixels_on_host, int n, int first_stream, void* toks_out,
+                        float* logits_out, float* logits_host, void* stream) {
+    if (!h || h->cfg.vit_layers <= 0 || h->cfg.proj_d_model <= 0 || h->cfg.gate_layers <= 0)
+        return fail(h, "sm_frame_step_multi: needs vision tower + projector + gate");
+    if (n < 1 || n > h->cfg.max_frames) return fail(h, "sm_frame_step_multi: n=%d outside [1, max_frames=%d]", n, h->cfg.max_frames);
+    if (first_stream < 0 || first_stream + n > h->n_streams) return fail(h, "sm_frame_step_multi: streams [%d, %d) outside [0, %d)", first_stream, first_stream + n, h->n_streams);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pipe_join(h, st)) return 1;
+    const sm_config& c = h->cfg;
+    const size_t px_bytes = static_cast<size_t>(n) * 3 * c.vit_image * c.vit_image * h->esz;
+    CUDA_OK(h, cudaMemcpyAsync(h->ws_pixels, pixels, px_bytes, pixels_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    if (run_vit(h, h->ws_pixels, n, nullptr, h->ws_pooled, st)) return 1;
+    const int saved = h->cur;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; i += kGemvBatch) {          // <= 4 streams share each pass over the projector weights
+        const int nv = std::min(kGemvBatch, n - i);
+        h->cur = first_stream + i;
+        rc = run_projector(h, static_cast<const char*>(h->ws_pooled) + static_cast<size_t>(i) * c.vit_hidden * h->esz,
+                           static_cast<char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz, nv, st, true);
+    }
+    h->cur = saved;
+    if (rc) return 1;
+    // the gate is stateless: the n frames are n rows of one weight pass (GEMMs from 5 rows on, else the batched GEMV chain)
+    static const int gemm_min = getenv("SMB_GATE_GEMM") ? atoi(getenv("SMB_GATE_GEMM")) : 5;
+    if (gemm_min > 0 && n >= gemm_min && n <= h->gate_gemm_cap) {
+        if (run_gate_gemm(h, h->pj_toks, h->gt_logits, n, st)) return 1;
+    } else {
+        for (int i = 0; i < n; i += kGemvBatch)
+            if (run_gate(h, static_cast<const char*>(h->pj_toks) + static_cast<size_t>(i) * c.proj_d_model * h->esz, h->gt_logits + 2 * i,
+                         std::min(kGemvBatch, n - i), st)) return 1;
+    }
+    if (toks_out) CUDA_OK(h, cudaMemcpyAsync(toks_out, h->pj_toks, static_cast<size_t>(n) * c.proj_d_model * h->esz, cudaMemcpyDeviceToDevice, st));
+    if (logits_out) CUDA_OK(h, cudaMemcpyAsync(logits_out, h->gt_logits, static_cast<size_t>(n) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (logits_host) CUDA_OK(h, cudaMemcpyAsync(logits_host, h->gt_logits, static_cast<size_t>(n) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return 0;
 }
 

@@ -57,6 +57,8 @@ struct GemvArgs {
     // flight): every weight byte is streamed once for NV frames.  Element strides between the vectors:
     long long x_stride, y_stride, resid_stride, z_stride;
     int nv_host;   // host-side copy of NV (selects the template instance)
+    long long conv_state_stride;   // GEPI_MAMBA_CONV: elements between the conv windows of the NV vectors (0: consecutive frames of ONE
+                                   // stream walk one window in order; > 0: the vectors are frames of different streams)
 };
 
 #ifndef SMB_GEMV_UNR1
@@ -174,7 +176,7 @@ __device__ __forceinline__ void gemv_finish_row(const GemvArgs& a, int n, int v,
             if (n < a.d_inner) {
                 // Mamba causal depth-wise conv as a rolling window (mamba_simple.py:215-221); the
                 // reference's full-sequence conv1d materialises T(conv + bias) before SiLU (:168-169)
-                T* st = reinterpret_cast<T*>(a.conv_state) + static_cast<size_t>(n) * a.d_conv;
+                T* st = reinterpret_cast<T*>(a.conv_state) + v * a.conv_state_stride + static_cast<size_t>(n) * a.d_conv;
                 const T* cw = reinterpret_cast<const T*>(a.conv_w) + static_cast<size_t>(n) * a.d_conv;
                 const float xn = rnd<T>(acc);
                 float c = 0.f;
@@ -314,6 +316,8 @@ struct ScanArgs {
     int d_inner, dt_rank, d_state;
     int nv;             // consecutive frames processed in order (xdb / x / z / y strided per frame)
     long long xdb_stride, x_stride, z_stride, y_stride;
+    long long state_stride;   // 0: the nv frames belong to one stream (state carried in a register); > 0: floats between the states
+                              // of the nv streams the frames belong to (multi-stream batching)
 };
 
 template <typename T>
@@ -341,6 +345,10 @@ __global__ void __launch_bounds__(256) mamba_scan_step_kernel(const ScanArgs a) 
         float hst = has_n ? *sp : 0.f;
         const float A = has_n ? -__expf(Cvt<T>::to_f(reinterpret_cast<const T*>(a.A_log)[static_cast<size_t>(d) * a.d_state + lane])) : 0.f;
         for (int v = 0; v < nv; ++v) {
+            if (a.state_stride != 0) {          // frame v belongs to its own stream: swap the state in and out
+                if (v > 0 && has_n) sp[(v - 1) * a.state_stride] = hst;
+                hst = has_n ? sp[v * a.state_stride] : 0.f;
+            }
             const T* xv_db = xdb + v * nxp;
             float acc = 0.f;
             for (int k = lane * 8; k < a.dt_rank; k += 256) {
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(256) mamba_scan_step_kernel(const ScanArgs a) 
                 reinterpret_cast<T*>(a.y)[v * a.y_stride + d] = Cvt<T>::from_f(yv);
             }
         }
-        if (has_n) *sp = hst;
+        if (has_n) sp[a.state_stride != 0 ? (nv - 1) * a.state_stride : 0] = hst;
     }
 }
 

@@ -88,6 +88,10 @@ class Engine:
             raise RuntimeError(self.lib.sm_last_error(None).decode())
         self._pinned_logits = torch.empty(cfg.max_frames, 2, dtype=torch.float32).pin_memory()
         self._pinned_ring = torch.empty(16, cfg.max_frames, 2, dtype=torch.float32).pin_memory()   # frame_submit tickets (kTicketRing)
+        # Buffers of the tickets in flight: the library reads `pixels` and writes the outputs on its internal streams after
+        # frame_submit has returned, so they must outlive the call.  One entry per ring slot, released when the slot is
+        # re-used (the library blocks on the old ticket first) -- the caller may drop or re-bind its tensors immediately.
+        self._ring_refs = [None] * 16
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int):
@@ -222,6 +226,23 @@ class Engine:
             self._pinned_logits.data_ptr(), self._stream()))
         return feats, toks, logits, self._pinned_logits[:B]
 
+    def frame_step_multi(self, pixels: torch.Tensor, first_stream: int = 0):
+        """One frame of each of ``pixels.shape[0]`` consecutive stream slots (sm_frame_step_multi): -> (toks [n, d_model],
+        logits_device [n, 2], logits_pinned_host [n, 2]); the host logits are valid after the current stream is synchronised."""
+        c = self.cfg
+        if pixels.dtype != c.dtype:
+            raise RuntimeError(f"pixels: expected dtype {c.dtype}, got {pixels.dtype}")
+        on_host = 0 if pixels.is_cuda else 1
+        if on_host and not pixels.is_pinned():
+            raise RuntimeError("pixels: host tensors must be pinned")
+        px = pixels.contiguous()
+        n = px.shape[0]
+        toks = torch.empty(n, c.proj_d_model, dtype=c.dtype, device=self.device)
+        logits = torch.empty(n, 2, dtype=torch.float32, device=self.device)
+        self._check(self.lib.sm_frame_step_multi(self._h, px.data_ptr(), on_host, n, int(first_stream), toks.data_ptr(),
+                                                 logits.data_ptr(), self._pinned_logits.data_ptr(), self._stream()))
+        return toks, logits, self._pinned_logits[:n]
+
     def frame_submit(self, pixels: torch.Tensor, want_feats: bool = False, want_device_outputs: bool = False):
         """Pipelined frame_step (sm_frame_submit): returns (ticket, feats|None, toks|None, logits_device|None,
         logits_pinned_host).  Nothing is ordered on the current stream: call ``frame_wait(ticket)`` before using
@@ -245,6 +266,7 @@ class Engine:
             toks.data_ptr() if toks is not None else None, logits.data_ptr() if logits is not None else None,
             host.data_ptr(), self._stream(), C.byref(tk)))
         self._next_ticket = tk.value + 1
+        self._ring_refs[tk.value % 16] = (px, feats, toks, logits)
         return tk.value, feats, toks, logits, host[:B]
 
     def frame_wait(self, ticket: int, block: bool = True, on_stream: bool = True):
@@ -252,6 +274,9 @@ class Engine:
         self._check(self.lib.sm_frame_wait(self._h, ticket, self._stream() if on_stream else None, 1 if block else 0))
 
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.cfg.llm_vocab):
+            # the reference's nn.Embedding raises IndexError here (e.g. an unexpanded <image> = -200 sentinel)
+            raise ValueError(f"token ids must lie in [0, {self.cfg.llm_vocab}), got [{int(ids.min())}, {int(ids.max())}]")
         ids32 = ids.to(device=self.device, dtype=torch.int32).contiguous()
         out = torch.empty(ids32.numel(), self.cfg.llm_hidden, dtype=self.cfg.dtype, device=self.device)
         self._check(self.lib.sm_embed_tokens(self._h, ids32.data_ptr(), ids32.numel(), out.data_ptr(), self._stream()))
@@ -342,7 +367,7 @@ class Engine:
         return out
 
     def test_attention(self, qkv: torch.Tensor, B: int, S: int, H: int, D: int, mode: int = -1) -> torch.Tensor:
-        """mode: -1 default kernel choice, 0 mma.sync kernel, 2 / 3 tcgen05 kernels (sm_debug_attention_mode)."""
+        """mode: -1 default kernel choice, 0 mma.sync kernel, 2 tcgen05 kernel (sm_debug_attention_mode)."""
         self._check(self.lib.sm_debug_attention_mode(self._h, mode))
         out = torch.empty(B * S, H * D, dtype=qkv.dtype, device=qkv.device)
         self._check(self.lib.sm_test_attention(self._h, qkv.data_ptr(), out.data_ptr(), B, S, H, D, self._stream()))

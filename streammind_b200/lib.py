@@ -46,6 +46,7 @@ SYMBOLS = {
     "sm_projector_step": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_gate_score": (_I, [_VP, _VP, _VP, _VP]),
     "sm_frame_step": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "sm_frame_step_multi": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "sm_frame_submit": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_longlong)]),
     "sm_frame_wait": (_I, [_VP, _LL, _VP, _I]),
     "sm_embed_tokens": (_I, [_VP, _VP, _I, _VP, _VP]),

@@ -15,6 +15,8 @@ videollama2_mistral.py:413,426-431).
 """
 from __future__ import annotations
 
+from collections import deque
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -164,13 +166,28 @@ class VideoMambaSeq:
 # --------------------------------------------------------------------------------------------------
 # B1: model API
 # --------------------------------------------------------------------------------------------------
+@dataclass
+class KVToken:
+    """Stand-in for hf ``past_key_values``: the cache itself stays on the device inside the handle."""
+    owner: object
+    length: int
+
+
+@dataclass
+class CausalLMOutput:
+    """The fields of hf ``CausalLMOutputWithPast`` that generation consumes."""
+    logits: torch.Tensor
+    past_key_values: Optional[KVToken] = None
+    loss: Optional[torch.Tensor] = None
+
+
 class StreamMindB200ForCausalLM:
     """Drop-in for the calls the streaming demo / serve worker make on ``Videollama2MistralForCausalLM``."""
 
     def __init__(self, cfg: EngineConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
-                 keep_frame_features: bool = False):
+                 keep_frame_features: bool = False, engine: Optional[Engine] = None, stream_id: int = 0):
         self.config = cfg
-        self.engine = Engine(cfg, device=device)
+        self.engine = engine if engine is not None else Engine(cfg, device=device)     # several stream objects may share one engine
         if state_dict is not None:
             self.load_state_dict(state_dict)
         self.vision_tower = CLIPVisionTower(self.engine)
@@ -179,16 +196,21 @@ class StreamMindB200ForCausalLM:
         # per-stream state, same attribute names as the reference (videollama2_mistral.py:159-162)
         self.frame_feature: Optional[torch.Tensor] = None
         self.interval_id_list: List[int] = []
-        self._tokens: Optional[torch.Tensor] = None          # [T, d_model]
+        self._tokens: List[torch.Tensor] = []                # projector tokens, chunks of [t, d_model] in frame order
         self._num_frames = 0
         self._dialogue = DialogueCache()
         self.last_prefill_len = 0
+        self._inflight = deque()                             # frames submitted ahead through the pipelined path (prefetch_frames)
+        self.stream_id = stream_id                           # stream slot of the engine this object drives (multi-stream handles)
 
     # ---- loading -------------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         self.engine.load_state_dict(sd)
         self.engine.finalize()
-        self.engine.reset_stream()
+        for s in range(self.config.n_streams):
+            self.engine.select_stream(s)
+            self.engine.reset_stream()
+        self.engine.select_stream(0)
 
     def get_vision_tower(self):
         return self.vision_tower
@@ -209,11 +231,18 @@ class StreamMindB200ForCausalLM:
 
     def reset_stream(self):
         """Start a new video (the reference never resets; one stream per model instance)."""
+        self._drain_inflight()
+        self.engine.select_stream(self.stream_id)
         self.engine.reset_stream()
         self.mm_projector.reset()
         self.frame_feature, self.interval_id_list = None, []
-        self._tokens, self._num_frames = None, 0
+        self._tokens, self._num_frames = [], 0
         self._dialogue.reset()
+
+    def _token_rows(self, idx: Sequence[int]) -> torch.Tensor:
+        toks = self._tokens[0] if len(self._tokens) == 1 else torch.cat(self._tokens, 0)
+        self._tokens = [toks]
+        return toks[torch.tensor(list(idx), device=toks.device)]
 
     # ---- per-frame path ------------------------------------------------------------------------
     def _encode_frames(self, frames: torch.Tensor):
@@ -230,7 +259,7 @@ class StreamMindB200ForCausalLM:
             if not chunk.is_cuda and not chunk.is_pinned():
                 chunk = chunk.to(e.device)
             feats, toks, _, lg_host = e.frame_step(chunk, want_feats=self.keep_frame_features)
-            self._tokens = toks if self._tokens is None else torch.cat([self._tokens, toks], 0)
+            self._tokens.append(toks)
             if self.keep_frame_features:
                 f = feats.unsqueeze(0)
                 self.frame_feature = f if self.frame_feature is None else torch.cat([self.frame_feature, f], 1)
@@ -238,6 +267,45 @@ class StreamMindB200ForCausalLM:
             last = lg_host[chunk.shape[0] - 1].clone()
         self._num_frames += frames.shape[0]
         return last
+
+    # ---- pipelined frames: encode ahead of the decisions (and under a running LLM decode) ----------------------------
+    def prefetch_frames(self, frames: torch.Tensor):
+        """Submit frames [t, 3, H, W] that LATER ``stream_generate_demo`` calls will be given, in this order, through the
+        pipelined path (sm_frame_submit: towers of 8 consecutive frames run as one chunk, projector / gate batched, up to
+        16 frames in flight on the library's own streams).  Nothing waits here.  The vision tower, projector and gate do
+        not depend on the LLM, so frames submitted before a fire are encoded WHILE its prefill + greedy decode run on the
+        caller's stream (north_star: the next frames' ViT encode overlaps the decode / KV appends); the reference does
+        the two strictly one after the other (videollama2_mistral.py:410-431).  At most 15 frames may be ahead."""
+        e = self.engine
+        if e.cfg.max_frames != 1:
+            raise RuntimeError("prefetch_frames needs a streaming engine (max_frames == 1)")
+        if frames.dim() != 4:
+            raise ValueError(f"expected frames [t, 3, H, W], got {tuple(frames.shape)}")
+        if len(self._inflight) + frames.shape[0] > 15:
+            raise RuntimeError("at most 15 frames may be submitted ahead of their stream_generate_demo calls")
+        if frames.dtype != e.cfg.dtype:
+            frames = frames.to(e.cfg.dtype)
+        e.select_stream(self.stream_id)
+        for i in range(frames.shape[0]):
+            f = frames[i:i + 1]
+            if not f.is_cuda and not f.is_pinned():
+                f = f.to(e.device)
+            tk, feats, toks, _, lg_host = e.frame_submit(f, want_feats=self.keep_frame_features, want_device_outputs=True)
+            self._inflight.append((tk, feats, toks, lg_host))
+
+    def _pop_prefetched(self):
+        tk, feats, toks, lg_host = self._inflight.popleft()
+        self.engine.frame_wait(tk, block=True, on_stream=True)       # decision on the host, tokens ordered on the current stream
+        self._tokens.append(toks)
+        if self.keep_frame_features:
+            f = feats.unsqueeze(0)
+            self.frame_feature = f if self.frame_feature is None else torch.cat([self.frame_feature, f], 1)
+        self._num_frames += 1
+        return lg_host[0].clone()
+
+    def _drain_inflight(self):
+        while self._inflight:
+            self._pop_prefetched()
 
     @torch.no_grad()
     def stream_generate_demo(self, inputs: Optional[torch.Tensor] = None, images_or_videos: Optional[torch.Tensor] = None,
@@ -252,7 +320,13 @@ class StreamMindB200ForCausalLM:
             raise NotImplementedError("`inputs_embeds` is not supported")
         if kwargs.get("do_sample", False):
             raise NotImplementedError("only greedy decoding (do_sample=False) is implemented on the device")
-        logits = self._encode_frames(images_or_videos)
+        self.engine.select_stream(self.stream_id)
+        if self._inflight:
+            if images_or_videos is not None and images_or_videos.shape[0] != 1:
+                raise ValueError("with prefetched frames every stream_generate_demo call consumes exactly one frame")
+            logits = self._pop_prefetched()
+        else:
+            logits = self._encode_frames(images_or_videos)
         self.last_gate_logits = logits
         pred = int(torch.softmax(logits, dim=0).argmax(dim=0).item()) if force_pred is None else int(force_pred)
         if pred == 0:
@@ -278,8 +352,22 @@ class StreamMindB200ForCausalLM:
         return stops
 
     def _generate_from_dialogue(self, ids: Sequence[int], kwargs) -> List[int]:
+        items = self._prefill_dialogue(ids)
+        out = self.engine.llm_decode(int(kwargs.get("max_new_tokens", 1024)), self._stop_ids(kwargs))
+        self._dialogue.commit(items, out)
+        return out
+
+    def _prefill_dialogue(self, ids: Sequence[int]) -> List[Item]:
+        """Bring this stream's KV cache up to the end of the dialogue ``ids`` (longest-common-prefix re-use); returns the
+        item sequence for ``DialogueCache.commit`` after decoding."""
         e = self.engine
+        e.select_stream(self.stream_id)
         items = expand_dialogue(ids, self.interval_id_list)
+        if len(items) > e.cfg.llm_max_ctx:
+            # checked BEFORE the cache is touched, so a too-long dialogue costs nothing and the stream state stays valid.
+            # There is no silent truncation policy: size EngineConfig.llm_max_ctx for the longest dialogue (the reference
+            # relies on Mistral's 32k positions); decoding itself never fails on a full cache, it returns what fits.
+            raise RuntimeError(f"dialogue of {len(items)} positions exceeds llm_max_ctx = {e.cfg.llm_max_ctx}")
         keep = self._dialogue.plan(items)
         if keep > e.kv_len:
             keep = e.kv_len
@@ -290,15 +378,12 @@ class StreamMindB200ForCausalLM:
         frame_pos = [i for i, (k, _) in enumerate(todo) if k == "f"]
         emb = torch.empty(len(todo), e.cfg.llm_hidden, dtype=e.cfg.dtype, device=e.device)
         if text_pos:
-            tid = torch.tensor([todo[i][1] for i in text_pos], dtype=torch.int32, device=e.device)
+            tid = torch.tensor([todo[i][1] for i in text_pos], dtype=torch.int32)
             emb[torch.tensor(text_pos, device=e.device)] = e.embed_tokens(tid)
         if frame_pos:
-            fidx = torch.tensor([todo[i][1] for i in frame_pos], device=e.device)
-            emb[torch.tensor(frame_pos, device=e.device)] = self._tokens[fidx]
+            emb[torch.tensor(frame_pos, device=e.device)] = self._token_rows([todo[i][1] for i in frame_pos])
         e.llm_prefill(emb)
-        out = e.llm_decode(int(kwargs.get("max_new_tokens", 1024)), self._stop_ids(kwargs))
-        self._dialogue.commit(items, out)
-        return out
+        return items
 
     @torch.no_grad()
     def generate(self, inputs: Optional[torch.Tensor] = None, images_or_videos: Optional[torch.Tensor] = None,
@@ -307,12 +392,144 @@ class StreamMindB200ForCausalLM:
         decode; returns new token ids [1, n]."""
         if kwargs.get("do_sample", False):
             raise NotImplementedError("only greedy decoding (do_sample=False) is implemented on the device")
-        self.reset_stream()
-        if images_or_videos is not None:
-            self._encode_frames(images_or_videos)
-            self.interval_id_list = [self._num_frames]
-        ids = inputs[0].tolist()
-        return torch.tensor([self._generate_from_dialogue(ids, kwargs)], dtype=torch.long)
+        # The reference's generate() re-encodes everything it is given and leaves the streaming attributes alone.  Here the
+        # stream state lives in the engine, so an offline call runs on a scratch stream slot when the handle has one
+        # (EngineConfig.n_streams > 1: the last slot) and the live stream is untouched; a single-slot handle has to reset
+        # its only stream -- a live stream on it is lost (documented difference).
+        saved = None
+        if self.config.n_streams > 1 and self.stream_id != self.config.n_streams - 1:
+            self._drain_inflight()
+            saved = (self.stream_id, self.frame_feature, self.interval_id_list, self._tokens, self._num_frames, self._dialogue, self.mm_projector)
+            self.stream_id = self.config.n_streams - 1
+            self._dialogue, self.mm_projector = DialogueCache(), VideoMambaSeq(self.engine)
+        try:
+            self.reset_stream()
+            if images_or_videos is not None:
+                self._encode_frames(images_or_videos)
+                self.interval_id_list = [self._num_frames]
+            ids = inputs[0].tolist()
+            out = torch.tensor([self._generate_from_dialogue(ids, kwargs)], dtype=torch.long)
+        finally:
+            if saved is not None:
+                (self.stream_id, self.frame_feature, self.interval_id_list, self._tokens, self._num_frames, self._dialogue, self.mm_projector) = saved
+                self.engine.select_stream(self.stream_id)
+        return out
+
+    @torch.no_grad()
+    def forward(self, input_ids: Optional[torch.Tensor] = None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds: Optional[torch.Tensor] = None, labels=None, use_cache: Optional[bool] = None,
+                output_attentions=None, output_hidden_states=None, images=None, return_dict=None, **kwargs):
+        """``Videollama2MistralForCausalLM.forward`` for inference (videollama2_mistral.py:173-259 -> hf
+        MistralForCausalLM.forward): appends ``inputs_embeds [1, L, hidden]`` -- or ``input_ids [1, L]`` whose ``<video>``
+        sentinels are replaced by the projector tokens of ``images`` (one tensor of frames [t, 3, H, W] per sentinel) -- to
+        the KV cache and returns the fp32 logits of the LAST position as ``CausalLMOutput.logits [1, 1, vocab]`` (what
+        ``generate`` consumes) with ``past_key_values`` = an opaque token of the handle's cache.  Passing that token back
+        continues the sequence; ``past_key_values=None`` starts a new one (hf semantics).  Training arguments
+        (``labels``, ``timestamp`` ...) are outside the inference path and raise."""
+        if labels is not None or kwargs.get("timestamp") is not None:
+            raise NotImplementedError("the training / scoring forward is not on the inference hot path")
+        e = self.engine
+        e.select_stream(self.stream_id)
+        if not isinstance(past_key_values, KVToken) or past_key_values.owner is not self or past_key_values.length != e.kv_len:
+            if past_key_values is not None and not isinstance(past_key_values, KVToken):
+                raise TypeError("past_key_values must be the token returned by an earlier forward() of this model (the KV cache lives on the device)")
+            e.kv_set_len(0)
+            self._dialogue.reset()
+        if inputs_embeds is None:
+            if input_ids is None:
+                raise ValueError("forward() needs input_ids or inputs_embeds")
+            ids = input_ids[0].tolist()
+            frames = [] if images is None else (list(images) if isinstance(images, (list, tuple)) else [images])
+            frames = [f[0] if isinstance(f, (list, tuple)) else f for f in frames]       # the reference passes (tensor, modal) pairs
+            n_sent = sum(1 for t in ids if t == VIDEO_TOKEN_INDEX)
+            if n_sent != len(frames):
+                raise ValueError(f"{n_sent} <video> sentinels but {len(frames)} frame tensors")
+            rows, chunk = [], []
+            for t in ids:
+                if t == VIDEO_TOKEN_INDEX:
+                    if chunk:
+                        rows.append(e.embed_tokens(torch.tensor(chunk)))
+                        chunk = []
+                    fr = frames.pop(0).to(device=e.device, dtype=e.cfg.dtype)
+                    for i in range(0, fr.shape[0], e.cfg.max_frames):
+                        _, pooled = e.vit_encode(fr[i:i + e.cfg.max_frames], want_feats=False)
+                        rows.append(e.projector_step(pooled))
+                else:
+                    chunk.append(int(t))
+            if chunk:
+                rows.append(e.embed_tokens(torch.tensor(chunk)))
+            emb = torch.cat(rows, 0)
+        else:
+            emb = inputs_embeds[0].to(device=e.device, dtype=e.cfg.dtype)
+        if e.kv_len + emb.shape[0] > e.cfg.llm_max_ctx:
+            raise RuntimeError(f"{e.kv_len} + {emb.shape[0]} positions exceed llm_max_ctx = {e.cfg.llm_max_ctx}")
+        logits = e.llm_prefill(emb.contiguous(), want_logits=True)
+        return CausalLMOutput(logits=logits.view(1, 1, -1), past_key_values=KVToken(self, e.kv_len))
+
+    __call__ = forward
+
+
+class MultiStreamSession:
+    """B video streams on ONE engine / GPU.  Every stream keeps the per-stream state the reference stores on
+    its model object (frame tokens, ``interval_id_list``, dialogue / KV cache, Mamba state: videollama2_mistral.py:159-162) in
+    its own slot of the handle; one call advances all of them by one frame:
+
+      * one vision-tower batch for the B frames, every pass over the projector / gate weights shared (sm_frame_step_multi);
+      * the streams whose gate fired are prefilled one by one (their dialogue suffixes differ in length) and then decoded
+        TOGETHER: each pass over the 14.2 GB of LLM weights yields one token per firing stream (sm_llm_decode_multi).
+
+    Results are those of B independent ``StreamMindB200ForCausalLM`` runs (same kernels, per-stream arithmetic independent
+    of the batch: tests/test_multi_stream_gpu.py)."""
+
+    def __init__(self, cfg: EngineConfig, state_dict: Dict[str, torch.Tensor], n_streams: int, device: int = 0):
+        import dataclasses
+        cfg = dataclasses.replace(cfg, n_streams=n_streams, max_frames=max(cfg.max_frames, n_streams))
+        self.config = cfg
+        self.engine = Engine(cfg, device=device)
+        self.streams = [StreamMindB200ForCausalLM(cfg, None, device=device, engine=self.engine, stream_id=s) for s in range(n_streams)]
+        self.streams[0].load_state_dict(state_dict)
+
+    def reset(self):
+        for m in self.streams:
+            m.reset_stream()
+
+    @torch.no_grad()
+    def stream_generate_demo_multi(self, inputs: Sequence[Sequence[int]], frames: torch.Tensor, force_pred=None, **kwargs):
+        """inputs[s]: prompt ids of stream s (with ``<video>`` sentinels); frames [B, 3, H, W]: the next frame of every stream.
+        -> list of (new ids | None, pred) per stream."""
+        e, B = self.engine, len(self.streams)
+        if frames.shape[0] != B or len(inputs) != B:
+            raise ValueError(f"expected one frame and one prompt per stream ({B})")
+        if frames.dtype != e.cfg.dtype:
+            frames = frames.to(e.cfg.dtype)
+        if not frames.is_cuda and not frames.is_pinned():
+            frames = frames.to(e.device)
+        toks, _, lg_host = e.frame_step_multi(frames, first_stream=0)
+        torch.cuda.current_stream().synchronize()
+        results, firing = [None] * B, []
+        for s, m in enumerate(self.streams):
+            m._tokens.append(toks[s:s + 1])
+            m._num_frames += 1
+            m.last_gate_logits = lg_host[s].clone()
+            pred = int(torch.softmax(m.last_gate_logits, dim=0).argmax(dim=0).item()) if force_pred is None else int(force_pred[s])
+            if pred:
+                m.interval_id_list.append(m._num_frames)
+                firing.append(s)
+            else:
+                results[s] = (None, 0)
+        max_new = int(kwargs.get("max_new_tokens", 1024))
+        stops = self.streams[0]._stop_ids(kwargs)
+        for lo in range(0, len(firing), 4):                     # the decode kernel takes up to 4 streams per pass
+            group = firing[lo:lo + 4]
+            items = [self.streams[s]._prefill_dialogue(list(inputs[s])) for s in group]
+            outs = e.llm_decode_multi(group, [max_new] * len(group), stops)
+            for s, it, out in zip(group, items, outs):
+                self.streams[s]._dialogue.commit(it, out)
+                results[s] = (out, 1)
+        return results
+
+    def close(self):
+        self.engine.close()
 
 
 def infer(model: StreamMindB200ForCausalLM, video: torch.Tensor, instruct: str, tokenizer, do_sample=False,

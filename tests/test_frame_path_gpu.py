@@ -191,9 +191,8 @@ def test_pipelined_submit_small(built_library, use_graphs):
     eng.close()
 
 
-def test_pipelined_and_persistent_full_size_fp16(built_library, monkeypatch):
-    """Full BASELINE shapes: (a) the pipelined path (tower and gate on two internal streams) and (b) the
-    persistent vision-tower kernel (SMB_MEGA=2) reproduce the serial per-kernel path."""
+def test_pipelined_full_size_fp16(built_library):
+    """Full BASELINE shapes: the pipelined path (tower and gate on two internal streams) reproduces the serial path."""
     dt = torch.float16
     cfg = engine_config(dt, small=False, llm_layers=0, max_frames=1, use_graphs=True)
     sd = make_weights(cfg)
@@ -213,14 +212,6 @@ def test_pipelined_and_persistent_full_size_fp16(built_library, monkeypatch):
         check_close(f"pipelined tokens {t}", outs[t][2], ref[t][1], 4e-3)
         check_close(f"pipelined logits {t}", outs[t][3], ref[t][2], 8e-3)
     eng.close()
-    monkeypatch.setenv("SMB_MEGA", "2")
-    eng2 = build_engine(cfg, sd)
-    for t in range(3):
-        f2, _, lg2, _ = eng2.frame_step(frames[t:t + 1], want_feats=True)
-        torch.cuda.synchronize()
-        check_close(f"persistent-kernel features {t}", f2, ref[t][0], 4e-3)  # two valid fp16 paths: noise floor ~1.6e-3
-        check_close(f"persistent-kernel logits {t}", lg2, ref[t][2], 8e-3)
-    eng2.close()
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
@@ -287,4 +278,65 @@ def test_batched_gate_gemm_full_size_fp16(built_library):
     # sit at that quantisation floor (measured 1.09e-3 GEMV, 1.14e-3 GEMM); the GEMM path must not be worse than the
     # GEMV path by more than a fraction of an ulp.
     assert e_gemv[1] < 1.5e-3 and e_gemm[1] < 1.5e-3 and e_gemm[1] < e_gemv[1] + 3e-4, (e_gemm, e_gemv)
+    eng.close()
+
+
+def test_pipelined_eight_tickets_full_size_vs_oracle(built_library):
+    """The configuration bench.py's frame stage runs -- streaming handle, 8 single-frame tickets = ONE tower chunk of 8
+    (tcgen05 attention, wide GEMM tiles), projector batches of 4, gate as tcgen05 GEMMs -- compared DIRECTLY with the
+    oracle (not with the serial path): features, projector tokens and gate logits of all 8 frames, fp16, full size.
+    End-to-end bound as in test_full_size_frame_path_fp16: max(1e-3, 1.5 x the fp16 noise floor of the 23-layer tower)."""
+    dt = torch.float16
+    cfg = engine_config(dt, small=False, llm_layers=0, max_frames=1, use_graphs=True)
+    sd = make_weights(cfg)
+    eng = build_engine(cfg, sd)
+    oc = oracle_configs(cfg)
+    sd32 = f32(sd)
+    frames = synth.make_frames(0, 0, 8, 336, dtype=dt)
+    feats_o, toks_o, logits_o = _oracle_frames(sd32, oc, dt, frames)
+    feats_x = R.clip_vision_tower(sd32, oc.vit, frames[:2].float())
+    floor = rel_err(feats_o[:2], feats_x)[1]
+    bound = max(1e-3, 1.5 * floor)
+    fd = frames.cuda()
+    for rep in range(2):                       # second pass replays the captured graphs
+        eng.reset_stream()
+        outs = [eng.frame_submit(fd[t:t + 1], want_feats=True, want_device_outputs=True) for t in range(8)]
+        eng.frame_wait(outs[-1][0], block=True)
+        torch.cuda.synchronize()
+        e = rel_err(torch.cat([o[1] for o in outs]), feats_o)
+        print(f"pass {rep}: 8-ticket pipelined features vs oracle {e} (fp16 noise floor {floor:.2e}, bound {bound:.2e})")
+        assert e[1] < bound and e[0] < 2.5 * bound, (e, bound)
+        check_close(f"8-ticket pipelined tokens vs oracle (pass {rep})", torch.cat([o[2] for o in outs]), toks_o, 4 * bound)
+        check_close(f"8-ticket pipelined gate logits vs oracle (pass {rep})", torch.cat([o[3] for o in outs]), logits_o, 8 * bound)
+    eng.close()
+
+
+def test_full_size_frame_path_bf16(built_library):
+    """BASELINE configs[2] runs in bf16: the full-size frame path (23-layer tower + projector + gate) in bf16 against the
+    oracle with bf16 rounding emulation.  bf16 keeps 8 mantissa bits, so the per-kernel bound is 8e-3 and the 23-layer
+    end-to-end bound max(8e-3, 1.5 x noise floor); projector and gate are also checked teacher-forced at 8e-3."""
+    dt = torch.bfloat16
+    cfg = engine_config(dt, small=False, llm_layers=0, max_frames=2, use_graphs=False)
+    sd = make_weights(cfg)
+    eng = build_engine(cfg, sd)
+    oc = oracle_configs(cfg)
+    sd32 = f32(sd)
+    frames = synth.make_frames(0, 0, 2, 336, dtype=dt)
+    feats_o, toks_o, logits_o = _oracle_frames(sd32, oc, dt, frames)
+    feats_x = R.clip_vision_tower(sd32, oc.vit, frames.float())
+    floor = rel_err(feats_o, feats_x)[1]
+    bound = max(8e-3, 1.5 * floor)
+    feats, toks, logits, _ = eng.frame_step(frames.cuda(), want_feats=True)
+    torch.cuda.synchronize()
+    e = rel_err(feats, feats_o)
+    print(f"bf16 full-size ViT features vs emulated oracle {e}, bf16 noise floor {floor:.2e}")
+    assert e[1] < bound and e[0] < 2.5 * bound, (e, floor)
+    check_close("bf16 end-to-end tokens", toks, toks_o, 4 * bound)
+    check_close("bf16 end-to-end gate logits", logits, logits_o, 8 * bound)
+    eng.reset_stream()
+    with R.emulate(dt):
+        pooled_o = torch.stack([R.pool_patches(feats_o[t]) for t in range(2)])
+    check_close("bf16 teacher-forced projector tokens", eng.projector_step(pooled_o.to(dt).cuda()), toks_o, 8e-3)
+    lg_tf = torch.stack([eng.gate_score(toks_o[t].to(dt).cuda()) for t in range(2)])
+    check_close("bf16 teacher-forced gate logits", lg_tf, logits_o, 8e-3)
     eng.close()
