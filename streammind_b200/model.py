@@ -481,13 +481,14 @@ class MultiStreamSession:
     Results are those of B independent ``StreamMindB200ForCausalLM`` runs (same kernels, per-stream arithmetic independent
     of the batch: tests/test_multi_stream_gpu.py)."""
 
-    def __init__(self, cfg: EngineConfig, state_dict: Dict[str, torch.Tensor], n_streams: int, device: int = 0):
+    def __init__(self, cfg: EngineConfig, state_dict: Optional[Dict[str, torch.Tensor]], n_streams: int, device: int = 0):
         import dataclasses
         cfg = dataclasses.replace(cfg, n_streams=n_streams, max_frames=max(cfg.max_frames, n_streams))
         self.config = cfg
         self.engine = Engine(cfg, device=device)
         self.streams = [StreamMindB200ForCausalLM(cfg, None, device=device, engine=self.engine, stream_id=s) for s in range(n_streams)]
-        self.streams[0].load_state_dict(state_dict)
+        if state_dict is not None:
+            self.streams[0].load_state_dict(state_dict)
 
     def reset(self):
         for m in self.streams:
