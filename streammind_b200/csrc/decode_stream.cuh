@@ -141,6 +141,19 @@ __device__ __forceinline__ long long ds_gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// mbarrier wait for the hot loops: try_wait with a suspend-time hint, so a waiting warp sleeps in hardware instead of
+// executing a poll loop (bounded: a protocol error traps instead of hanging the box)
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+        if (!ok && ++spins > (1u << 20)) { printf("smb: decode ring mbarrier timeout (cta %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    } while (!ok);
+}
 __device__ __forceinline__ void ds_consumer_sync() { named_bar_sync(1, kDsConsumerThreads); }
 
 // Grid barrier of the consumer side (thread 0 of every CTA arrives and polls; bounded spin so that a logic error traps
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                 const DsOp& op = p.ops[cur.oi];
                 const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
                 const int slot = cur.seq % p.n_slots, use = cur.seq / p.n_slots;
-                if (use > 0) mbar_wait(&empty_bar[slot], (use - 1) & 1);
+                if (use > 0) mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
                 const int nr = min(cur.RJ, cur.j1 - cur.j);
                 const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
                 mbar_arrive_expect_tx(&full_bar[slot], bytes * op.nmat);
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
         }
     };
     unsigned bar_target = epoch * static_cast<unsigned>(p.n_barriers) * G;
-    int seq = 0;
+    int seq = 0, ring_slot = 0, ring_par = 0;            // chunk sequence number, its ring slot and the parity of that slot's use
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const DsOp& op = p.ops[oi];
         if (op.type == DS_GEMV) {
@@ -364,35 +377,50 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
             const bool diag0 = (lane >> 2) == 2 * (lane & 3), diag1 = (lane >> 2) == 2 * (lane & 3) + 1;   // this lane holds D[g][g] in c0 / c1
             const uint2* xp = reinterpret_cast<const uint2*>(xs + c0) + lane;   // block b of vector v: xp[v * xq + 32 b]
             const int xq = p.xcap / 4;
+            // The hot loop is kept branch-free and division-free (ncu, profiles/r02_decode_kernel.md: an earlier form with a
+            // guard per block executed ~3700 warp instructions per 32 KB slot, 22 % of them mbarrier polls): blocks go in
+            // unguarded batches of 8 and 2 (nblk is even), the ring position advances incrementally.
+            const uint2* ring_u2 = reinterpret_cast<const uint2*>(ring) + (static_cast<size_t>(sr) * K + c0) / 4 + lane;
+            float* part_w = part + (static_cast<size_t>(m) * nloc * P + pt) * NV;           // + local row * P * NV
+            const int skip_math = p.dbg_flags & 1;
             for (int j = j0; j < j1; j += RJ, ++seq) {
-                if (seq % kDsGroups != grp) continue;
-                const int slot = seq % p.n_slots, use = seq / p.n_slots;
-                stamp(1);
-                mbar_wait(&full_bar[slot], use & 1);
-                stamp(j == j0 ? 6 : 7);                         // time spent waiting for the first / a later chunk of the op
-                if (j + jr < j1 && !(p.dbg_flags & 1)) {
-                    const uint2* wp = reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(ring + static_cast<size_t>(slot) * kDsSlotBytes) +
-                                                                     static_cast<size_t>(sr) * K + c0) + lane;
+                const int slot = ring_slot, par = ring_par;
+                if (++ring_slot == p.n_slots) { ring_slot = 0; ring_par ^= 1; }
+                if (kDsGroups > 1 && seq % kDsGroups != grp) continue;
+                mbar_wait_hint(&full_bar[slot], par);
+                if (j + jr < j1 && !skip_math) {
+                    const uint2* wp = ring_u2 + slot * (kDsSlotBytes / 8);
                     float acc[NPAIR][2][4];
 #pragma unroll
                     for (int q = 0; q < NPAIR; ++q)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) { acc[q][e][0] = 0.f; acc[q][e][1] = 0.f; acc[q][e][2] = 0.f; acc[q][e][3] = 0.f; }
-                    for (int b0 = 0; b0 < nblk; b0 += 8) {           // 8 blocks per batch: all their loads in flight together
+                    int b = 0;
+                    for (; b + 8 <= nblk; b += 8) {                  // 8 blocks per batch: all their loads in flight together
                         uint2 w[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) w[u] = b0 + u < nblk ? wp[(b0 + u) * 32] : make_uint2(0u, 0u);
+                        for (int u = 0; u < 8; ++u) w[u] = wp[(b + u) * 32];
 #pragma unroll
                         for (int q = 0; q < NPAIR; ++q) {
                             uint2 xa[8], xb[8];
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
-                                const bool in = b0 + u < nblk;
-                                xa[u] = in ? xp[(2 * q) * xq + (b0 + u) * 32] : make_uint2(0u, 0u);
-                                xb[u] = (in && 2 * q + 1 < NV) ? xp[(2 * q + 1) * xq + (b0 + u) * 32] : make_uint2(0u, 0u);
+                                xa[u] = xp[(2 * q) * xq + (b + u) * 32];
+                                xb[u] = 2 * q + 1 < NV ? xp[(2 * q + 1) * xq + (b + u) * 32] : make_uint2(0u, 0u);
                             }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) ds_mma_16816<T>(acc[q][u & 1], xa[u].x, xb[u].x, xa[u].y, xb[u].y, w[u].x, w[u].y);
+                        }
+                    }
+                    for (; b < nblk; b += 2) {
+                        const uint2 w0 = wp[b * 32], w1 = wp[b * 32 + 32];
+#pragma unroll
+                        for (int q = 0; q < NPAIR; ++q) {
+                            const uint2 xa0 = xp[(2 * q) * xq + b * 32], xa1 = xp[(2 * q) * xq + b * 32 + 32];
+                            uint2 xb0 = make_uint2(0u, 0u), xb1 = make_uint2(0u, 0u);
+                            if (2 * q + 1 < NV) { xb0 = xp[(2 * q + 1) * xq + b * 32]; xb1 = xp[(2 * q + 1) * xq + b * 32 + 32]; }
+                            ds_mma_16816<T>(acc[q][0], xa0.x, xb0.x, xa0.y, xb0.y, w0.x, w0.y);
+                            ds_mma_16816<T>(acc[q][1], xa1.x, xb1.x, xa1.y, xb1.y, w1.x, w1.y);
                         }
                     }
                     float tot[NV];
@@ -403,7 +431,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                         tot[v] = warp_sum(diag0 ? d0 : diag1 ? d1 : 0.f);
                     }
                     if (lane == 0) {
-                        float* dst = part + ((static_cast<size_t>(m) * nloc + (j - j0 + jr)) * P + pt) * NV;
+                        float* dst = part_w + static_cast<size_t>(j - j0 + jr) * P * NV;
 #pragma unroll
                         for (int v = 0; v < NV; ++v) dst[v] = tot[v];
                     }
