@@ -153,6 +153,22 @@ int sm_frame_submit(sm_handle* h, const void* pixels, int pixels_on_host, int B,
                     float* logits_out, float* logits_host, void* stream, long long* ticket);
 int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host);
 
+/* Cognition sampling of a frame-token segment before the LLM (videollama2_arch.py:595-611, used by the eval
+ * forward at :676-681).  toks [n, d] model dtype (device) -> out [k, d], the kept rows in their original order, and
+ * (optional) indices_out [k] int32 (device).  k = sm_cognition_count(n, percentage, mode).
+ *   mode 0 "log" = exponential_sampling as the reference ships it: torch.linspace(0, n - 1, k).int() rows (float32
+ *           linspace exactly as ATen's CPU kernel evaluates it on this host), k = int(percentage n) or 1;
+ *   mode 1 "similarity" = similarity_sampling: the k = max(int(percentage n), 1) rows most cosine-similar to the LAST
+ *           row (torch cosine_similarity arithmetic in the model dtype; ties -> lower index). */
+int sm_cognition_sample(sm_handle* h, const void* toks, int n, int d, int mode, double percentage, void* out, int32_t* indices_out,
+                        void* stream);
+int sm_cognition_count(int n, double percentage, int mode);
+/* Host-only: torch.linspace(0, n - 1, steps).int() -> out [steps] as ATen's CPU kernel evaluates it (the reference calls
+ * torch.linspace without a device, i.e. on the host): fused = 1 one FMA per element (ATen's AVX2 / AVX512 builds), 0 product
+ * and sum rounded separately (its DEFAULT build), -1 = what this host's torch would do (the rule sm_cognition_sample uses).
+ * Checked against torch under each ATEN_CPU_CAPABILITY in tests/test_cognition_cpu.py. */
+int sm_linspace_indices(int n, int steps, int fused, int* out);
+
 /* embed_tokens (videollama2_arch.py:967,977): ids [n] int32 device -> out [n, hidden]. */
 int sm_embed_tokens(sm_handle* h, const int32_t* ids, int n, void* out, void* stream);
 

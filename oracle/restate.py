@@ -554,3 +554,33 @@ def greedy_decode(sd: SD, cfg: MistralCfg, embeds: torch.Tensor, cache: KVCache,
             break
         logits = mistral_forward(sd, LLM_PREFIX, cfg, emb[tok][None, :], cache)
     return (out, all_logits) if return_logits else out
+
+
+# --------------------------------------------------------------------------------------------
+# 8f-4: cognition sampling of a frame-token segment before the LLM
+# --------------------------------------------------------------------------------------------
+def exponential_sampling(tokens: torch.Tensor, percentage: float = 0.6):
+    """videollama2_arch.py:595-601 (the shipped variant: linearly spaced indices): returns (kept rows, indices)."""
+    n = tokens.size(0)
+    num = 1 if int(percentage * n) == 0 else int(percentage * n)
+    idx = torch.linspace(0, n - 1, num).int().tolist()
+    return tokens[idx], idx
+
+
+def similarity_sampling(tokens: torch.Tensor, percentage: float = 0.6):
+    """videollama2_arch.py:603-611: the max(int(p n), 1) rows most cosine-similar to the last row, original order kept.
+    torch's cosine_similarity (ATen: normalise both operands by clamp_min(norm, eps), multiply, sum) with every tensor
+    rounded to the emulated dtype; sums in float64 so that no summation order matters.  The reference's argsort is
+    unstable, i.e. tie order is unspecified there; here ties go to the lower index."""
+    x = tokens.double()
+    last = x[-1]
+    eps = 1e-8
+    nx = _r(x.pow(2).sum(-1).sqrt().float()).clamp_min(eps).double()
+    nl = nx[-1]
+    a = _r((x / nx[:, None]).float()).double()
+    b = _r((last / nl).float()).double()
+    sim = _r(_r((a * b[None]).float()).double().sum(-1).float())
+    k = max(int(percentage * x.shape[0]), 1)
+    order = sorted(range(x.shape[0]), key=lambda i: (-float(sim[i]), i))
+    idx = sorted(order[:k])
+    return tokens[idx], idx

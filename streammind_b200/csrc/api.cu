@@ -78,6 +78,7 @@ struct sm_handle {
     void* pre_src = nullptr; size_t pre_src_bytes = 0;
     void* pre_tmp = nullptr; size_t pre_tmp_bytes = 0;
     void* pre_lut = nullptr; float pre_lut_key[6] = {0, 0, 0, 0, 0, 0};
+    void* cog_buf = nullptr; size_t cog_bytes = 0;      // sm_cognition_sample scratch (indices + similarities), grow-only
     std::unordered_map<std::string, Slot> slots;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
     PFN_encodeTiled encode = nullptr;
@@ -1870,6 +1871,85 @@ int sm_frame_wait(sm_handle* h, long long ticket, void* stream, int block_host) 
     cudaEvent_t ev = h->ev_gate[ticket % kTicketRing];
     if (stream != nullptr || !block_host) CUDA_OK(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
     if (block_host) CUDA_OK(h, cudaEventSynchronize(ev));
+    return 0;
+}
+
+// torch.linspace(0, n - 1, steps).int() as the reference gets it: the call has no device argument, so it is ATen's CPU
+// kernel (aten/src/ATen/native/cpu/RangeFactoriesKernel.cpp) whatever device the model is on.  In float32:
+// step = (end - start) / (steps - 1); element i is start + step * i below steps / 2 and end - step * (steps - i - 1) from
+// there on, truncated toward zero by .int().  ATen's AVX2 / AVX512 builds contract each multiply-add into ONE fused
+// multiply-add, its DEFAULT build (no FMA hardware) rounds twice -- the two differ whenever the product lands within an
+// ulp of an integer (n = 17, steps = 15: index 7 is 7 with FMA, 8 without), so the host's capability is part of the rule.
+static void linspace_indices(int n, int steps, bool fused, int* out) {
+    const float start = 0.f, end = static_cast<float>(n - 1);
+    if (steps == 1) { out[0] = 0; return; }
+    const float step = (end - start) / static_cast<float>(steps - 1);
+    const int halfway = steps / 2;
+    for (int i = 0; i < steps; ++i) {
+        const float a = i < halfway ? step : -step, b = static_cast<float>(i < halfway ? i : steps - i - 1), c = i < halfway ? start : end;
+        volatile float prod = a * b;                       // volatile: keeps the unfused product a separately rounded float
+        out[i] = static_cast<int>(fused ? fmaf(a, b, c) : prod + c);
+    }
+}
+
+// does ATen on this host run its AVX2 / AVX512 (FMA) kernels?  (torch.backends.cpu.get_cpu_capability() != "DEFAULT")
+static bool host_fused_multiply_add() {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2");
+}
+
+int sm_cognition_count(int n, double percentage, int mode) {
+    if (n < 1) return 0;
+    const int k = static_cast<int>(percentage * n);           // Python: int(percentage * n), float64 product
+    return mode == 0 ? (k == 0 ? 1 : k) : std::max(k, 1);
+}
+
+int sm_linspace_indices(int n, int steps, int fused, int* out) {
+    if (n < 1 || steps < 1 || !out || fused < -1 || fused > 1) return 1;
+    linspace_indices(n, steps, fused < 0 ? host_fused_multiply_add() : fused == 1, out);
+    return 0;
+}
+
+int sm_cognition_sample(sm_handle* h, const void* toks, int n, int d, int mode, double percentage, void* out, int32_t* indices_out,
+                        void* stream) {
+    if (!h || !toks || !out) return fail(h, "sm_cognition_sample: null argument");
+    if (n < 1 || d < 1) return fail(h, "sm_cognition_sample: n=%d d=%d", n, d);
+    if (mode != 0 && mode != 1) return fail(h, "sm_cognition_sample: mode %d (0 = linspace, 1 = similarity)", mode);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int k = sm_cognition_count(n, percentage, mode);
+    // scratch: indices [n] + similarities [n]
+    const size_t need = static_cast<size_t>(n) * (sizeof(int) + sizeof(float));
+    if (need > h->cog_bytes) {
+        CUDA_OK(h, cudaStreamSynchronize(st));
+        if (h->cog_buf) { cudaFree(h->cog_buf); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), h->cog_buf)); }
+        CUDA_OK(h, cudaMalloc(&h->cog_buf, need));
+        h->allocs.push_back(h->cog_buf);
+        h->cog_bytes = need;
+    }
+    int* d_idx = static_cast<int*>(h->cog_buf);
+    float* d_sim = reinterpret_cast<float*>(d_idx + n);
+    if (mode == 0) {
+        std::vector<int> idx(k);
+        linspace_indices(n, k, host_fused_multiply_add(), idx.data());
+        CUDA_OK(h, cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
+        CUDA_OK(h, cudaStreamSynchronize(st));                 // idx is a stack-lifetime host buffer
+    } else {
+        if (static_cast<size_t>(n) * sizeof(int) > 200 * 1024) return fail(h, "sm_cognition_sample: at most %d tokens", 200 * 1024 / 4);
+        DISPATCH_T(h, T, {
+            cos_sim_rows_kernel<T><<<(n + 7) / 8, 256, 0, st>>>((const T*)toks, n, d, 1e-8f, d_sim);
+            count_launch(h);
+        })
+        CUDA_OK(h, cudaFuncSetAttribute(topk_keep_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        topk_keep_order_kernel<<<1, 1024, static_cast<size_t>(n) * sizeof(int), st>>>(d_sim, n, k, d_idx);
+        count_launch(h);
+    }
+    DISPATCH_T(h, T, {
+        gather_rows_kernel<T><<<k, 256, 0, st>>>((const T*)toks, d_idx, (T*)out, k, d);
+        count_launch(h);
+    })
+    if (indices_out) CUDA_OK(h, cudaMemcpyAsync(indices_out, d_idx, sizeof(int) * k, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(h, cudaGetLastError());
     return 0;
 }
 

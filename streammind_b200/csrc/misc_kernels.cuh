@@ -446,4 +446,58 @@ __global__ void gqa_expand_rows_kernel(const T* __restrict__ v, T* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Cognition sampling before the LLM (/root/reference/streammind/model/videollama2_arch.py:595-611):
+// similarity_sampling keeps the top-k frame tokens by cosine similarity with the LAST token, in their original order.
+//   sim_i = T(sum_d T(T(x_id / n_i) * T(x_Ld / n_L))),  n_i = max(T(sqrt(sum_d x_id^2)), eps)      (torch's
+//   cosine_similarity: normalise, multiply, sum, every tensor materialised in T); sums in fp64, so the result does not
+//   depend on the summation order and equals the oracle bit for bit.  One warp per row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cos_sim_rows_kernel(const T* __restrict__ x, int n, int d, float eps, float* __restrict__ sim) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const T* xi = x + static_cast<long long>(warp) * d;
+    const T* xl = x + static_cast<long long>(n - 1) * d;
+    double si = 0.0, sl = 0.0;
+    for (int k = lane; k < d; k += 32) {
+        const double a = Cvt<T>::to_f(xi[k]), b = Cvt<T>::to_f(xl[k]);
+        si += a * a;
+        sl += b * b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { si += __shfl_xor_sync(0xffffffffu, si, o); sl += __shfl_xor_sync(0xffffffffu, sl, o); }
+    const float ni = fmaxf(rnd<T>(static_cast<float>(sqrt(si))), eps), nl = fmaxf(rnd<T>(static_cast<float>(sqrt(sl))), eps);
+    double acc = 0.0;
+    for (int k = lane; k < d; k += 32) {
+        const float a = rnd<T>(Cvt<T>::to_f(xi[k]) / ni), b = rnd<T>(Cvt<T>::to_f(xl[k]) / nl);
+        acc += static_cast<double>(rnd<T>(a * b));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sim[warp] = rnd<T>(static_cast<float>(acc));
+}
+
+// Indices of the k largest sim values in ascending index order; ties go to the lower index (the reference's unstable argsort
+// leaves tie order unspecified).  One CTA; rank by counting (n <= a few thousand frame tokens).
+__global__ void __launch_bounds__(1024) topk_keep_order_kernel(const float* __restrict__ sim, int n, int k, int* __restrict__ idx_out) {
+    extern __shared__ int keep[];                  // [n]
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float si = sim[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float sj = sim[j];
+            rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+        }
+        keep[i] = rank < k ? 1 : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!keep[i]) continue;
+        int pos = 0;
+        for (int j = 0; j < i; ++j) pos += keep[j];
+        idx_out[pos] = i;
+    }
+}
+
 }  // namespace smb

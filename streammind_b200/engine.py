@@ -273,6 +273,18 @@ class Engine:
         """Order the current stream after (on_stream) and/or block the host until (block) ticket's outputs."""
         self._check(self.lib.sm_frame_wait(self._h, ticket, self._stream() if on_stream else None, 1 if block else 0))
 
+    def cognition_sample(self, toks: torch.Tensor, percentage: float, sample_type: str):
+        """exponential_sampling ('log') / similarity_sampling ('similarity') of a frame-token segment [n, d]
+        (videollama2_arch.py:595-611) -> (kept rows [k, d] in their original order, their indices [k] int32)."""
+        t = self._t(toks, "toks")
+        n, d = t.shape
+        mode = {"log": 0, "similarity": 1}[sample_type]
+        k = self.lib.sm_cognition_count(n, float(percentage), mode)
+        out = torch.empty(k, d, dtype=t.dtype, device=self.device)
+        idx = torch.empty(k, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sm_cognition_sample(self._h, t.data_ptr(), n, d, mode, float(percentage), out.data_ptr(), idx.data_ptr(), self._stream()))
+        return out, idx
+
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.cfg.llm_vocab):
             # the reference's nn.Embedding raises IndexError here (e.g. an unexpanded <image> = -200 sentinel)

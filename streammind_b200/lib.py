@@ -49,6 +49,9 @@ SYMBOLS = {
     "sm_frame_step_multi": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "sm_frame_submit": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_longlong)]),
     "sm_frame_wait": (_I, [_VP, _LL, _VP, _I]),
+    "sm_cognition_sample": (_I, [_VP, _VP, _I, _I, _I, C.c_double, _VP, _VP, _VP]),
+    "sm_cognition_count": (_I, [_I, C.c_double, _I]),
+    "sm_linspace_indices": (_I, [_I, _I, _I, _VP]),
     "sm_embed_tokens": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_prefill": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sm_llm_decode": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),

@@ -185,8 +185,12 @@ class StreamMindB200ForCausalLM:
     """Drop-in for the calls the streaming demo / serve worker make on ``Videollama2MistralForCausalLM``."""
 
     def __init__(self, cfg: EngineConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None, device: int = 0,
-                 keep_frame_features: bool = False, engine: Optional[Engine] = None, stream_id: int = 0):
+                 keep_frame_features: bool = False, engine: Optional[Engine] = None, stream_id: int = 0,
+                 sample_per: float = 0.5, sample_type: str = "ssss"):
         self.config = cfg
+        # cognition sampling of every <video> span in forward() (videollama2_mistral.py:166-167,204-205; arch.py:676-681):
+        # "log" / "similarity" thin the span on the device, anything else (the reference's default "ssss") keeps it whole
+        self.sample_per, self.sample_type = sample_per, sample_type
         self.engine = engine if engine is not None else Engine(cfg, device=device)     # several stream objects may share one engine
         if state_dict is not None:
             self.load_state_dict(state_dict)
@@ -451,9 +455,14 @@ class StreamMindB200ForCausalLM:
                         rows.append(e.embed_tokens(torch.tensor(chunk)))
                         chunk = []
                     fr = frames.pop(0).to(device=e.device, dtype=e.cfg.dtype)
+                    span = []
                     for i in range(0, fr.shape[0], e.cfg.max_frames):
                         _, pooled = e.vit_encode(fr[i:i + e.cfg.max_frames], want_feats=False)
-                        rows.append(e.projector_step(pooled))
+                        span.append(e.projector_step(pooled))
+                    span = span[0] if len(span) == 1 else torch.cat(span, 0)
+                    if self.sample_type in ("log", "similarity"):
+                        span, _ = e.cognition_sample(span.contiguous(), self.sample_per, self.sample_type)
+                    rows.append(span)
                 else:
                     chunk.append(int(t))
             if chunk:
