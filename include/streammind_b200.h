@@ -205,10 +205,6 @@ int sm_decode_stats(sm_handle* h, double* ms, long long* steps, long long* token
  * 5 token selection (tools/decode_probe.py). */
 int sm_debug_decode_phases(sm_handle* h, long long* device_buf);
 
-/* Debug / test: activations the last decode step left behind (lane-major, model dtype): which = 0 residual stream x [hidden],
- * 1 qkv of the last layer before RoPE [(Hq + 2 Hk) D], 2 attention output of the last layer [Hq D], 3 SwiGLU output [ffn]. */
-int sm_debug_decode_buffer(sm_handle* h, int which, void* out, long long bytes, void* stream);
-
 /* Debug / test: fp32 logits [vocab] of the LAST decode step of lane `lane` (0 for sm_llm_decode) -> logits_out (device). */
 int sm_debug_decode_logits(sm_handle* h, int lane, float* logits_out, void* stream);
 

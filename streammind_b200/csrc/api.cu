@@ -139,12 +139,14 @@ struct sm_handle {
     long long kv_stream_stride = 0;    // elements between the caches of consecutive streams inside kc[l] / vc[l]
     // ---- persistent decode kernel (decode_stream.cuh)
     DsOp* ds_ops = nullptr;            // device op list of one decode step
-    int ds_n_ops = 0, ds_n_barriers = 0, ds_xcap = 0, ds_part_rows = 0 /* max over ops of nmat * rows-per-CTA * P */;
-    unsigned* ds_sync = nullptr;       // grid-barrier counter, epoch, all-done flag, per (lane, kv head) arrival counters
+    int ds_n_ops = 0, ds_xcap = 0, ds_part_rows = 0 /* max over ops of nmat * rows-per-CTA * P */;
+    unsigned* ds_sync = nullptr;       // [1] epoch of the decode kernel (never reset: its exchange tags derive from it), [2] all-done flag
     DsStreamState* ds_state = nullptr; // [kDsMaxStreams]
-    int *ds_out = nullptr, *ds_stop = nullptr, *ds_cand_idx = nullptr;   // ds_out [kDsMaxStreams][kDsMaxNew]
-    float *ds_att_part = nullptr, *ds_cand_val = nullptr, *ds_logits = nullptr;
-    void *ds_x = nullptr, *ds_qkv = nullptr, *ds_att = nullptr, *ds_m = nullptr;   // decode activations [kDsMaxStreams][...]
+    int *ds_out = nullptr, *ds_stop = nullptr;   // ds_out [kDsMaxStreams][kDsMaxNew]
+    float* ds_logits = nullptr;
+    // exchange buffers of the decode kernel (tagged 8-byte words, decode_stream.cuh): [kDsMaxStreams][elements / 2]
+    unsigned long long *ds_x_ll = nullptr, *ds_qkv_ll = nullptr, *ds_att_ll = nullptr, *ds_m_ll = nullptr;
+    unsigned long long *ds_att_part = nullptr, *ds_cand = nullptr;
     long long* ds_dbg = nullptr;       // sm_debug_decode_phases: per-phase ns of CTA 0
     double ds_ms = 0.0;                // device time of the decode steps since the last sm_decode_stats reset (CUDA events)
     long long ds_steps = 0, ds_tokens = 0, ds_ctx_sum = 0;
@@ -938,36 +940,38 @@ int build_decode_ops(sm_handle* h) {
     if (kDsMaxStreams * Hk > G) return fail(h, "decode kernel: %d lanes x %d kv heads exceed %d SMs", kDsMaxStreams, Hk, G);
     std::vector<DsOp> ops;
     int part_rows = 0, xcap = 0;
-    auto gemv = [&](const void* W0, const void* W1, int N, int K, int pro, int epi, const void* x, long long xs, const void* nw,
-                    void* y, long long ys, void* resid, long long rs) -> int {
+    // x / y: exchange buffers of the input and of what the op publishes, [lane][K / 2] and [lane][N / 2] words
+    auto gemv = [&](const void* W0, const void* W1, int N, int K, int pro, int epi, const unsigned long long* x, const void* nw,
+                    unsigned long long* y) -> int {
+        if (N % 2 || K % 4) return fail(h, "decode kernel: GEMV shape %d x %d (rows must be even, columns a multiple of 4)", N, K);
+        if (epi == DSE_RESID && (N != H || ds_rows_per_cta(H, G) > kDsResidRows))
+            return fail(h, "decode kernel: residual rows per CTA exceed %d (hidden %d on %d SMs)", kDsResidRows, H, G);
         DsOp o{};
         o.type = DS_GEMV; o.W0 = W0; o.W1 = W1; o.nmat = W1 ? 2 : 1; o.N = N; o.K = K;
         if (ds_geometry(h, K, o.nmat, &o.R, &o.P)) return 1;
-        o.pro = pro; o.epi = epi; o.x = x; o.x_stride = xs; o.nw = nw; o.eps = c.llm_eps; o.y = y; o.y_stride = ys;
-        o.resid = resid; o.resid_stride = rs;
+        o.pro = pro; o.epi = epi; o.xll = x; o.xll_stride = K / 2; o.nw = nw; o.eps = c.llm_eps; o.yll = y; o.yll_stride = N / 2;
+        if (epi == DSE_LOGITS) { o.logits = h->ds_logits; o.logits_stride = N; }
         ops.push_back(o);
-        part_rows = std::max(part_rows, o.nmat * ((N + G - 1) / G) * o.P);
+        part_rows = std::max(part_rows, o.nmat * ds_rows_per_cta(N, G) * o.P);
         xcap = std::max(xcap, (K + 7) & ~7);
         return 0;
     };
-    int n_bar = 0;
+    if (D != 128) return fail(h, "decode kernel: head_dim %d (128 only)", D);
     for (int l = 0; l < c.llm_layers; ++l) {
         const MistralLayer& L = h->llm[l];
-        if (gemv(L.wqkv, nullptr, QKV, H, l == 0 ? DSP_EMBED_RMSNORM : DSP_RMSNORM, DSE_STORE, h->ds_x, H, L.in_ln, h->ds_qkv, QKV, nullptr, 0)) return 1;
+        if (gemv(L.wqkv, nullptr, QKV, H, l == 0 ? DSP_EMBED_RMSNORM : DSP_RMSNORM, DSE_STORE, h->ds_x_ll, L.in_ln, h->ds_qkv_ll)) return 1;
         DsOp a{};
-        a.type = DS_ATTN; a.qkv = h->ds_qkv; a.qkv_stride = QKV; a.kc = h->kc[l]; a.vc = h->vc[l];
-        a.kv_stream_stride = h->kv_stream_stride; a.att = h->ds_att; a.Hq = Hq; a.Hk = Hk; a.max_ctx = c.llm_max_ctx;
+        a.type = DS_ATTN; a.qkv_ll = h->ds_qkv_ll; a.qkv_ll_stride = QKV / 2; a.kc = h->kc[l]; a.vc = h->vc[l];
+        a.kv_stream_stride = h->kv_stream_stride; a.att_ll = h->ds_att_ll; a.Hq = Hq; a.Hk = Hk; a.max_ctx = c.llm_max_ctx;
         a.rope_theta = c.llm_rope_theta;
         a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
         ops.push_back(a);
-        if (gemv(L.wo, nullptr, H, Hq * D, DSP_PLAIN, l == 0 ? DSE_RESID_EMBED : DSE_RESID, h->ds_att, Hq * D, nullptr, nullptr, 0, h->ds_x, H)) return 1;
-        if (gemv(L.wgu, static_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz, F, H, DSP_RMSNORM, DSE_SWIGLU, h->ds_x, H,
-                 L.post_ln, h->ds_m, F, nullptr, 0)) return 1;
-        if (gemv(L.wd, nullptr, H, F, DSP_PLAIN, DSE_RESID, h->ds_m, F, nullptr, nullptr, 0, h->ds_x, H)) return 1;
-        n_bar += 5;
+        if (gemv(L.wo, nullptr, H, Hq * D, DSP_PLAIN, DSE_RESID, h->ds_att_ll, nullptr, h->ds_x_ll)) return 1;
+        if (gemv(L.wgu, static_cast<const char*>(L.wgu) + static_cast<size_t>(F) * H * h->esz, F, H, DSP_RMSNORM, DSE_SWIGLU, h->ds_x_ll,
+                 L.post_ln, h->ds_m_ll)) return 1;
+        if (gemv(L.wd, nullptr, H, F, DSP_PLAIN, DSE_RESID, h->ds_m_ll, nullptr, h->ds_x_ll)) return 1;
     }
-    if (gemv(h->lm_head, nullptr, V, H, DSP_RMSNORM, DSE_LOGITS, h->ds_x, H, h->lm_norm, h->ds_logits, V, nullptr, 0)) return 1;
-    n_bar += 1;
+    if (gemv(h->lm_head, nullptr, V, H, DSP_RMSNORM, DSE_LOGITS, h->ds_x_ll, h->lm_norm, nullptr)) return 1;
     DsOp fin{};
     fin.type = DS_FINAL;
     ops.push_back(fin);
@@ -975,7 +979,6 @@ int build_decode_ops(sm_handle* h) {
     if (!h->ds_ops) return fail(h, "decode kernel: out of device memory");
     CUDA_OK(h, cudaMemcpy(h->ds_ops, ops.data(), ops.size() * sizeof(DsOp), cudaMemcpyHostToDevice));
     h->ds_n_ops = static_cast<int>(ops.size());
-    h->ds_n_barriers = n_bar;
     h->ds_xcap = xcap;
     h->ds_part_rows = part_rows;
     return 0;
@@ -1002,16 +1005,23 @@ int launch_decode_step_t(sm_handle* h, int nv, cudaStream_t st) {
     if (m.n_slots < 2) return fail(h, "decode kernel: %d lanes leave no room for the weight ring", nv);
     DsParams p{};
     p.ops = h->ds_ops; p.n_ops = h->ds_n_ops; p.n_slots = m.n_slots; p.xcap = h->ds_xcap; p.x_bytes = m.x_bytes; p.part_cap = m.part_cap;
-    p.sync = h->ds_sync; p.n_barriers = h->ds_n_barriers; p.st = h->ds_state; p.out_ids = h->ds_out; p.out_stride = kDsMaxNew;
+    p.sync = h->ds_sync; p.st = h->ds_state; p.out_ids = h->ds_out; p.out_stride = kDsMaxNew;
     p.stop = h->ds_stop; p.embed = h->lm_embed; p.H = h->cfg.llm_hidden; p.att_part = h->ds_att_part;
-    p.cand_val = h->ds_cand_val; p.cand_idx = h->ds_cand_idx; p.dbg = h->ds_dbg;
+    p.cand = h->ds_cand; p.dbg = h->ds_dbg;
     {
         static const int ahead = getenv("SMB_DS_L2_AHEAD") ? atoi(getenv("SMB_DS_L2_AHEAD")) : 0;   // measured: an L2 prefetch cursor 8 / 16 chunks ahead is slower (3.65 / 5.4 vs 3.32 ms per step)
         static const int flags = getenv("SMB_DS_DBG") ? atoi(getenv("SMB_DS_DBG")) : 0;
+        static const int inflight = getenv("SMB_DS_INFLIGHT") ? atoi(getenv("SMB_DS_INFLIGHT")) : 0;
         p.l2_ahead = std::max(0, ahead) & ~1;
         p.dbg_flags = flags;
+        p.max_inflight = inflight >= m.n_slots ? 0 : std::max(0, inflight);
     }
     const dim3 grid(h->num_sms), block(kDsThreads);
+    {
+        static bool once = false;
+        if (!once && getenv("SMB_DS_POLL_NS")) { const unsigned ns = atoi(getenv("SMB_DS_POLL_NS")); cudaMemcpyToSymbol(ds_poll_ns, &ns, sizeof ns); }
+        once = true;
+    }
     switch (nv) {
         case 1: decode_stream_kernel<T, 1><<<grid, block, m.total, st>>>(p); break;
         case 2: decode_stream_kernel<T, 2><<<grid, block, m.total, st>>>(p); break;
@@ -1422,15 +1432,15 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->lw_part2 = static_cast<float*>(A(static_cast<size_t>(8) * 64 * std::max(QKV, H) * sizeof(float)));
         // persistent decode kernel: activations of up to kDsMaxStreams lanes, state, split-KV partials, argmax candidates
         const size_t NL = kDsMaxStreams;
-        h->ds_x = A(NL * H * e); h->ds_qkv = A(NL * QKV * e); h->ds_att = A(NL * Hq * D * e); h->ds_m = A(NL * F * e);
+        auto LLA = [&](size_t words) { return static_cast<unsigned long long*>(A(words * sizeof(unsigned long long))); };   // zeroed: tag 0 never matches
+        h->ds_x_ll = LLA(NL * H / 2); h->ds_qkv_ll = LLA(NL * QKV / 2); h->ds_att_ll = LLA(NL * Hq * D / 2); h->ds_m_ll = LLA(NL * F / 2);
         h->ds_logits = static_cast<float*>(A(NL * V * sizeof(float)));
-        h->ds_sync = static_cast<unsigned*>(A((8 + 2 * NL * Hk) * sizeof(unsigned)));
+        h->ds_sync = static_cast<unsigned*>(A(8 * sizeof(unsigned)));
         h->ds_state = static_cast<DsStreamState*>(A(NL * sizeof(DsStreamState)));
         h->ds_out = static_cast<int*>(A(NL * kDsMaxNew * sizeof(int)));
         h->ds_stop = static_cast<int*>(A(64 * sizeof(int)));
-        h->ds_att_part = static_cast<float*>(A(NL * Hq * h->num_sms * (D + 2) * sizeof(float)));
-        h->ds_cand_val = static_cast<float*>(A(NL * h->num_sms * sizeof(float)));
-        h->ds_cand_idx = static_cast<int*>(A(NL * h->num_sms * sizeof(int)));
+        h->ds_att_part = LLA(NL * Hq * h->num_sms * (D + 2));
+        h->ds_cand = LLA(NL * h->num_sms * 2);
         h->kv_lens.assign(h->n_streams, 0);
     }
     if (oom) {
@@ -2022,7 +2032,7 @@ int sm_llm_decode_multi(sm_handle* h, int n, const int* stream_ids, const int* m
     for (int i = 0; i < n_stop; ++i) stopbuf[1 + i] = stop_ids[i];
     CUDA_OK(h, cudaMemcpyAsync(h->ds_stop, stopbuf, sizeof stopbuf, cudaMemcpyHostToDevice, st));
     CUDA_OK(h, cudaMemcpyAsync(h->ds_state, hs, sizeof(DsStreamState) * n, cudaMemcpyHostToDevice, st));
-    CUDA_OK(h, cudaMemsetAsync(h->ds_sync, 0, (8 + 2 * static_cast<size_t>(kDsMaxStreams) * c.llm_kv_heads) * sizeof(unsigned), st));
+    CUDA_OK(h, cudaMemsetAsync(h->ds_sync + 2, 0, sizeof(unsigned), st));      // the all-done flag; the epoch in [1] keeps counting
     ds_first_token_kernel<<<1, 1024, 0, st>>>(h->lw_logits, c.llm_vocab, c.llm_vocab, n, h->ds_state, h->ds_out, kDsMaxNew, h->ds_stop, h->ds_sync);
     count_launch(h);
     CUDA_OK(h, cudaGetLastError());
@@ -2088,15 +2098,6 @@ int sm_decode_stats(sm_handle* h, double* ms, long long* steps, long long* token
 int sm_debug_decode_phases(sm_handle* h, long long* device_buf) {
     if (!h) return 1;
     h->ds_dbg = device_buf;
-    return 0;
-}
-
-int sm_debug_decode_buffer(sm_handle* h, int which, void* out, long long bytes, void* stream) {
-    if (!h || !h->ds_x || !out) return fail(h, "sm_debug_decode_buffer: bad argument");
-    const void* src = which == 0 ? h->ds_x : which == 1 ? h->ds_qkv : which == 2 ? h->ds_att : which == 3 ? h->ds_m : nullptr;
-    if (!src) return fail(h, "sm_debug_decode_buffer: which = %d", which);
-    cudaSetDevice(h->device);
-    CUDA_OK(h, cudaMemcpyAsync(out, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

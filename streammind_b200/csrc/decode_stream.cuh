@@ -4,7 +4,8 @@
 //
 // Why one kernel: as separate launches (7 per layer) every projection pays a prologue (stage + normalise the input
 // vector), a pipeline fill and a tail, during which HBM idles: 0.64 of the HBM roofline at ctx 4k (round 1).  Here
-// one CTA per SM walks a device-resident op list (GEMV, attention, final argmax) with a grid barrier after each op,
+// one CTA per SM walks a device-resident op list (GEMV, attention, final argmax); activations travel between the CTAs as
+// tagged 8-byte words that the consumer polls (no grid barrier anywhere in the step, see "activation exchange" below),
 // and the WEIGHT stream never stops: producer warps run ahead of the consumers through a shared-memory ring
 // (kDsSlots x 32 KB, filled by cp.async.bulk, one mbarrier pair per slot) across op boundaries -- weights do not
 // depend on activations -- so epilogue + grid barrier + next prologue (~2-3 us) hide under up to 192 KB / SM of
@@ -19,8 +20,8 @@
 //
 // Attention op (one query per stream): CTA (stream, kv head, KV slice) applies RoPE to the group's q heads and to the
 // new k, appends k / v to the cache, runs online softmax over its slice (all query heads of the GQA group share each
-// K / V read), writes an un-normalised partial; the LAST CTA to finish a (stream, kv head) merges the slices in
-// fixed order (split-KV combine folded in: no extra launch, no extra grid barrier).
+// K / V read), publishes an un-normalised partial; the CTA of slice 0 of a (stream, kv head) merges the slices in
+// fixed order (split-KV combine folded in: no extra launch, no counter, no barrier).
 // Rounding points are those of the reference (oracle/restate.py mistral_forward): RMSNorm output, every projection
 // output, RoPE products, softmax probabilities before P.V, silu and its product, residual sums, logits.
 #pragma once
@@ -40,6 +41,7 @@ constexpr int kDsThreads = (kDsConsumerWarps + kDsProducerWarps) * 32;
 constexpr int kDsSlotBytes = 32 * 1024;
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxStreams = 4;
+constexpr int kDsResidRows = 64;            // rows of the residual stream one CTA may own (hidden <= 64 x SMs)
 
 enum DsOpType : int { DS_GEMV = 0, DS_ATTN = 1, DS_FINAL = 2 };
 enum DsPro : int {
@@ -49,8 +51,8 @@ enum DsPro : int {
 };
 enum DsEpi : int {
     DSE_STORE = 0,        // y = T(acc)
-    DSE_RESID = 1,        // resid[n] = T(resid[n] + T(acc))                     (in-place residual stream)
-    DSE_RESID_EMBED = 2,  // resid[n] = T(embed[token][n] + T(acc))              (first layer: the residual stream starts here)
+    DSE_RESID = 1,        // y = resid[n] = T(resid[n] + T(acc))                 (the residual stream: row n lives in the shared memory of its
+                          //                                                      owner CTA for the whole step, starting as embed[token][n])
     DSE_SWIGLU = 3,       // two matrices: y = T(T(silu(T(acc0))) * T(acc1))     (hf MistralMLP)
     DSE_LOGITS = 4,       // y(float) = float(T(acc)); per-CTA argmax candidate  (lm_head, logits leave it in T)
 };
@@ -63,21 +65,21 @@ struct DsOp {
     int nmat, N, K;        // N rows per matrix
     int R, P;              // slot rows (both matrices together), parts per row; R * P == kDsGroupWarps
     int pro, epi;
-    const void* x;         // [NV][x_stride] model dtype (ignored for DSP_EMBED_RMSNORM)
-    long long x_stride;
+    const unsigned long long* xll;   // [NV][xll_stride] tagged words, two elements each: the input vector as the previous op
+    long long xll_stride;            // published it (ignored for DSP_EMBED_RMSNORM)
     const void* nw;        // RMSNorm weight
     float eps;
-    void* y;               // [NV][y_stride] (T, or float for DSE_LOGITS)
-    long long y_stride;
-    void* resid;           // [NV][resid_stride]
-    long long resid_stride;
+    unsigned long long* yll;         // [NV][yll_stride] tagged words: what this op publishes (not DSE_LOGITS)
+    long long yll_stride;
+    float* logits;         // DSE_LOGITS: [NV][logits_stride] fp32
+    long long logits_stride;
     // ---- DS_ATTN
-    const void* qkv;       // [NV][qkv_stride]: q (Hq*D) | k (Hk*D) | v (Hk*D) of the new token, before RoPE
-    long long qkv_stride;
+    const unsigned long long* qkv_ll;   // [NV][qkv_ll_stride] tagged words: q (Hq*D) | k (Hk*D) | v (Hk*D) of the new token, before RoPE
+    long long qkv_ll_stride;
+    unsigned long long* att_ll;         // [NV][Hq*D/2] tagged words: the attention output
     void* kc;              // K cache of this layer: [n_streams][Hk][max_ctx][D]
     void* vc;
     long long kv_stream_stride;   // elements between the caches of consecutive streams
-    void* att;             // [NV][Hq*D]
     int Hq, Hk, max_ctx;
     float rope_theta, scale_log2e;
 };
@@ -100,20 +102,19 @@ struct DsParams {
     int xcap;                // elements per staged vector (max K over the ops, multiple of 8)
     int x_bytes;             // bytes of the staging region: max(NV * xcap * 2, attention scratch)
     int part_cap;            // floats in the partial-sum area
-    unsigned* sync;          // [0] grid-barrier counter, [1] epoch (steps run since reset), [2] all-done flag, [8..] per (pass, lane, kv head) arrival counters
-    int n_barriers;          // grid barriers per step
+    unsigned* sync;          // [1] epoch (steps run since the handle was created: never reset, the exchange tags derive from it), [2] all-done flag
     DsStreamState* st;       // [NV]
     int* out_ids;            // [NV][out_stride]
     int out_stride;
     const int* stop;         // [0] = count, then ids
     const void* embed;       // [vocab][H]
     int H;
-    float* att_part;         // [NV][Hq][S][D + 2] split-KV partials
-    float* cand_val;         // [NV][gridDim.x] per-CTA argmax candidates
-    int* cand_idx;
+    unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
+    unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
     int l2_ahead;            // chunks the L2 prefetch cursor runs ahead of the ring (even; 0 = off)
-    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 skip grid barriers, 4 skip the attention body, 8 no L2 prefetch
-    long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue, 1 ring compute, 2 epilogue, 3 barrier, 4 attention, 5 final, 6 wait for an op's first chunk, 7 wait for later chunks)
+    int max_inflight;        // bulk copies of this CTA that may be in flight at once (0 = as many as the ring has free slots)
+    int dbg_flags;           // measurement only: 1 skip the consumer math, 8 no L2 prefetch
+    long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
 
 __device__ __forceinline__ void ds_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -156,23 +157,45 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void ds_consumer_sync() { named_bar_sync(1, kDsConsumerThreads); }
 
-// Grid barrier of the consumer side (thread 0 of every CTA arrives and polls; bounded spin so that a logic error traps
-// instead of hanging the box).  All CTAs are co-resident: the launch uses one CTA per SM.
-__device__ __forceinline__ void ds_grid_barrier(unsigned* ctr, unsigned target, bool skip = false) {
-    if (skip) { ds_consumer_sync(); return; }
-    // The CTA barrier orders every consumer thread's global writes before thread 0's release (release is cumulative);
-    // the acquire on the other side is ordered before the other threads' reads by the second CTA barrier.  Data written by
-    // other CTAs is read with ld.global.cg (L2), never through a possibly stale L1 line.
-    ds_consumer_sync();
-    if (threadIdx.x == 0) {
-        ds_red_release(ctr, 1u);
-        unsigned spins = 0;
-        while (static_cast<int>(ds_ld_acquire(ctr) - target) < 0) {
-            if (++spins > (1u << 25)) { printf("smb: decode grid barrier timeout (cta %d, target %u)\n", blockIdx.x, target); __trap(); }
-        }
-    }
-    ds_consumer_sync();
+// ---- activation exchange between CTAs: tagged 8-byte words ("LL" protocol).
+// Every value a later op needs from other CTAs travels as ONE naturally aligned 64-bit store: 32 bits of payload (two
+// model-dtype elements, or one fp32 / int) + a 32-bit tag that names (decode step, producing op).  A 64-bit scalar access
+// is single-copy atomic, so a reader that sees the tag it expects has the payload of that very store: no fence, no
+// counter, no grid barrier -- the consumer polls the words it needs and the gap between two ops is one store transit
+// plus one L2 read instead of [fence, atomic, poll round trips, then the read].  Why a buffer can be re-used by the same
+// op of the next layer without further handshakes: a CTA reads op k's output only in an op in which it also produces
+// something that every CTA's next op consumes, so nobody reaches op k + 2 (let alone k + 5) before all readers are done.
+__device__ __forceinline__ void ds_ll_store(unsigned long long* p, uint32_t payload, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((static_cast<unsigned long long>(tag) << 32) | payload) : "memory");
 }
+__device__ __forceinline__ unsigned long long ds_ll_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// two adjacent words with one 16-byte request (each 64-bit half is its own atomic access: both tags are checked)
+__device__ __forceinline__ void ds_ll_load2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// poll until the word carries `tag` (r = a first load already issued); bounded, so that a protocol error traps instead of hanging the box
+__device__ __forceinline__ uint32_t ds_ll_wait(const unsigned long long* p, unsigned long long r, uint32_t tag) {
+    unsigned spins = 0;
+    while (static_cast<uint32_t>(r >> 32) != tag) {
+        if (++spins > (1u << 21)) { printf("smb: decode exchange timeout (cta %d thread %d, tag %u, found %u)\n", blockIdx.x, threadIdx.x, tag, static_cast<uint32_t>(r >> 32)); __trap(); }
+        r = ds_ll_load(p);
+    }
+    return static_cast<uint32_t>(r);
+}
+// one round of a batched poll failed: back off briefly (pollers share the L2 ports with the weight stream); bounded
+__device__ unsigned ds_poll_ns = 20;
+__device__ __forceinline__ void ds_ll_retry(unsigned& spins, uint32_t tag) {
+    __nanosleep(ds_poll_ns);
+    if (++spins > (1u << 21)) { printf("smb: decode exchange timeout (cta %d thread %d, tag %u)\n", blockIdx.x, threadIdx.x, tag); __trap(); }
+}
+__device__ __forceinline__ bool ds_ll_ok(unsigned long long r, uint32_t tag) { return static_cast<uint32_t>(r >> 32) == tag; }
+__device__ __forceinline__ uint32_t ds_ll_get(const unsigned long long* p, uint32_t tag) { return ds_ll_wait(p, ds_ll_load(p), tag); }
+// rows per CTA of a GEMV op: even, so that a CTA's outputs are whole two-element words
+__host__ __device__ __forceinline__ int ds_rows_per_cta(int N, int G) { return (((N + G - 1) / G) + 1) & ~1; }
 
 template <typename T>
 __device__ __forceinline__ float ds_dot8(const uint4& w, const uint4& xv, float s) {
@@ -206,6 +229,414 @@ __device__ __forceinline__ T ds_ldcg_t(const T* p) {
     return t;
 }
 
+// The attention op of the decode kernel.  Register discipline matters here: if the kernel spills anywhere, ptxas schedules the
+// WHOLE kernel for low register use and pairs every shared-memory load of the weight-streaming loop with its MMA (the loop
+// then runs at load latency: +30 % per step, measured).  So the projection's words are polled one at a time into shared
+// memory while the K / V rows of the first block (64 registers) are in flight, not held in registers next to them.
+template <typename T, int NV>
+__device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamState* st, unsigned long long* att_part, T* xs,
+                                            uint32_t tag_in, uint32_t tag_out) {
+    const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, cta = blockIdx.x;
+    // ------------------------------------------------------------------ decode attention, split over the KV length
+    // Every dependent global access costs ~2 us while the weight stream saturates HBM, so the op is arranged as few
+    // dependent rounds as possible: (1) q / new k / new v (polled from the projection's exchange words) AND this
+    // warp's K rows AND its V rows (asked into L2 one op earlier) are requested together; (2) RoPE, scores, softmax,
+    // P.V from registers / shared memory; (3) the slice's partial is published as tagged words; (4) the CTA of slice 0
+    // of a (lane, kv head) polls all slices and merges them in fixed order: no counter, no fence, no grid barrier.
+    constexpr int D = 128, VPL = 4, KB = 16, GM = 4;   // GM query heads per pass (GQA groups of 8: two passes)              // KB keys per warp block: lane pair = key, lane = 4 output dims
+    const int Hq = op.Hq, Hk = op.Hk, group = Hq / Hk;
+    const int S = max(1, G / Hk);                        // KV slices per (lane, kv head): independent of NV, so a stream's
+                                                         // arithmetic (and ids) do not depend on what it is batched with
+    float* sm_q = reinterpret_cast<float*>(xs);           // [group][D] rotated q heads of the group (fp32 values of T)
+    float* sm_kn = sm_q + group * D;                      // [D] rotated new k
+    float* sm_vn = sm_kn + D;                             // [D] new v
+    float* sm_cs = sm_vn + D;                             // [D/2] cos, [D/2] sin
+    float* sm_m = sm_cs + D;                              // [8][8]
+    float* sm_l = sm_m + kDsGroupWarps * 8;
+    float* sm_o = sm_l + kDsGroupWarps * 8;               // [8][group][D]
+    float* sm_p = sm_o + kDsGroupWarps * group * D + warp * group * KB;   // this warp's [group][KB] probabilities of a key block
+    float* sm_raw = sm_o + kDsGroupWarps * group * D + kDsConsumerWarps * group * KB;   // [(group + 2) D] q heads | k | v of this kv head as projected
+    for (int item = cta; item < NV * Hk * S; item += G) {
+        const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
+        const int pos = st[v].pos, kv_len = pos + 1;
+        const int slot_kv = st[v].kv_slot;
+        const unsigned long long* ql = op.qkv_ll + v * op.qkv_ll_stride;
+        T* kcache = reinterpret_cast<T*>(op.kc) + slot_kv * op.kv_stream_stride + static_cast<long long>(hk) * op.max_ctx * D;
+        T* vcache = reinterpret_cast<T*>(op.vc) + slot_kv * op.kv_stream_stride + static_cast<long long>(hk) * op.max_ctx * D;
+        const int per = (kv_len + S - 1) / S;
+        const int kbeg = s * per, kend = min(kv_len, kbeg + per);
+        const int half = lane & 1, kslot = lane >> 1;        // this lane scores dims [64 half, 64 half + 64) of key kb0 + kslot
+        // ---- round 1: everything that does not depend on anything else is requested now
+        uint4 kreg[D / 16];                                 // half a K row (64 dims) of this lane's key
+        uint2 vreg[KB];                                     // V (this lane's 4 dims) of the block's keys
+        const int kb_first = kbeg + warp * KB;
+        auto load_block = [&](int kb0) {
+            const int key = kb0 + kslot;
+            if (key < kend && key != pos) {
+                const uint4* krow = reinterpret_cast<const uint4*>(kcache + static_cast<long long>(key) * D + half * (D / 2));
+#pragma unroll
+                for (int c = 0; c < D / 16; ++c) kreg[c] = krow[c];
+            }
+#pragma unroll
+            for (int b = 0; b < KB; ++b) {
+                const int kk = kb0 + b;
+                if (kk < kend && kk != pos) vreg[b] = *reinterpret_cast<const uint2*>(vcache + static_cast<long long>(kk) * D + lane * VPL);
+            }
+        };
+        load_block(kb_first);
+        // poll the projection's words of this kv head (q heads | k | v: (group + 2) D / 2 words) into shared memory
+        for (int w = tid; w < (group + 2) * (D / 2); w += kDsConsumerThreads) {
+            const int hh = w / (D / 2), d2 = w % (D / 2);
+            const int src = (hh < group ? (hk * group + hh) * D : hh == group ? (Hq + hk) * D : (Hq + Hk + hk) * D) / 2 + d2;
+            const float2 f = Cvt<T>::unpack2(ds_ll_get(ql + src, tag_in));
+            sm_raw[2 * w] = f.x;
+            sm_raw[2 * w + 1] = f.y;
+        }
+        // RoPE tables for this position (hf MistralRotaryEmbedding: fp32 angle, cos / sin cast to T)
+        if (tid < D / 2) {
+            const float inv = powf(op.rope_theta, -2.0f * tid / D);
+            float sn, cs;
+            sincosf(pos * inv, &sn, &cs);
+            sm_cs[tid] = rnd<T>(cs);
+            sm_cs[D / 2 + tid] = rnd<T>(sn);
+        }
+        ds_consumer_sync();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kDsConsumerThreads;
+            if (i < (group + 1) * (D / 2)) {
+                const int hh = i / (D / 2), d = i % (D / 2);
+                const float cs = sm_cs[d], sn = sm_cs[D / 2 + d];
+                const float x1 = sm_raw[hh * D + d], x2 = sm_raw[hh * D + d + D / 2];
+                float* dst = hh < group ? sm_q + hh * D : sm_kn;
+                dst[d] = rnd<T>(rnd<T>(x1 * cs) + rnd<T>(-x2 * sn));
+                dst[d + D / 2] = rnd<T>(rnd<T>(x2 * cs) + rnd<T>(x1 * sn));
+            }
+        }
+        if (tid < D) sm_vn[tid] = sm_raw[(group + 1) * D + tid];
+        ds_consumer_sync();
+        if (kbeg <= pos && pos < kend && tid < D) {          // the slice holding the new position appends it
+            kcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_kn[tid]);
+            vcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_vn[tid]);
+        }
+        for (int gb = 0; gb < group; gb += GM) {
+        if (gb > 0) { ds_consumer_sync(); load_block(kb_first); }     // second pass of a wide GQA group re-reads K / V
+        // ---- round 2: per warp, blocks of KB keys.  Scores: a lane pair owns a key (64 dims each against the group's
+        // q heads broadcast from shared memory, one shuffle per head); block-wise online softmax (one warp_max per
+        // head per block); P.V: lane = 4 output dims, probabilities broadcast from shared memory.
+        float mx[GM], l[GM], o[GM][VPL];
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+            mx[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) o[g][i] = 0.f;
+        }
+        for (int kb0 = kb_first; kb0 < kend; kb0 += kDsConsumerWarps * KB) {
+            if (kb0 != kb_first) load_block(kb0);     // slices longer than 16 warps x 16 keys (ctx > 4.6k): next round
+            const int key = kb0 + kslot;
+            const bool valid = key < kend;
+            float sc[GM];
+#pragma unroll
+            for (int g = 0; g < GM; ++g) sc[g] = 0.f;
+            if (valid && key != pos) {
+#pragma unroll
+                for (int c = 0; c < D / 16; ++c) {
+                    const uint4 u = kreg[c];
+                    const float2 k0 = Cvt<T>::unpack2(u.x), k1 = Cvt<T>::unpack2(u.y), k2 = Cvt<T>::unpack2(u.z), k3 = Cvt<T>::unpack2(u.w);
+#pragma unroll
+                    for (int g = 0; g < GM; ++g) {
+                        if (gb + g < group) {
+                            const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8);
+                            const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8 + 4);
+                            float t = sc[g];
+                            t = fmaf(qa.x, k0.x, t); t = fmaf(qa.y, k0.y, t); t = fmaf(qa.z, k1.x, t); t = fmaf(qa.w, k1.y, t);
+                            t = fmaf(qb.x, k2.x, t); t = fmaf(qb.y, k2.y, t); t = fmaf(qb.z, k3.x, t); t = fmaf(qb.w, k3.y, t);
+                            sc[g] = t;
+                        }
+                    }
+                }
+            } else if (valid) {                      // the new token: its k is still in shared memory
+                for (int d = half * (D / 2); d < (half + 1) * (D / 2); ++d) {
+                    const float kd = sm_kn[d];
+#pragma unroll
+                    for (int g = 0; g < GM; ++g)
+                        if (gb + g < group) sc[g] = fmaf(sm_q[(gb + g) * D + d], kd, sc[g]);
+                }
+            }
+            float cfac[GM];
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (gb + g < group) {
+                    const float full = sc[g] + __shfl_xor_sync(0xffffffffu, sc[g], 1);   // both halves of the key
+                    const float sv = valid ? full * op.scale_log2e : -INFINITY;
+                    const float mn = fmaxf(mx[g], warp_max(sv));
+                    cfac[g] = exp2f(mx[g] - mn);                              // 0 for the first block (mx = -inf)
+                    const float pr = valid ? rnd<T>(exp2f(sv - mn)) : 0.f;    // P is rounded to T before it multiplies V
+                    l[g] = l[g] * cfac[g] + (half == 0 ? pr : 0.f);           // lane-local partial of the row sum
+                    if (half == 0) sm_p[g * KB + kslot] = pr;
+                    mx[g] = mn;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < GM; ++g)
+                if (gb + g < group) {
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) o[g][i] *= cfac[g];
+                }
+#pragma unroll
+            for (int b = 0; b < KB; ++b) {
+                const int kk = kb0 + b;
+                if (kk < kend) {
+                    float vv[VPL];
+                    if (kk == pos) {
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) vv[i] = sm_vn[lane * VPL + i];
+                    } else {
+                        const float2 a = Cvt<T>::unpack2(vreg[b].x), bb = Cvt<T>::unpack2(vreg[b].y);
+                        vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
+                    }
+#pragma unroll
+                    for (int g = 0; g < GM; ++g)
+                        if (gb + g < group) {
+                            const float pr = sm_p[g * KB + b];
+#pragma unroll
+                            for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(pr, vv[i], o[g][i]);
+                        }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < GM; ++g)
+            if (gb + g < group) l[g] = warp_sum(l[g]);
+        // ---- round 3: merge the warps in fixed order (upper half into lower half, then across the 8), write this
+        // slice's partial, count the arrival
+        const int w8 = warp & (kDsGroupWarps - 1);
+        if (kDsGroups > 1 && warp >= kDsGroupWarps) {
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (gb + g < group) {
+                    if (lane == 0) { sm_m[w8 * 8 + g] = mx[g]; sm_l[w8 * 8 + g] = l[g]; }
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) sm_o[(w8 * group + g) * D + lane * VPL + i] = o[g][i];
+                }
+            }
+        }
+        if (kDsGroups > 1) ds_consumer_sync();
+        if (warp < kDsGroupWarps) {
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (kDsGroups > 1 && gb + g < group) {
+                    const float pm = sm_m[w8 * 8 + g], pl = sm_l[w8 * 8 + g];
+                    const float mn = fmaxf(mx[g], pm);
+                    const float c0 = mx[g] == -INFINITY ? 0.f : exp2f(mx[g] - mn), c1 = pm == -INFINITY ? 0.f : exp2f(pm - mn);
+                    l[g] = l[g] * c0 + pl * c1;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) o[g][i] = o[g][i] * c0 + sm_o[(w8 * group + g) * D + lane * VPL + i] * c1;
+                    mx[g] = mn;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                if (gb + g < group) {
+                    if (lane == 0) { sm_m[w8 * 8 + g] = mx[g]; sm_l[w8 * 8 + g] = l[g]; }
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) sm_o[(w8 * group + g) * D + lane * VPL + i] = o[g][i];
+                }
+            }
+        }
+        ds_consumer_sync();
+        unsigned long long* pbase = att_part + (static_cast<long long>(v) * Hq + hk * group) * S * (D + 2);
+        const int npass = min(GM, group - gb);
+        for (int idx = tid; idx < npass * D; idx += kDsConsumerThreads) {
+            const int g = idx / D, d = idx % D;
+            float mm = -INFINITY;
+            for (int w = 0; w < kDsGroupWarps; ++w) mm = fmaxf(mm, sm_m[w * 8 + g]);
+            float ll = 0.f, oo = 0.f;
+            for (int w = 0; w < kDsGroupWarps; ++w) {
+                const float c = sm_m[w * 8 + g] == -INFINITY ? 0.f : exp2f(sm_m[w * 8 + g] - mm);
+                ll += sm_l[w * 8 + g] * c;
+                oo += sm_o[(w * group + g) * D + d] * c;
+            }
+            unsigned long long* dst = pbase + (static_cast<long long>(gb + g) * S + s) * (D + 2);
+            ds_ll_store(dst + 2 + d, __float_as_uint(oo), tag_out);
+            if (d == 0) { ds_ll_store(dst, __float_as_uint(mm), tag_out); ds_ll_store(dst + 1, __float_as_uint(ll), tag_out); }
+        }
+        ds_consumer_sync();      // the scratch is rewritten by the next pass / item / op
+        }   // gb
+    }
+    // ---- round 4: the S CTAs of a (lane, kv head) share the merge: CTA s takes output pairs [s cnt, (s + 1) cnt) of the
+    // group's heads, polls their partials of ALL slices in one round (a thread per (pair, slice)), then one thread
+    // per pair folds the slices in fixed order and publishes the word
+    {
+        const int npair = group * (D / 2), cnt = (npair + S - 1) / S;
+        float4* sm_mg = reinterpret_cast<float4*>(sm_o);                 // [cnt][S] (m, l, o0, o1)
+        for (int item = cta; item < NV * Hk * S; item += G) {
+            const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
+            const int p0 = s * cnt, p1 = min(npair, p0 + cnt);
+            const unsigned long long* pbase = att_part + (static_cast<long long>(v) * Hq + hk * group) * S * (D + 2);
+            constexpr int UM = 1;
+            for (int i0 = tid; i0 < (p1 - p0) * S; i0 += UM * kDsConsumerThreads) {
+                unsigned long long r[UM][4];
+                const unsigned long long* q[UM];
+                int dp2[UM];
+#pragma unroll
+                for (int u = 0; u < UM; ++u) {
+                    const int i = i0 + u * kDsConsumerThreads;
+                    q[u] = pbase; dp2[u] = 0;
+                    if (i < (p1 - p0) * S) {
+                        const int pr = p0 + i / S, z = i % S, g = pr / (D / 2);
+                        dp2[u] = 2 * (pr % (D / 2));
+                        q[u] = pbase + (static_cast<long long>(g) * S + z) * (D + 2);
+                    }
+                }
+                unsigned spins = 0;
+                for (bool ok = false; !ok;) {
+#pragma unroll
+                    for (int u = 0; u < UM; ++u)
+                        if (i0 + u * kDsConsumerThreads < (p1 - p0) * S) {
+                            ds_ll_load2(q[u], r[u][0], r[u][1]);
+                            ds_ll_load2(q[u] + 2 + dp2[u], r[u][2], r[u][3]);
+                        }
+                    ok = true;
+#pragma unroll
+                    for (int u = 0; u < UM; ++u)
+                        if (i0 + u * kDsConsumerThreads < (p1 - p0) * S)
+                            ok = ok && ds_ll_ok(r[u][0], tag_out) && ds_ll_ok(r[u][1], tag_out) && ds_ll_ok(r[u][2], tag_out) && ds_ll_ok(r[u][3], tag_out);
+                    if (!ok) ds_ll_retry(spins, tag_out);
+                }
+#pragma unroll
+                for (int u = 0; u < UM; ++u) {
+                    const int i = i0 + u * kDsConsumerThreads;
+                    if (i < (p1 - p0) * S)
+                        sm_mg[i] = make_float4(__uint_as_float(static_cast<uint32_t>(r[u][0])), __uint_as_float(static_cast<uint32_t>(r[u][1])),
+                                               __uint_as_float(static_cast<uint32_t>(r[u][2])), __uint_as_float(static_cast<uint32_t>(r[u][3])));
+                }
+            }
+            ds_consumer_sync();
+            if (tid < p1 - p0) {
+                const int pr = p0 + tid, g = pr / (D / 2), dp = pr % (D / 2);
+                float mm = -INFINITY, ll = 0.f, o0 = 0.f, o1 = 0.f;
+                for (int z = 0; z < S; ++z) {
+                    const float4 t = sm_mg[tid * S + z];
+                    if (t.x != -INFINITY) {
+                        const float mn = fmaxf(mm, t.x);
+                        const float c0 = exp2f(mm - mn), c1 = exp2f(t.x - mn);     // c0 = 0 while mm = -inf
+                        ll = ll * c0 + t.y * c1;
+                        o0 = o0 * c0 + t.z * c1;
+                        o1 = o1 * c0 + t.w * c1;
+                        mm = mn;
+                    }
+                }
+                ds_ll_store(op.att_ll + static_cast<long long>(v) * (Hq * D / 2) + (hk * group + g) * (D / 2) + dp, Cvt<T>::pack2(o0 / ll, o1 / ll), tag_out);
+            }
+            ds_consumer_sync();      // the scratch is rewritten by the next item / op
+        }
+    }
+}
+
+struct DsRingState { int seq, slot, par; };   // chunk sequence number of this CTA, its ring slot and the parity of that slot's use
+
+// The weight-streaming phase of a GEMV op.
+template <typename T, int NV>
+__device__ __forceinline__ void ds_ring_phase(const DsOp& op, uint64_t* full_bar, uint64_t* empty_bar, int n_slots, int x_bytes, int xcap,
+                                          int dbg_flags, int j0, int j1, DsRingState* state) {
+    extern __shared__ __align__(128) uint8_t ds_smem[];            // same carve-up as the kernel: ring | staged vectors | partial sums
+    const uint8_t* ring = ds_smem;
+    const T* xs = reinterpret_cast<const T*>(ds_smem + static_cast<size_t>(n_slots) * kDsSlotBytes);
+    float* part = reinterpret_cast<float*>(ds_smem + static_cast<size_t>(n_slots) * kDsSlotBytes + x_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = op.K, nloc = j1 - j0;
+    DsRingState rs = *state;
+    // ---- stream this CTA's rows through the ring
+    const int RJ = op.R / op.nmat, P = op.P;
+    const int grp = warp / kDsGroupWarps, wg = warp - grp * kDsGroupWarps;   // consumer group and warp within it
+    const int sr = wg / P, pt = wg - sr * P;                   // slot row and part of this warp
+    const int m = sr / RJ, jr = sr - m * RJ;                   // matrix and row within the chunk
+    const int cols = K / P, c0 = pt * cols;
+    // The reduction runs on the tensor cores (mma.sync m16n8k16, fp32 accumulate) with a "diagonal" arrangement: the B
+    // operand's 8 columns are 8 consecutive 16-weight segments of ONE weight row (256 contiguous bytes: lane l reads
+    // bytes [8 l, 8 l + 8), conflict-free), the A operand's rows 0..7 are the matching 16-element segments of vector 0
+    // (rows 8..15: vector 1), so D[m][m] accumulates sum_k w[16 m + k] x[16 m + k]; off-diagonal products are discarded.
+    // A slot costs 128 HMMA + 256 LDS.64 instead of ~1100 FMA / unpack / LDS, and a second stream rides along for free.
+    // Measured (tools/decode_probe.py, profiles/r02_decode_kernel.md): this drains a slot in ~800 clk -- about the rate
+    // HBM delivers -- because legacy HMMA on sm_100 issues one m16n8k16 per ~26 clk per sub-partition; an fp32-FMA
+    // consumer with the vector in registers is equally issue-bound, and running both pipes side by side did not beat
+    // either.  Per (row, part): two accumulators (even / odd blocks), one butterfly of the 8 diagonal elements;
+    // partials over the parts are summed in FIXED order by the epilogue.
+    const int nblk = cols / 128;                                   // 128-weight blocks of this warp's part (even)
+    constexpr int NPAIR = (NV + 1) / 2;                            // A operands: vectors (2 q, 2 q + 1) on rows (0..7, 8..15)
+    const bool diag0 = (lane >> 2) == 2 * (lane & 3), diag1 = (lane >> 2) == 2 * (lane & 3) + 1;   // this lane holds D[g][g] in c0 / c1
+    const uint2* xp = reinterpret_cast<const uint2*>(xs + c0) + lane;   // block b of vector v: xp[v * xq + 32 b]
+    const int xq = xcap / 4;
+    // The hot loop is kept branch-free and division-free (ncu, profiles/r02_decode_kernel.md: an earlier form with a
+    // guard per block executed ~3700 warp instructions per 32 KB slot, 22 % of them mbarrier polls): blocks go in
+    // unguarded batches of 8 and 2 (nblk is even), the ring position advances incrementally.
+    const uint2* ring_u2 = reinterpret_cast<const uint2*>(ring) + (static_cast<size_t>(sr) * K + c0) / 4 + lane;
+    float* part_w = part + (static_cast<size_t>(m) * nloc * P + pt) * NV;           // + local row * P * NV
+    const int skip_math = dbg_flags & 1;
+    for (int j = j0; j < j1; j += RJ, ++rs.seq) {
+        const int slot = rs.slot, par = rs.par;
+        if (++rs.slot == n_slots) { rs.slot = 0; rs.par ^= 1; }
+        if (kDsGroups > 1 && rs.seq % kDsGroups != grp) continue;
+        mbar_wait_hint(&full_bar[slot], par);
+        if (j + jr < j1 && !skip_math) {
+            const uint2* wp = ring_u2 + slot * (kDsSlotBytes / 8);
+            float acc[NPAIR][2][4];
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { acc[q][e][0] = 0.f; acc[q][e][1] = 0.f; acc[q][e][2] = 0.f; acc[q][e][3] = 0.f; }
+            int b = 0;
+            for (; b + 8 <= nblk; b += 8) {                  // 8 blocks per batch: all their loads in flight together
+                uint2 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = *(wp + (b + u) * 32);
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    uint2 xa[8], xb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        xa[u] = *(xp + (2 * q) * xq + (b + u) * 32);
+                        xb[u] = 2 * q + 1 < NV ? *(xp + (2 * q + 1) * xq + (b + u) * 32) : make_uint2(0u, 0u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ds_mma_16816<T>(acc[q][u & 1], xa[u].x, xb[u].x, xa[u].y, xb[u].y, w[u].x, w[u].y);
+                }
+            }
+            for (; b < nblk; b += 2) {
+                const uint2 w0 = *(wp + b * 32), w1 = *(wp + b * 32 + 32);
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    const uint2 xa0 = *(xp + (2 * q) * xq + b * 32), xa1 = *(xp + (2 * q) * xq + b * 32 + 32);
+                    uint2 xb0 = make_uint2(0u, 0u), xb1 = make_uint2(0u, 0u);
+                    if (2 * q + 1 < NV) { xb0 = *(xp + (2 * q + 1) * xq + b * 32); xb1 = *(xp + (2 * q + 1) * xq + b * 32 + 32); }
+                    ds_mma_16816<T>(acc[q][0], xa0.x, xb0.x, xa0.y, xb0.y, w0.x, w0.y);
+                    ds_mma_16816<T>(acc[q][1], xa1.x, xb1.x, xa1.y, xb1.y, w1.x, w1.y);
+                }
+            }
+            float tot[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int q = v >> 1, o = (v & 1) * 2;
+                const float d0 = acc[q][0][o] + acc[q][1][o], d1 = acc[q][0][o + 1] + acc[q][1][o + 1];
+                tot[v] = warp_sum(diag0 ? d0 : diag1 ? d1 : 0.f);
+            }
+            if (lane == 0) {
+                float* dst = part_w + static_cast<size_t>(j - j0 + jr) * P * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) dst[v] = tot[v];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+    }
+    *state = rs;
+}
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsParams p) {
     extern __shared__ __align__(128) uint8_t ds_smem[];
@@ -216,7 +647,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
     __shared__ float red[kDsConsumerWarps * NV];
     __shared__ float cand_v[kDsConsumerWarps];
     __shared__ int cand_i[kDsConsumerWarps];
-    __shared__ int flag_last;
+    __shared__ float resid_own[NV][kDsResidRows];      // this CTA's rows of the residual stream (values of T)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -240,7 +671,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
             for (; c.oi < p.n_ops; ++c.oi) {
                 const DsOp& op = p.ops[c.oi];
                 if (op.type != DS_GEMV) continue;
-                const int rpc = (op.N + G - 1) / G;
+                const int rpc = ds_rows_per_cta(op.N, G);
                 c.j = min(op.N, cta * rpc); c.j1 = min(op.N, c.j + rpc); c.RJ = op.R / op.nmat;
                 if (c.j < c.j1) return;
             }
@@ -271,6 +702,13 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                 const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
                 const int slot = cur.seq % p.n_slots, use = cur.seq / p.n_slots;
                 if (use > 0) mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
+                if (p.max_inflight > 0 && cur.seq >= p.max_inflight) {
+                    // Bound the requests queued in the memory system: every byte in flight beyond bandwidth x latency only
+                    // lengthens the queue that the latency-critical accesses of the consumers (activations, barrier flags)
+                    // wait in.  Chunk seq is issued once chunk seq - max_inflight has landed.
+                    const int ps = cur.seq - p.max_inflight;
+                    mbar_wait_hint(&full_bar[ps % p.n_slots], (ps / p.n_slots) & 1);
+                }
                 const int nr = min(cur.RJ, cur.j1 - cur.j);
                 const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
                 mbar_arrive_expect_tx(&full_bar[slot], bytes * op.nmat);
@@ -287,42 +725,114 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
 
     // ====================================================================== consumers
     const int tid = threadIdx.x;                      // 0 .. kDsConsumerThreads-1
-    const bool timed = p.dbg != nullptr && cta == 0 && tid == 0;
-    long long t_last = timed ? ds_gtimer() : 0;
-    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // accumulated in registers (a global read-modify-write per stamp would dominate)
+    const bool timed = p.dbg != nullptr && tid == 0;        // every CTA keeps its own phase clock: rows 8 (cta + 1) .. of the buffer; CTA 0 also rows 0..7
+    // phase clocks: 32-bit ns, accumulated in registers (a global read-modify-write per stamp would dominate); categories 0, 1, 2, 4
+    unsigned t_last = timed ? static_cast<unsigned>(ds_gtimer()) : 0u;
+    unsigned t_acc[4] = {0u, 0u, 0u, 0u};
     auto stamp = [&](int cat) {
         if (timed) {
-            const long long t = ds_gtimer();
+            const unsigned t = static_cast<unsigned>(ds_gtimer());
+            const int ci = cat == 4 ? 3 : cat;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) t_acc[c] += c == cat ? t - t_last : 0;
+            for (int c = 0; c < 4; ++c) t_acc[c] += c == ci ? t - t_last : 0u;
             t_last = t;
         }
     };
-    unsigned bar_target = epoch * static_cast<unsigned>(p.n_barriers) * G;
-    int seq = 0, ring_slot = 0, ring_par = 0;            // chunk sequence number, its ring slot and the parity of that slot's use
+    {   // the residual stream starts as the embedding of the token fed (hf MistralModel: inputs_embeds = embed_tokens(ids))
+        const int rpcH = ds_rows_per_cta(p.H, G), h0 = min(p.H, cta * rpcH), hn = min(p.H, h0 + rpcH) - h0;
+        for (int i = tid; i < NV * hn; i += kDsConsumerThreads) {
+            const int v = i / hn, r = i - v * hn;
+            resid_own[v][r] = Cvt<T>::to_f((reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(p.st[v].tok) * p.H)[h0 + r]);
+        }
+    }
+    // tag of what op oi publishes in this step (never 0: a buffer that was never written cannot match)
+    const uint32_t tag0 = epoch * static_cast<uint32_t>(p.n_ops + 1) + 1u;
+    auto tag_of = [&](int oi) { return (tag0 + static_cast<uint32_t>(oi)) | 0x80000000u; };
+    DsRingState rs{0, 0, 0};
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const DsOp& op = p.ops[oi];
         if (op.type == DS_GEMV) {
             const int K = op.K;
-            // ---- prologue: stage pro(x_v) for every stream
+            const int rpc = ds_rows_per_cta(op.N, G);
+            const int j0 = min(op.N, cta * rpc), j1 = min(op.N, j0 + rpc);
+            const int nloc = j1 - j0;
+            if (oi + 1 < p.n_ops && p.ops[oi + 1].type == DS_ATTN && tid == 0) {
+                // The K / V rows the attention op after this projection will read do not depend on it: ask L2 for this CTA's
+                // slices now, so that they arrive under the weight stream instead of behind it.
+                const DsOp& an = p.ops[oi + 1];
+                const int S = max(1, G / an.Hk);
+                for (int item = cta; item < NV * an.Hk * S; item += G) {
+                    const int v = item / (an.Hk * S), hk = (item / S) % an.Hk, sl = item % S;
+                    const int pos = p.st[v].pos, per = (pos + 1 + S - 1) / S;
+                    const int kbeg = sl * per, kend = min(pos, kbeg + per);          // cached keys only (position pos is appended by the op)
+                    if (kend > kbeg) {
+                        const long long off = p.st[v].kv_slot * an.kv_stream_stride + (static_cast<long long>(hk) * an.max_ctx + kbeg) * 128;
+                        const uint32_t bytes = static_cast<uint32_t>(kend - kbeg) * 128u * static_cast<uint32_t>(sizeof(T));
+                        ds_prefetch_l2(reinterpret_cast<const T*>(an.kc) + off, bytes);
+                        ds_prefetch_l2(reinterpret_cast<const T*>(an.vc) + off, bytes);
+                    }
+                }
+            }
+            if (nloc == 0) continue;          // no rows of this op: nothing to read, nothing to publish (the producers skip it too)
+            const uint32_t tag_in = tag_of(oi - 1), tag_out = tag_of(oi);
+            // ---- prologue: stage pro(x_v) for every stream; x_v is polled word by word from the previous op's exchange buffer
 #pragma unroll 1
             for (int v = 0; v < NV; ++v) {
-                const T* x0 = op.pro == DSP_EMBED_RMSNORM
-                                  ? reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(p.st[v].tok) * p.H
-                                  : reinterpret_cast<const T*>(op.x) + v * op.x_stride;
                 T* xv = xs + static_cast<size_t>(v) * p.xcap;
-                if (op.pro == DSP_PLAIN) {
-                    for (int k = tid * 8; k < K; k += kDsConsumerThreads * 8)
-                        *reinterpret_cast<uint4*>(xv + k) = __ldcg(reinterpret_cast<const uint4*>(x0 + k));   // written by other CTAs: L2 only
-                } else {
-                    float s2 = 0.f;
+                float s2 = 0.f;
+                if (op.pro == DSP_EMBED_RMSNORM) {
+                    const T* x0 = reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(p.st[v].tok) * p.H;
                     for (int k = tid * 8; k < K; k += kDsConsumerThreads * 8) {
-                        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(x0 + k));
+                        const uint4 u = *reinterpret_cast<const uint4*>(x0 + k);
                         *reinterpret_cast<uint4*>(xv + k) = u;
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const float2 f = Cvt<T>::unpack2(w[i]); s2 = fmaf(f.x, f.x, s2); s2 = fmaf(f.y, f.y, s2); }
                     }
+                } else {
+                    const unsigned long long* xl = op.xll + v * op.xll_stride;
+                    uint2* xw = reinterpret_cast<uint2*>(xv);
+                    const int nq = K / 4;                                               // word pairs = 4 elements
+                    constexpr int UB = 4;                                               // 16-byte polls in flight per thread
+                    for (int q0 = tid; q0 < nq; q0 += UB * kDsConsumerThreads) {
+                        unsigned long long r[UB][2];
+                        unsigned spins = 0;
+                        {   // wait on ONE word pair first (a waiting CTA must not flood L2 with polls: they share its ports with the
+                            // weight stream), then fetch the batch -- usually complete by then
+                            const unsigned long long* sp = xl + 2 * q0;
+                            for (;;) {
+                                ds_ll_load2(sp, r[0][0], r[0][1]);
+                                if (ds_ll_ok(r[0][0], tag_in) && ds_ll_ok(r[0][1], tag_in)) break;
+                                ds_ll_retry(spins, tag_in);
+                            }
+                        }
+                        for (bool ok = false; !ok;) {           // the whole batch is polled again until every tag matches (one round trip per try)
+#pragma unroll
+                            for (int u = 0; u < UB; ++u) {
+                                const int q = q0 + u * kDsConsumerThreads;
+                                if (q < nq) ds_ll_load2(xl + 2 * q, r[u][0], r[u][1]);
+                            }
+                            ok = true;
+#pragma unroll
+                            for (int u = 0; u < UB; ++u) {
+                                const int q = q0 + u * kDsConsumerThreads;
+                                if (q < nq) ok = ok && ds_ll_ok(r[u][0], tag_in) && ds_ll_ok(r[u][1], tag_in);
+                            }
+                            if (!ok) ds_ll_retry(spins, tag_in);
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            const int q = q0 + u * kDsConsumerThreads;
+                            if (q < nq) {
+                                const uint32_t d0 = static_cast<uint32_t>(r[u][0]), d1 = static_cast<uint32_t>(r[u][1]);
+                                xw[q] = make_uint2(d0, d1);
+                                const float2 f = Cvt<T>::unpack2(d0), g = Cvt<T>::unpack2(d1);
+                                s2 = fmaf(f.x, f.x, s2); s2 = fmaf(f.y, f.y, s2); s2 = fmaf(g.x, g.x, s2); s2 = fmaf(g.y, g.y, s2);
+                            }
+                        }
+                    }
+                }
+                if (op.pro != DSP_PLAIN) {
                     s2 = warp_sum(s2);
                     if (lane == 0) red[warp * NV + v] = s2;
                 }
@@ -354,129 +864,40 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
             }
             stamp(0);
             // ---- stream this CTA's rows through the ring
-            const int rpc = (op.N + G - 1) / G;
-            const int j0 = min(op.N, cta * rpc), j1 = min(op.N, j0 + rpc);
-            const int nloc = j1 - j0;
-            const int RJ = op.R / op.nmat, P = op.P;
-            const int grp = warp / kDsGroupWarps, wg = warp - grp * kDsGroupWarps;   // consumer group and warp within it
-            const int sr = wg / P, pt = wg - sr * P;                   // slot row and part of this warp
-            const int m = sr / RJ, jr = sr - m * RJ;                   // matrix and row within the chunk
-            const int cols = K / P, c0 = pt * cols;
-            // The reduction runs on the tensor cores (mma.sync m16n8k16, fp32 accumulate) with a "diagonal" arrangement: the B
-            // operand's 8 columns are 8 consecutive 16-weight segments of ONE weight row (256 contiguous bytes: lane l reads
-            // bytes [8 l, 8 l + 8), conflict-free), the A operand's rows 0..7 are the matching 16-element segments of vector 0
-            // (rows 8..15: vector 1), so D[m][m] accumulates sum_k w[16 m + k] x[16 m + k]; off-diagonal products are discarded.
-            // A slot costs 128 HMMA + 256 LDS.64 instead of ~1100 FMA / unpack / LDS, and a second stream rides along for free.
-            // Measured (tools/decode_probe.py, profiles/r02_decode_kernel.md): this drains a slot in ~800 clk -- about the rate
-            // HBM delivers -- because legacy HMMA on sm_100 issues one m16n8k16 per ~26 clk per sub-partition; an fp32-FMA
-            // consumer with the vector in registers is equally issue-bound, and running both pipes side by side did not beat
-            // either.  Per (row, part): two accumulators (even / odd blocks), one butterfly of the 8 diagonal elements;
-            // partials over the parts are summed in FIXED order by the epilogue.
-            const int nblk = cols / 128;                                   // 128-weight blocks of this warp's part (even)
-            constexpr int NPAIR = (NV + 1) / 2;                            // A operands: vectors (2 q, 2 q + 1) on rows (0..7, 8..15)
-            const bool diag0 = (lane >> 2) == 2 * (lane & 3), diag1 = (lane >> 2) == 2 * (lane & 3) + 1;   // this lane holds D[g][g] in c0 / c1
-            const uint2* xp = reinterpret_cast<const uint2*>(xs + c0) + lane;   // block b of vector v: xp[v * xq + 32 b]
-            const int xq = p.xcap / 4;
-            // The hot loop is kept branch-free and division-free (ncu, profiles/r02_decode_kernel.md: an earlier form with a
-            // guard per block executed ~3700 warp instructions per 32 KB slot, 22 % of them mbarrier polls): blocks go in
-            // unguarded batches of 8 and 2 (nblk is even), the ring position advances incrementally.
-            const uint2* ring_u2 = reinterpret_cast<const uint2*>(ring) + (static_cast<size_t>(sr) * K + c0) / 4 + lane;
-            float* part_w = part + (static_cast<size_t>(m) * nloc * P + pt) * NV;           // + local row * P * NV
-            const int skip_math = p.dbg_flags & 1;
-            for (int j = j0; j < j1; j += RJ, ++seq) {
-                const int slot = ring_slot, par = ring_par;
-                if (++ring_slot == p.n_slots) { ring_slot = 0; ring_par ^= 1; }
-                if (kDsGroups > 1 && seq % kDsGroups != grp) continue;
-                mbar_wait_hint(&full_bar[slot], par);
-                if (j + jr < j1 && !skip_math) {
-                    const uint2* wp = ring_u2 + slot * (kDsSlotBytes / 8);
-                    float acc[NPAIR][2][4];
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) { acc[q][e][0] = 0.f; acc[q][e][1] = 0.f; acc[q][e][2] = 0.f; acc[q][e][3] = 0.f; }
-                    int b = 0;
-                    for (; b + 8 <= nblk; b += 8) {                  // 8 blocks per batch: all their loads in flight together
-                        uint2 w[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) w[u] = wp[(b + u) * 32];
-#pragma unroll
-                        for (int q = 0; q < NPAIR; ++q) {
-                            uint2 xa[8], xb[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                xa[u] = xp[(2 * q) * xq + (b + u) * 32];
-                                xb[u] = 2 * q + 1 < NV ? xp[(2 * q + 1) * xq + (b + u) * 32] : make_uint2(0u, 0u);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) ds_mma_16816<T>(acc[q][u & 1], xa[u].x, xb[u].x, xa[u].y, xb[u].y, w[u].x, w[u].y);
-                        }
-                    }
-                    for (; b < nblk; b += 2) {
-                        const uint2 w0 = wp[b * 32], w1 = wp[b * 32 + 32];
-#pragma unroll
-                        for (int q = 0; q < NPAIR; ++q) {
-                            const uint2 xa0 = xp[(2 * q) * xq + b * 32], xa1 = xp[(2 * q) * xq + b * 32 + 32];
-                            uint2 xb0 = make_uint2(0u, 0u), xb1 = make_uint2(0u, 0u);
-                            if (2 * q + 1 < NV) { xb0 = xp[(2 * q + 1) * xq + b * 32]; xb1 = xp[(2 * q + 1) * xq + b * 32 + 32]; }
-                            ds_mma_16816<T>(acc[q][0], xa0.x, xb0.x, xa0.y, xb0.y, w0.x, w0.y);
-                            ds_mma_16816<T>(acc[q][1], xa1.x, xb1.x, xa1.y, xb1.y, w1.x, w1.y);
-                        }
-                    }
-                    float tot[NV];
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const int q = v >> 1, o = (v & 1) * 2;
-                        const float d0 = acc[q][0][o] + acc[q][1][o], d1 = acc[q][0][o + 1] + acc[q][1][o + 1];
-                        tot[v] = warp_sum(diag0 ? d0 : diag1 ? d1 : 0.f);
-                    }
-                    if (lane == 0) {
-                        float* dst = part_w + static_cast<size_t>(j - j0 + jr) * P * NV;
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) dst[v] = tot[v];
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[slot]);
-            }
+            const int P = op.P;
+            ds_ring_phase<T, NV>(op, full_bar, empty_bar, p.n_slots, p.x_bytes, p.xcap, p.dbg_flags, j0, j1, &rs);
             ds_consumer_sync();
             stamp(1);
-            // ---- epilogue: one thread per output row, fixed-order sum of the parts
+            // ---- epilogue: one thread per output row (fixed-order sum of the parts); neighbouring lanes pair their rows into one
+            // exchange word
             float best = -INFINITY;
             int best_i = 0x7fffffff;
 #pragma unroll 1
             for (int v = 0; v < NV; ++v) {
                 if (op.epi == DSE_LOGITS) { best = -INFINITY; best_i = 0x7fffffff; }
-                for (int r = tid; r < nloc; r += kDsConsumerThreads) {
-                    const int n = j0 + r;
-                    float a0 = 0.f, a1 = 0.f;
-                    for (int q = 0; q < P; ++q) a0 += part[(static_cast<size_t>(r) * P + q) * NV + v];
-                    if (op.nmat == 2)
-                        for (int q = 0; q < P; ++q) a1 += part[((static_cast<size_t>(nloc) + r) * P + q) * NV + v];
-                    switch (op.epi) {
-                        case DSE_STORE: (reinterpret_cast<T*>(op.y) + v * op.y_stride)[n] = Cvt<T>::from_f(a0); break;
-                        case DSE_RESID: {
-                            T* rs = reinterpret_cast<T*>(op.resid) + v * op.resid_stride;
-                            rs[n] = Cvt<T>::from_f(Cvt<T>::to_f(ds_ldcg_t(rs + n)) + rnd<T>(a0));
-                            break;
-                        }
-                        case DSE_RESID_EMBED: {
-                            const T* e = reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(p.st[v].tok) * p.H;
-                            (reinterpret_cast<T*>(op.resid) + v * op.resid_stride)[n] = Cvt<T>::from_f(Cvt<T>::to_f(e[n]) + rnd<T>(a0));
-                            break;
-                        }
-                        case DSE_SWIGLU: {
-                            const float g = rnd<T>(ds_silu(rnd<T>(a0)));
-                            (reinterpret_cast<T*>(op.y) + v * op.y_stride)[n] = Cvt<T>::from_f(g * rnd<T>(a1));
-                            break;
-                        }
-                        case DSE_LOGITS: {
-                            const float lg = rnd<T>(a0);
-                            (reinterpret_cast<float*>(op.y) + v * op.y_stride)[n] = lg;
-                            if (lg > best || (lg == best && n < best_i)) { best = lg; best_i = n; }
-                            break;
+                for (int rb = 0; rb < nloc; rb += kDsConsumerThreads) {
+                    const int r = rb + tid, n = j0 + r;
+                    float out = 0.f;
+                    if (r < nloc) {
+                        float a0 = 0.f, a1 = 0.f;
+                        for (int q = 0; q < P; ++q) a0 += part[(static_cast<size_t>(r) * P + q) * NV + v];
+                        if (op.nmat == 2)
+                            for (int q = 0; q < P; ++q) a1 += part[((static_cast<size_t>(nloc) + r) * P + q) * NV + v];
+                        switch (op.epi) {
+                            case DSE_STORE: out = rnd<T>(a0); break;
+                            case DSE_RESID: out = rnd<T>(resid_own[v][r] + rnd<T>(a0)); resid_own[v][r] = out; break;
+                            case DSE_SWIGLU: out = rnd<T>(rnd<T>(ds_silu(rnd<T>(a0))) * rnd<T>(a1)); break;
+                            default: {      // DSE_LOGITS
+                                out = rnd<T>(a0);
+                                (op.logits + v * op.logits_stride)[n] = out;
+                                if (out > best || (out == best && n < best_i)) { best = out; best_i = n; }
+                                break;
+                            }
                         }
                     }
+                    const float hi = __shfl_xor_sync(0xffffffffu, out, 1);      // row r + 1 (nloc is even)
+                    if (op.epi != DSE_LOGITS && r < nloc && !(r & 1))
+                        ds_ll_store(op.yll + v * op.yll_stride + ((j0 + r) >> 1), Cvt<T>::pack2(out, hi), tag_out);
                 }
                 if (op.epi == DSE_LOGITS) {
                     // CTA-level argmax candidate (first index wins ties, like torch.argmax)
@@ -491,306 +912,38 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                     if (tid == 0) {
                         for (int w = 1; w < kDsConsumerWarps; ++w)
                             if (cand_v[w] > best || (cand_v[w] == best && cand_i[w] < best_i)) { best = cand_v[w]; best_i = cand_i[w]; }
-                        p.cand_val[v * G + cta] = best;
-                        p.cand_idx[v * G + cta] = best_i;
+                        unsigned long long* cd = p.cand + (static_cast<size_t>(v) * G + cta) * 2;
+                        ds_ll_store(cd, __float_as_uint(best), tag_out);
+                        ds_ll_store(cd + 1, static_cast<uint32_t>(best_i), tag_out);
                     }
                     ds_consumer_sync();
                 }
             }
             stamp(2);
-            bar_target += G;
-            ds_grid_barrier(p.sync, bar_target, (p.dbg_flags & 2) != 0);
-            stamp(3);
         } else if (op.type == DS_ATTN) {
-            // ------------------------------------------------------------------ decode attention, split over the KV length
-            // Every dependent global access costs ~2 us while the weight stream saturates HBM, so the op is arranged as few
-            // dependent rounds as possible: (1) q / new k / new v AND this warp's K rows AND its V rows are requested
-            // together; (2) RoPE, scores, softmax, P.V from registers / shared memory; (3) partial + arrival counter;
-            // (4) the last CTA of a (lane, kv head) merges all slices with one round of loads.
-            constexpr int D = 128, VPL = 4, KB = 16, GM = 4;   // GM query heads per pass (GQA groups of 8: two passes)              // KB keys per warp block: lane pair = key, lane = 4 output dims
-            const int Hq = op.Hq, Hk = op.Hk, group = Hq / Hk;
-            const int S = max(1, G / Hk);                        // KV slices per (lane, kv head): independent of NV, so a stream's
-                                                                 // arithmetic (and ids) do not depend on what it is batched with
-            float* sm_q = reinterpret_cast<float*>(xs);           // [group][D] rotated q heads of the group (fp32 values of T)
-            float* sm_kn = sm_q + group * D;                      // [D] rotated new k
-            float* sm_vn = sm_kn + D;                             // [D] new v
-            float* sm_cs = sm_vn + D;                             // [D/2] cos, [D/2] sin
-            float* sm_m = sm_cs + D;                              // [8][8]
-            float* sm_l = sm_m + kDsGroupWarps * 8;
-            float* sm_o = sm_l + kDsGroupWarps * 8;               // [8][group][D]
-            float* sm_p = sm_o + kDsGroupWarps * group * D + warp * group * KB;   // this warp's [group][KB] probabilities of a key block
-            for (int item = cta; item < NV * Hk * S && !(p.dbg_flags & 4); item += G) {
-                const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
-                const int pos = p.st[v].pos, kv_len = pos + 1;
-                const int slot_kv = p.st[v].kv_slot;
-                const T* qkv = reinterpret_cast<const T*>(op.qkv) + v * op.qkv_stride;
-                T* kcache = reinterpret_cast<T*>(op.kc) + slot_kv * op.kv_stream_stride + static_cast<long long>(hk) * op.max_ctx * D;
-                T* vcache = reinterpret_cast<T*>(op.vc) + slot_kv * op.kv_stream_stride + static_cast<long long>(hk) * op.max_ctx * D;
-                const int per = (kv_len + S - 1) / S;
-                const int kbeg = s * per, kend = min(kv_len, kbeg + per);
-                const int half = lane & 1, kslot = lane >> 1;        // this lane scores dims [64 half, 64 half + 64) of key kb0 + kslot
-                // ---- round 1: everything that does not depend on anything else is requested now
-                float x1[2], x2[2];                                 // this thread's (head, d) pairs of q / new k before RoPE
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int i = tid + r * kDsConsumerThreads;
-                    x1[r] = 0.f; x2[r] = 0.f;
-                    if (i < (group + 1) * (D / 2)) {
-                        const int hh = i / (D / 2), d = i % (D / 2);
-                        const T* src = hh < group ? qkv + (hk * group + hh) * D : qkv + (Hq + hk) * D;
-                        x1[r] = Cvt<T>::to_f(ds_ldcg_t(src + d));
-                        x2[r] = Cvt<T>::to_f(ds_ldcg_t(src + d + D / 2));
-                    }
-                }
-                float vnew = 0.f;
-                if (tid < D) vnew = Cvt<T>::to_f(ds_ldcg_t(qkv + (Hq + Hk + hk) * D + tid));
-                uint4 kreg[D / 16];                                 // half a K row (64 dims) of this lane's key
-                uint2 vreg[KB];                                     // V (this lane's 4 dims) of the block's keys
-                const int kb_first = kbeg + warp * KB;
-                auto load_block = [&](int kb0) {
-                    const int key = kb0 + kslot;
-                    if (key < kend && key != pos) {
-                        const uint4* krow = reinterpret_cast<const uint4*>(kcache + static_cast<long long>(key) * D + half * (D / 2));
-#pragma unroll
-                        for (int c = 0; c < D / 16; ++c) kreg[c] = krow[c];
-                    }
-#pragma unroll
-                    for (int b = 0; b < KB; ++b) {
-                        const int kk = kb0 + b;
-                        if (kk < kend && kk != pos) vreg[b] = *reinterpret_cast<const uint2*>(vcache + static_cast<long long>(kk) * D + lane * VPL);
-                    }
-                };
-                load_block(kb_first);
-                // RoPE tables for this position (hf MistralRotaryEmbedding: fp32 angle, cos / sin cast to T)
-                if (tid < D / 2) {
-                    const float inv = powf(op.rope_theta, -2.0f * tid / D);
-                    float sn, cs;
-                    sincosf(pos * inv, &sn, &cs);
-                    sm_cs[tid] = rnd<T>(cs);
-                    sm_cs[D / 2 + tid] = rnd<T>(sn);
-                }
-                ds_consumer_sync();
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int i = tid + r * kDsConsumerThreads;
-                    if (i < (group + 1) * (D / 2)) {
-                        const int hh = i / (D / 2), d = i % (D / 2);
-                        const float cs = sm_cs[d], sn = sm_cs[D / 2 + d];
-                        float* dst = hh < group ? sm_q + hh * D : sm_kn;
-                        dst[d] = rnd<T>(rnd<T>(x1[r] * cs) + rnd<T>(-x2[r] * sn));
-                        dst[d + D / 2] = rnd<T>(rnd<T>(x2[r] * cs) + rnd<T>(x1[r] * sn));
-                    }
-                }
-                if (tid < D) sm_vn[tid] = vnew;
-                ds_consumer_sync();
-                if (kbeg <= pos && pos < kend && tid < D) {          // the slice holding the new position appends it
-                    kcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_kn[tid]);
-                    vcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_vn[tid]);
-                }
-                for (int gb = 0; gb < group; gb += GM) {
-                if (gb > 0) { ds_consumer_sync(); load_block(kb_first); }     // second pass of a wide GQA group re-reads K / V
-                // ---- round 2: per warp, blocks of KB keys.  Scores: a lane pair owns a key (64 dims each against the group's
-                // q heads broadcast from shared memory, one shuffle per head); block-wise online softmax (one warp_max per
-                // head per block); P.V: lane = 4 output dims, probabilities broadcast from shared memory.
-                float mx[GM], l[GM], o[GM][VPL];
-#pragma unroll
-                for (int g = 0; g < GM; ++g) {
-                    mx[g] = -INFINITY; l[g] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < VPL; ++i) o[g][i] = 0.f;
-                }
-                for (int kb0 = kb_first; kb0 < kend; kb0 += kDsConsumerWarps * KB) {
-                    if (kb0 != kb_first) load_block(kb0);     // slices longer than 16 warps x 16 keys (ctx > 4.6k): next round
-                    const int key = kb0 + kslot;
-                    const bool valid = key < kend;
-                    float sc[GM];
-#pragma unroll
-                    for (int g = 0; g < GM; ++g) sc[g] = 0.f;
-                    if (valid && key != pos) {
-#pragma unroll
-                        for (int c = 0; c < D / 16; ++c) {
-                            const uint4 u = kreg[c];
-                            const float2 k0 = Cvt<T>::unpack2(u.x), k1 = Cvt<T>::unpack2(u.y), k2 = Cvt<T>::unpack2(u.z), k3 = Cvt<T>::unpack2(u.w);
-#pragma unroll
-                            for (int g = 0; g < GM; ++g) {
-                                if (gb + g < group) {
-                                    const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8);
-                                    const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8 + 4);
-                                    float t = sc[g];
-                                    t = fmaf(qa.x, k0.x, t); t = fmaf(qa.y, k0.y, t); t = fmaf(qa.z, k1.x, t); t = fmaf(qa.w, k1.y, t);
-                                    t = fmaf(qb.x, k2.x, t); t = fmaf(qb.y, k2.y, t); t = fmaf(qb.z, k3.x, t); t = fmaf(qb.w, k3.y, t);
-                                    sc[g] = t;
-                                }
-                            }
-                        }
-                    } else if (valid) {                      // the new token: its k is still in shared memory
-                        for (int d = half * (D / 2); d < (half + 1) * (D / 2); ++d) {
-                            const float kd = sm_kn[d];
-#pragma unroll
-                            for (int g = 0; g < GM; ++g)
-                                if (gb + g < group) sc[g] = fmaf(sm_q[(gb + g) * D + d], kd, sc[g]);
-                        }
-                    }
-                    float cfac[GM];
-#pragma unroll
-                    for (int g = 0; g < GM; ++g) {
-                        if (gb + g < group) {
-                            const float full = sc[g] + __shfl_xor_sync(0xffffffffu, sc[g], 1);   // both halves of the key
-                            const float sv = valid ? full * op.scale_log2e : -INFINITY;
-                            const float mn = fmaxf(mx[g], warp_max(sv));
-                            cfac[g] = exp2f(mx[g] - mn);                              // 0 for the first block (mx = -inf)
-                            const float pr = valid ? rnd<T>(exp2f(sv - mn)) : 0.f;    // P is rounded to T before it multiplies V
-                            l[g] = l[g] * cfac[g] + (half == 0 ? pr : 0.f);           // lane-local partial of the row sum
-                            if (half == 0) sm_p[g * KB + kslot] = pr;
-                            mx[g] = mn;
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int g = 0; g < GM; ++g)
-                        if (gb + g < group) {
-#pragma unroll
-                            for (int i = 0; i < VPL; ++i) o[g][i] *= cfac[g];
-                        }
-#pragma unroll
-                    for (int b = 0; b < KB; ++b) {
-                        const int kk = kb0 + b;
-                        if (kk < kend) {
-                            float vv[VPL];
-                            if (kk == pos) {
-#pragma unroll
-                                for (int i = 0; i < VPL; ++i) vv[i] = sm_vn[lane * VPL + i];
-                            } else {
-                                const float2 a = Cvt<T>::unpack2(vreg[b].x), bb = Cvt<T>::unpack2(vreg[b].y);
-                                vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
-                            }
-#pragma unroll
-                            for (int g = 0; g < GM; ++g)
-                                if (gb + g < group) {
-                                    const float pr = sm_p[g * KB + b];
-#pragma unroll
-                                    for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(pr, vv[i], o[g][i]);
-                                }
-                        }
-                    }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int g = 0; g < GM; ++g)
-                    if (gb + g < group) l[g] = warp_sum(l[g]);
-                // ---- round 3: merge the warps in fixed order (upper half into lower half, then across the 8), write this
-                // slice's partial, count the arrival
-                const int w8 = warp & (kDsGroupWarps - 1);
-                if (kDsGroups > 1 && warp >= kDsGroupWarps) {
-#pragma unroll
-                    for (int g = 0; g < GM; ++g) {
-                        if (gb + g < group) {
-                            if (lane == 0) { sm_m[w8 * 8 + g] = mx[g]; sm_l[w8 * 8 + g] = l[g]; }
-#pragma unroll
-                            for (int i = 0; i < VPL; ++i) sm_o[(w8 * group + g) * D + lane * VPL + i] = o[g][i];
-                        }
-                    }
-                }
-                if (kDsGroups > 1) ds_consumer_sync();
-                if (warp < kDsGroupWarps) {
-#pragma unroll
-                    for (int g = 0; g < GM; ++g) {
-                        if (kDsGroups > 1 && gb + g < group) {
-                            const float pm = sm_m[w8 * 8 + g], pl = sm_l[w8 * 8 + g];
-                            const float mn = fmaxf(mx[g], pm);
-                            const float c0 = mx[g] == -INFINITY ? 0.f : exp2f(mx[g] - mn), c1 = pm == -INFINITY ? 0.f : exp2f(pm - mn);
-                            l[g] = l[g] * c0 + pl * c1;
-#pragma unroll
-                            for (int i = 0; i < VPL; ++i) o[g][i] = o[g][i] * c0 + sm_o[(w8 * group + g) * D + lane * VPL + i] * c1;
-                            mx[g] = mn;
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int g = 0; g < GM; ++g) {
-                        if (gb + g < group) {
-                            if (lane == 0) { sm_m[w8 * 8 + g] = mx[g]; sm_l[w8 * 8 + g] = l[g]; }
-#pragma unroll
-                            for (int i = 0; i < VPL; ++i) sm_o[(w8 * group + g) * D + lane * VPL + i] = o[g][i];
-                        }
-                    }
-                }
-                ds_consumer_sync();
-                float* pbase = p.att_part + (static_cast<long long>(v) * Hq + hk * group) * S * (D + 2);
-                const int npass = min(GM, group - gb);
-                for (int idx = tid; idx < npass * D; idx += kDsConsumerThreads) {
-                    const int g = idx / D, d = idx % D;
-                    float mm = -INFINITY;
-                    for (int w = 0; w < kDsGroupWarps; ++w) mm = fmaxf(mm, sm_m[w * 8 + g]);
-                    float ll = 0.f, oo = 0.f;
-                    for (int w = 0; w < kDsGroupWarps; ++w) {
-                        const float c = sm_m[w * 8 + g] == -INFINITY ? 0.f : exp2f(sm_m[w * 8 + g] - mm);
-                        ll += sm_l[w * 8 + g] * c;
-                        oo += sm_o[(w * group + g) * D + d] * c;
-                    }
-                    float* dst = pbase + (static_cast<long long>(gb + g) * S + s) * (D + 2);
-                    dst[2 + d] = oo;
-                    if (d == 0) { dst[0] = mm; dst[1] = ll; }
-                }
-                ds_consumer_sync();
-                if (tid == 0) {
-                    unsigned* ctr = p.sync + 8 + (gb / GM) * (kDsMaxStreams * Hk) + v * Hk + hk;      // one counter per pass
-                    const unsigned old = ds_atom_add_acq_rel(ctr, 1u);     // release this CTA's partial, acquire the others'
-                    flag_last = (old == static_cast<unsigned>(S - 1));
-                    if (flag_last) *ctr = 0u;
-                }
-                ds_consumer_sync();
-                // ---- round 4: the last CTA of this (lane, kv head) merges the slices in fixed order, all loads in one round
-                if (flag_last) {
-                    T* att = reinterpret_cast<T*>(op.att) + static_cast<long long>(v) * Hq * D;
-                    for (int idx = tid; idx < npass * D; idx += kDsConsumerThreads) {
-                        const int g = gb + idx / D, d = idx % D;
-                        const float* pp = pbase + static_cast<long long>(g) * S * (D + 2);
-                        float mm = -INFINITY, ll = 0.f, oo = 0.f;
-                        for (int z0 = 0; z0 < S; z0 += 6) {
-                            float pm[6], pl[6], po[6];
-#pragma unroll
-                            for (int u = 0; u < 6; ++u) {
-                                const int z = min(z0 + u, S - 1);
-                                pm[u] = __ldcg(pp + z * (D + 2));
-                                pl[u] = __ldcg(pp + z * (D + 2) + 1);
-                                po[u] = __ldcg(pp + z * (D + 2) + 2 + d);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 6; ++u) {
-                                if (z0 + u < S && pm[u] != -INFINITY) {
-                                    const float mn = fmaxf(mm, pm[u]);
-                                    const float c0 = exp2f(mm - mn), c1 = exp2f(pm[u] - mn);     // c0 = 0 while mm = -inf
-                                    ll = ll * c0 + pl[u] * c1;
-                                    oo = oo * c0 + po[u] * c1;
-                                    mm = mn;
-                                }
-                            }
-                        }
-                        att[(hk * group + g) * D + d] = Cvt<T>::from_f(oo / ll);
-                    }
-                }
-                }   // gb
-                if (item + G < NV * Hk * S) ds_consumer_sync();      // smem scratch is reused by the next item
-            }
+            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, tag_of(oi - 1), tag_of(oi));
             stamp(4);
-            bar_target += G;
-            ds_grid_barrier(p.sync, bar_target, (p.dbg_flags & 2) != 0);
-            stamp(3);
         } else {
             // ------------------------------------------------------------------ DS_FINAL: token selection (CTA 0)
             if (timed) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) p.dbg[c] += t_acc[c];
+                for (int c = 0; c < 4; ++c) {
+                    const int cat = c == 3 ? 4 : c;
+                    p.dbg[8 * (cta + 1) + cat] += t_acc[c];
+                    if (cta == 0) p.dbg[cat] += t_acc[c];
+                }
             }
             if (cta == 0 && warp == 0) {
                 int all_done = 1;
                 for (int v = 0; v < NV; ++v) {
                     float best = -INFINITY;
                     int best_i = 0x7fffffff;
-                    for (int c = lane; c < G; c += 32) {
-                        const float cv = __ldcg(p.cand_val + v * G + c);
-                        const int ci = __ldcg(p.cand_idx + v * G + c);
+                    const DsOp& head = p.ops[oi - 1];                                  // the lm_head GEMV: only CTAs with rows published a candidate
+                    const int n_cand = (head.N + ds_rows_per_cta(head.N, G) - 1) / ds_rows_per_cta(head.N, G);
+                    for (int c = lane; c < n_cand; c += 32) {
+                        const unsigned long long* cd = p.cand + (static_cast<size_t>(v) * G + c) * 2;
+                        const float cv = __uint_as_float(ds_ll_get(cd, tag_of(oi - 1)));
+                        const int ci = static_cast<int>(ds_ll_get(cd + 1, tag_of(oi - 1)));
                         if (cv > best || (cv == best && ci < best_i)) { best = cv; best_i = ci; }
                     }
 #pragma unroll
@@ -869,7 +1022,7 @@ __global__ void __launch_bounds__(1024) ds_first_token_kernel(const float* __res
 // bytes of the attention scratch that aliases the vector staging region (GQA group g)
 inline size_t decode_stream_attn_scratch_bytes(int group) {
     return (static_cast<size_t>(group) * 128 + 3 * 128 + 2 * kDsGroupWarps * 8 + static_cast<size_t>(kDsGroupWarps) * group * 128 +
-            static_cast<size_t>(kDsConsumerWarps) * group * 16) * sizeof(float);
+            static_cast<size_t>(kDsConsumerWarps) * group * 16 + static_cast<size_t>(group + 2) * 128) * sizeof(float);
 }
 inline size_t decode_stream_smem_bytes(int n_slots, int x_bytes, int part_cap) {
     return static_cast<size_t>(n_slots) * kDsSlotBytes + static_cast<size_t>(x_bytes) + static_cast<size_t>(part_cap) * sizeof(float);

@@ -58,7 +58,6 @@ SYMBOLS = {
     "sm_llm_decode_multi": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP]),
     "sm_decode_stats": (_I, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _I]),
     "sm_debug_decode_logits": (_I, [_VP, _I, _VP, _VP]),
-    "sm_debug_decode_buffer": (_I, [_VP, _I, _VP, _LL, _VP]),
     "sm_debug_decode_phases": (_I, [_VP, _VP]),
     "sm_kv_len": (_I, [_VP]),
     "sm_kv_set_len": (_I, [_VP, _I]),

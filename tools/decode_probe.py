@@ -35,7 +35,7 @@ for s in range(a.streams):
 sids = list(range(a.streams))
 eng.llm_decode_multi(sids, [8] * a.streams)            # warm-up
 eng.decode_stats(reset=True)
-buf = torch.zeros(8, dtype=torch.int64, device=dev)
+buf = torch.zeros(8 * 160, dtype=torch.int64, device=dev)
 if a.phases:
     eng.lib.sm_debug_decode_phases(eng._h, C.c_void_p(buf.data_ptr()))
 eng.llm_decode_multi(sids, [a.new] * a.streams)
@@ -50,6 +50,12 @@ if a.phases:
     torch.cuda.synchronize()
     names = ["prologue", "ring-compute", "epilogue", "barrier", "attention", "final", "wait-first-chunk", "wait-later-chunks"]
     v = buf.cpu().tolist()
+    per = torch.tensor(v[8:8 + 8 * 148], dtype=torch.float64).view(148, 8) / st["steps"] / 1e3
+    for c, n in ((0, "prologue"), (1, "ring"), (2, "epilogue"), (4, "attention")):
+        col = per[:, c]
+        order = col.argsort()
+        print(f"  per-CTA {n}: min {col.min():.0f} (cta {int(order[0])}), median {col.median():.0f}, max {col.max():.0f} (cta {int(order[-1])}); "
+              f"lowest 5: {[int(x) for x in order[:5]]}, highest 5: {[int(x) for x in order[-5:]]}")
     tot = sum(v[:8])
     print("CTA 0 phases (us per step): " + ", ".join(f"{n} {x / st['steps'] / 1e3:.1f}" for n, x in zip(names, v)) + f", sum {tot / st['steps'] / 1e3:.1f}")
 eng.close()

@@ -1,4 +1,9 @@
 #!/bin/bash
-timeout 200 python -m pytest tests/test_preprocess_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 100 python tools/preprocess_bench.py 2>&1 | tail -3
-timeout 300 python -m pytest tests -m gpu -x -q --deselect tests/test_preprocess_gpu.py 2>&1 | tail -2
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_llm_gpu.py tests/test_llm_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -3
+echo "== ctx 2048"
+timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --phases 2>&1 | tail -6
+echo "== nomath"
+SMB_DS_DBG=1 timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --phases 2>&1 | tail -1
+echo "== 2 streams"
+timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --streams 2 --phases 2>&1 | tail -1
