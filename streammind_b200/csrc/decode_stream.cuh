@@ -231,8 +231,8 @@ __device__ __forceinline__ T ds_ldcg_t(const T* p) {
 
 // The attention op of the decode kernel.  Register discipline matters here: if the kernel spills anywhere, ptxas schedules the
 // WHOLE kernel for low register use and pairs every shared-memory load of the weight-streaming loop with its MMA (the loop
-// then runs at load latency: +30 % per step, measured).  So the projection's words are polled one at a time into shared
-// memory while the K / V rows of the first block (64 registers) are in flight, not held in registers next to them.
+// then runs at load latency: +30 % per step, measured).  So the projection's words are polled at most two at a time while
+// the K / V rows of the first block (64 registers) are in flight.
 template <typename T, int NV>
 __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamState* st, unsigned long long* att_part, T* xs,
                                             uint32_t tag_in, uint32_t tag_out) {
@@ -256,7 +256,6 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
     float* sm_l = sm_m + kDsGroupWarps * 8;
     float* sm_o = sm_l + kDsGroupWarps * 8;               // [8][group][D]
     float* sm_p = sm_o + kDsGroupWarps * group * D + warp * group * KB;   // this warp's [group][KB] probabilities of a key block
-    float* sm_raw = sm_o + kDsGroupWarps * group * D + kDsConsumerWarps * group * KB;   // [(group + 2) D] q heads | k | v of this kv head as projected
     for (int item = cta; item < NV * Hk * S; item += G) {
         const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
         const int pos = st[v].pos, kv_len = pos + 1;
@@ -285,36 +284,34 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             }
         };
         load_block(kb_first);
-        // poll the projection's words of this kv head (q heads | k | v: (group + 2) D / 2 words) into shared memory
-        for (int w = tid; w < (group + 2) * (D / 2); w += kDsConsumerThreads) {
-            const int hh = w / (D / 2), d2 = w % (D / 2);
-            const int src = (hh < group ? (hk * group + hh) * D : hh == group ? (Hq + hk) * D : (Hq + Hk + hk) * D) / 2 + d2;
-            const float2 f = Cvt<T>::unpack2(ds_ll_get(ql + src, tag_in));
-            sm_raw[2 * w] = f.x;
-            sm_raw[2 * w + 1] = f.y;
-        }
-        // RoPE tables for this position (hf MistralRotaryEmbedding: fp32 angle, cos / sin cast to T)
-        if (tid < D / 2) {
-            const float inv = powf(op.rope_theta, -2.0f * tid / D);
-            float sn, cs;
-            sincosf(pos * inv, &sn, &cs);
-            sm_cs[tid] = rnd<T>(cs);
-            sm_cs[D / 2 + tid] = rnd<T>(sn);
-        }
-        ds_consumer_sync();
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int i = tid + r * kDsConsumerThreads;
-            if (i < (group + 1) * (D / 2)) {
-                const int hh = i / (D / 2), d = i % (D / 2);
-                const float cs = sm_cs[d], sn = sm_cs[D / 2 + d];
-                const float x1 = sm_raw[hh * D + d], x2 = sm_raw[hh * D + d + D / 2];
+        // Poll the projection's words of this kv head and rotate them in the same thread: a job is two adjacent dims d, d + 1
+        // (d < D/2) of a q head / the new k -- the word holding them and the word holding d + D/2, d + D/2 + 1 -- or one word
+        // of the new v.  cos / sin of the position (hf MistralRotaryEmbedding: fp32 angle, cos / sin cast to T) are evaluated
+        // while the first poll is in flight.
+        for (int jb = tid; jb < (group + 1) * (D / 4) + D / 2; jb += kDsConsumerThreads) {
+            if (jb < (group + 1) * (D / 4)) {
+                const int hh = jb / (D / 4), d = 2 * (jb % (D / 4));
+                const unsigned long long* wa = ql + (((hh < group ? (hk * group + hh) * D : (Hq + hk) * D) + d) >> 1);
+                unsigned long long ra = ds_ll_load(wa), rb = ds_ll_load(wa + D / 4);
+                float cs0, sn0, cs1, sn1;
+                sincosf(pos * powf(op.rope_theta, -2.0f * d / D), &sn0, &cs0);
+                sincosf(pos * powf(op.rope_theta, -2.0f * (d + 1) / D), &sn1, &cs1);
+                cs0 = rnd<T>(cs0); sn0 = rnd<T>(sn0); cs1 = rnd<T>(cs1); sn1 = rnd<T>(sn1);
+                unsigned spins = 0;
+                while (!(ds_ll_ok(ra, tag_in) && ds_ll_ok(rb, tag_in))) { ds_ll_retry(spins, tag_in); ra = ds_ll_load(wa); rb = ds_ll_load(wa + D / 4); }
+                const float2 x1 = Cvt<T>::unpack2(static_cast<uint32_t>(ra)), x2 = Cvt<T>::unpack2(static_cast<uint32_t>(rb));
                 float* dst = hh < group ? sm_q + hh * D : sm_kn;
-                dst[d] = rnd<T>(rnd<T>(x1 * cs) + rnd<T>(-x2 * sn));
-                dst[d + D / 2] = rnd<T>(rnd<T>(x2 * cs) + rnd<T>(x1 * sn));
+                dst[d] = rnd<T>(rnd<T>(x1.x * cs0) + rnd<T>(-x2.x * sn0));
+                dst[d + 1] = rnd<T>(rnd<T>(x1.y * cs1) + rnd<T>(-x2.y * sn1));
+                dst[d + D / 2] = rnd<T>(rnd<T>(x2.x * cs0) + rnd<T>(x1.x * sn0));
+                dst[d + D / 2 + 1] = rnd<T>(rnd<T>(x2.y * cs1) + rnd<T>(x1.y * sn1));
+            } else {
+                const int w = jb - (group + 1) * (D / 4);
+                const float2 f = Cvt<T>::unpack2(ds_ll_get(ql + ((Hq + Hk + hk) * D) / 2 + w, tag_in));
+                sm_vn[2 * w] = f.x;
+                sm_vn[2 * w + 1] = f.y;
             }
         }
-        if (tid < D) sm_vn[tid] = sm_raw[(group + 1) * D + tid];
         ds_consumer_sync();
         if (kbeg <= pos && pos < kend && tid < D) {          // the slice holding the new position appends it
             kcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_kn[tid]);
@@ -797,15 +794,6 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                     for (int q0 = tid; q0 < nq; q0 += UB * kDsConsumerThreads) {
                         unsigned long long r[UB][2];
                         unsigned spins = 0;
-                        {   // wait on ONE word pair first (a waiting CTA must not flood L2 with polls: they share its ports with the
-                            // weight stream), then fetch the batch -- usually complete by then
-                            const unsigned long long* sp = xl + 2 * q0;
-                            for (;;) {
-                                ds_ll_load2(sp, r[0][0], r[0][1]);
-                                if (ds_ll_ok(r[0][0], tag_in) && ds_ll_ok(r[0][1], tag_in)) break;
-                                ds_ll_retry(spins, tag_in);
-                            }
-                        }
                         for (bool ok = false; !ok;) {           // the whole batch is polled again until every tag matches (one round trip per try)
 #pragma unroll
                             for (int u = 0; u < UB; ++u) {
@@ -1022,7 +1010,7 @@ __global__ void __launch_bounds__(1024) ds_first_token_kernel(const float* __res
 // bytes of the attention scratch that aliases the vector staging region (GQA group g)
 inline size_t decode_stream_attn_scratch_bytes(int group) {
     return (static_cast<size_t>(group) * 128 + 3 * 128 + 2 * kDsGroupWarps * 8 + static_cast<size_t>(kDsGroupWarps) * group * 128 +
-            static_cast<size_t>(kDsConsumerWarps) * group * 16 + static_cast<size_t>(group + 2) * 128) * sizeof(float);
+            static_cast<size_t>(kDsConsumerWarps) * group * 16) * sizeof(float);
 }
 inline size_t decode_stream_smem_bytes(int n_slots, int x_bytes, int part_cap) {
     return static_cast<size_t>(n_slots) * kDsSlotBytes + static_cast<size_t>(x_bytes) + static_cast<size_t>(part_cap) * sizeof(float);
