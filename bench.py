@@ -220,6 +220,36 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+def reference_gpu_vit(dev, dt, frames_dev, n=24):
+    """Secondary figure: the reference's own GPU path for the vision tower -- hf CLIPVisionModel (24 layers, hidden states kept,
+    what CLIPVisionTower.forward runs: clip_encoder.py:41-53) executed by PyTorch on this GPU in the model dtype, one frame per
+    call as in the streaming demo.  Timed with CUDA events after the main measurement; not part of `value`."""
+    import torch
+    try:
+        from streammind_b200 import hf_reference, synth
+        sd = synth.make_vit_weights(1234, dt, device=dev, layers=24)
+        m = hf_reference.build_hf_clip(sd, 1024, 4096, 24, 16, 336, 14, 1e-5, dt, device=dev)
+        del sd
+        for i in range(5):
+            hf_reference.clip_features(m, frames_dev[i:i + 1])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(n):
+            hf_reference.clip_features(m, frames_dev[i % frames_dev.shape[0]:i % frames_dev.shape[0] + 1])
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / n
+        del m
+        torch.cuda.empty_cache()
+        return {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "frames_timed": n,
+                "note": "hf CLIPVisionModel (transformers, PyTorch kernels) on the same GPU, B = 1 per call, model dtype, ViT encode only -- "
+                        "compare with configs1_frames_stage.serial_b1_frames_per_s (which also runs the projector and the gate)"}
+    except Exception as e:                                    # transformers missing / out of memory: the key says so
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def _load_full_model(model_or_engine, cfg, dev, dt, seed=1234):
     """random-init weights of the full configuration, generated on the device part by part (17 GB in bf16)"""
     import torch
@@ -394,8 +424,9 @@ def run_stream_workload(args):
         if ms_first is not None and args.steps >= intervals:
             line["whole_stream"] = {"frames": n_frames, "seconds": ms_first / 1e3, "frames_per_s": n_frames / (ms_first / 1e3),
                                     "note": f"the first {intervals} steps = exactly one configs stream (rank 0 clock)"}
-        if args.with_frames_stage:
+        if (args.with_frames_stage or world == 1) and not args.no_frames_stage:
             line["configs1_frames_stage"] = frames_stage(eng, frames_dev[:64], peaks)
+            line["reference_gpu_vit"] = reference_gpu_vit(dev, dt, frames_dev[:8])
         emit(line)
     eng.close()
     if world > 1:
@@ -603,7 +634,8 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="serial frame path (sm_frame_step per call), no overlap with the decode")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--with-frames-stage", action="store_true", help="also time the configs[1] sub-path on the same handle (extra key)")
+    ap.add_argument("--with-frames-stage", action="store_true", help="also time the configs[1] sub-path on the same handle (extra keys); default at N = 1")
+    ap.add_argument("--no-frames-stage", action="store_true", help="skip the configs[1] sub-path / reference-on-GPU extra keys")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
