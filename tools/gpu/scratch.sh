@@ -1,10 +1,6 @@
 #!/bin/bash
-for cfg in "0 100000" "1 100000" "2 100000" "3 100000" "0 1000" "0 100" "1 100"; do
-set -- $cfg
-echo "== wait $1 hint $2"
-SMB_DS_WAIT=$1 SMB_DS_HINT_NS=$2 timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --phases 2>&1 | tail -1
-done
-echo "== nomath wait 1"
-SMB_DS_DBG=1 SMB_DS_WAIT=1 timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --phases 2>&1 | tail -1
-echo "== nomath wait 3"
-SMB_DS_DBG=1 SMB_DS_WAIT=3 timeout 120 python tools/decode_probe.py --layers 32 --ctx 2048 --phases 2>&1 | tail -1
+mkdir -p gpurun_out
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_r02.csv \
+    -k regex:"attention|decode_stream|ds_first|gather_rows|gemm_tc|gemv|gqa_expand|im2col|layernorm|mamba|rmsnorm_rows|rope_append|splitk|swiglu|vit_|preprocess" \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graphs --no-frames-stage > gpurun_out/ncu_launch_r02.log 2>&1
+tail -c 300 gpurun_out/ncu_launch_r02.log; wc -l gpurun_out/launches_r02.csv

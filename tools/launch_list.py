@@ -8,8 +8,12 @@ rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))
 hdr = rows[0]
 ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg = defaultdict(lambda: [0, 0.0])
+# a capture filtered with -k regex:<this library's kernels> prints base names without the smb:: namespace: then every row is ours
+filtered = not any("smb::" in r[ik] for r in rows[1:])
 for r in rows[1:]:
     name = r[ik].split("<")[0].split("(")[0].replace("void ", "")
+    if filtered:
+        name = "smb::" + name
     if "smb::" not in name:
         name = "(not this library: torch fill / copy / random init)"
     us = float(r[iv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}.get(r[iu], 1e-3)
