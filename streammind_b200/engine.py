@@ -170,7 +170,7 @@ class Engine:
         bg = (C.c_int * 3)(*[int(x * 255) for x in image_mean])      # the reference's background colour expression
         self._check(self.lib.sm_preprocess_frames(self._h, t.data_ptr(), n, H, W, 1 if t.is_cuda else 0, mean, std, bg,
                                                   out.data_ptr(), self._stream()))
-        if not t.is_cuda:
+        if not t.is_cuda and not t.is_pinned():
             torch.cuda.current_stream(self.device).synchronize()          # the pageable host buffer may go away with `t`
         return out
 

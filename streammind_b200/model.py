@@ -248,11 +248,20 @@ class StreamMindB200ForCausalLM:
         self._tokens = [toks]
         return toks[torch.tensor(list(idx), device=toks.device)]
 
+    def _pixels(self, frames):
+        """Raw uint8 RGB frames [t, H, W, 3] (what the video decoder yields) are preprocessed on the device -- expand2square + CLIP
+        preprocess of the reference's process_video (mm_utils.py:446-464), bit for bit -- instead of by PIL on the host; anything else
+        is taken as already normalised pixels [t, 3, H, W]."""
+        if isinstance(frames, torch.Tensor) and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3:
+            return self.engine.preprocess_frames(frames)
+        return frames
+
     # ---- per-frame path ------------------------------------------------------------------------
     def _encode_frames(self, frames: torch.Tensor):
         """encode_images_or_videos_score_cls_inference_allframe_demo (videollama2_arch.py:173-203),
         incremental: returns gate logits [2] fp32 (host) of the last frame."""
         e = self.engine
+        frames = self._pixels(frames)
         if frames.dim() != 4:
             raise ValueError(f"expected frames [t, 3, H, W], got {tuple(frames.shape)}")
         if frames.dtype != e.cfg.dtype:
@@ -283,6 +292,7 @@ class StreamMindB200ForCausalLM:
         e = self.engine
         if e.cfg.max_frames != 1:
             raise RuntimeError("prefetch_frames needs a streaming engine (max_frames == 1)")
+        frames = self._pixels(frames)
         if frames.dim() != 4:
             raise ValueError(f"expected frames [t, 3, H, W], got {tuple(frames.shape)}")
         if len(self._inflight) + frames.shape[0] > 15:
