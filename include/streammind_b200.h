@@ -222,6 +222,12 @@ int sm_test_gemm(sm_handle* h, const void* x /*[M,K]*/, const void* w /*[N,K]*/,
 int sm_test_gemm_trace(sm_handle* h, long long* device_buf);
 int sm_test_attention(sm_handle* h, const void* qkv /*[B*S, 3*H*D]*/, void* out /*[B*S, H*D]*/, int B, int S, int H,
                       int D, void* stream);
+/* The LLM prefill attention alone (causal, GQA, head_dim 128; hf MistralForCausalLM SDPA as reached from
+ * videollama2_mistral.py:234-243): P query rows at positions pos0 .. pos0 + P - 1 (row i of q: Hq heads x 128 at column
+ * h * 128, row pitch q_pitch elements, already rotated) against a cache [Hk][max_ctx][128] holding pos0 + P positions;
+ * out [P, Hq * 128].  n_splits: -1 = the mma.sync kernel, 0 = tcgen05 kernel with the planned key-range split, > 0 forced. */
+int sm_test_kv_attention(sm_handle* h, const void* q, int q_pitch, const void* kcache, const void* vcache, int max_ctx, void* out,
+                         int P, int pos0, int Hq, int Hk, int n_splits, void* stream);
 
 /* Per-kernel-class CUDA-event timing (used by bench.py's roofline pass; adds two event records per
  * launch, so keep it off on the timed path; ignored while capturing / replaying graphs).

@@ -21,6 +21,7 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_kv_tc.cuh"
 #include "preprocess.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
@@ -131,6 +132,8 @@ struct sm_handle {
     std::vector<void*> kc, vc;
     int pmax = 0;
     void *lw_x = nullptr, *lw_hn = nullptr, *lw_qkv = nullptr, *lw_att = nullptr, *lw_gu = nullptr, *lw_m = nullptr;
+    float *lw_akv_o = nullptr, *lw_akv_ml = nullptr;   // split-KV partials of the tcgen05 prefill attention: [lw_akv_rows][Hq][128] and [..][2]
+    int lw_akv_rows = 0;
     float *lw_logits = nullptr, *lw_part2 = nullptr;   // lw_logits [n_streams][V]: last-position logits of each stream's prefill; lw_part2: split-K partials of the few-row prefill GEMMs
     // ---- per-stream state (multi-stream batching): the handle holds n_streams video streams that share
     // its weights; `cur` is the stream the single-stream entry points act on (sm_stream_select)
@@ -542,6 +545,48 @@ int launch_attn_tc_t(sm_handle* h, const AttnArgs& a, int heads, int batch, cuda
     return 0;
 }
 
+// tcgen05 prefill attention (attention_kv_tc.cuh): causal GQA, d = 128, queries = rows of a packed (already rotated) activation,
+// keys / values = one stream's cache [Hk][max_ctx][128].  n_splits: 0 = planned (about one wave of CTAs), > 0 forced (tests).
+int plan_attn_kv_splits(const sm_handle* h, int P, int pos0, int group, int Hk) {
+    const int TB = 128 / group, q_tiles = (P + TB - 1) / TB, nb_max = (pos0 + P + 127) / 128;
+    return std::max(1, std::min(nb_max, h->num_sms / (q_tiles * Hk)));
+}
+bool attn_kv_tc_ok(const sm_handle* h, int D, int Hq, int Hk) {
+    static const int env_on = getenv("SMB_PREFILL_ATTN_TC") ? atoi(getenv("SMB_PREFILL_ATTN_TC")) : 1;
+    const int on = h->attn_mode >= 0 ? (h->attn_mode != 0) : env_on;
+    if (!on || D != 128 || Hq % Hk != 0) return false;
+    const int group = Hq / Hk;
+    return 128 % group == 0 && (128 / group) % 8 == 0;
+}
+template <typename T>
+int launch_attn_kv_tc_t(sm_handle* h, const void* q, int q_rows, int q_pitch, int col_q, const void* kc, const void* vc, int max_ctx, void* o,
+                        int o_ss, int P, int pos0, int Hq, int Hk, float scale_log2e, int n_splits, cudaStream_t st) {
+    if (!kon(h, KC_ATTN)) return 0;
+    const int group = Hq / Hk, TB = 128 / group;
+    if (n_splits <= 0) n_splits = plan_attn_kv_splits(h, P, pos0, group, Hk);
+    if (n_splits > 1 && (h->lw_akv_o == nullptr || static_cast<long long>(n_splits) * P > h->lw_akv_rows))
+        return fail(h, "prefill attention: %d splits x %d positions exceed the partial buffer (%d rows)", n_splits, P, h->lw_akv_rows);
+    const CUtensorMap* tq = get_tmap(h, q, q_rows, q_pitch, TB);
+    const CUtensorMap* tk = get_tmap(h, kc, Hk * max_ctx, 128, 128);
+    const CUtensorMap* tv = get_tmap(h, vc, Hk * max_ctx, 128, 128);
+    if (!tq || !tk || !tv) return 1;
+    AttnKvArgs a{};
+    a.o = o; a.o_ss = o_ss; a.P = P; a.pos0 = pos0; a.group = group; a.Hq = Hq; a.max_ctx = max_ctx; a.col_q = col_q;
+    a.n_splits = n_splits; a.scale_log2e = scale_log2e; a.ws_o = h->lw_akv_o; a.ws_ml = h->lw_akv_ml;
+    {
+        ProfScope ps(h, KC_ATTN, st);
+        const dim3 grid((P + TB - 1) / TB, Hk, n_splits);
+        CUDA_OK(h, launch_pdl(h, attention_kv_tc_kernel<T>, grid, dim3(kAkvThreads), static_cast<size_t>(attn_kv_smem_bytes()), st, *tq, *tk, *tv, a));
+        count_launch(h);
+        if (n_splits > 1) {
+            CUDA_OK(h, launch_pdl(h, attention_kv_merge_kernel<T>, dim3(P, Hq), dim3(128), 0, st, a));
+            count_launch(h);
+        }
+    }
+    CUDA_OK(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_attn(sm_handle* h, const AttnArgs& a, int D, int heads, int batch, cudaStream_t st) {
     // one frame alone is only 80 CTAs of 128 query rows: the 64-row mma.sync kernel (160 CTAs) fills the machine better
     static const int env_tc = getenv("SMB_ATTN_TC") ? atoi(getenv("SMB_ATTN_TC")) : 1;
@@ -572,6 +617,7 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
+    CUDA_OK(h, cudaFuncSetAttribute(attention_kv_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_kv_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
@@ -887,7 +933,10 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         a.o_bs = 0; a.o_ss = Hq * D;
         a.q_len = P; a.kv_len = pos0 + P; a.q_pos0 = pos0; a.causal = 1; a.group = Hq / Hk;
         a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
-        if (launch_attn(h, a, D, Hq, 1, st)) return 1;
+        if (attn_kv_tc_ok(h, D, Hq, Hk)) {
+            DISPATCH_T(h, T, { if (launch_attn_kv_tc_t<T>(h, h->lw_qkv, h->pmax, QKV, 0, a.k, a.v, c.llm_max_ctx, h->lw_att, Hq * D, P, pos0, Hq, Hk,
+                                                          a.scale_log2e, 0, st)) return 1; })
+        } else if (launch_attn(h, a, D, Hq, 1, st)) return 1;
         if (few) { if (gemm_few_rows(h, h->lw_att, P, L.wo, H, Hq * D, h->lw_x, true, h->lw_part2, st)) return 1; }
         else if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
@@ -1009,10 +1058,8 @@ int launch_decode_step_t(sm_handle* h, int nv, cudaStream_t st) {
     p.stop = h->ds_stop; p.embed = h->lm_embed; p.H = h->cfg.llm_hidden; p.att_part = h->ds_att_part;
     p.cand = h->ds_cand; p.dbg = h->ds_dbg;
     {
-        static const int ahead = getenv("SMB_DS_L2_AHEAD") ? atoi(getenv("SMB_DS_L2_AHEAD")) : 0;   // measured: an L2 prefetch cursor 8 / 16 chunks ahead is slower (3.65 / 5.4 vs 3.32 ms per step)
         static const int flags = getenv("SMB_DS_DBG") ? atoi(getenv("SMB_DS_DBG")) : 0;
         static const int inflight = getenv("SMB_DS_INFLIGHT") ? atoi(getenv("SMB_DS_INFLIGHT")) : 0;
-        p.l2_ahead = std::max(0, ahead) & ~1;
         p.dbg_flags = flags;
         p.max_inflight = inflight >= m.n_slots ? 0 : std::max(0, inflight);
     }
@@ -1430,6 +1477,12 @@ int sm_create(sm_handle** out, int device, const sm_config* cfg) {
         h->lw_logits = static_cast<float*>(A(static_cast<size_t>(h->n_streams) * V * sizeof(float)));
         h->kv_stream_stride = static_cast<long long>(Hk) * c.llm_max_ctx * D;
         h->lw_part2 = static_cast<float*>(A(static_cast<size_t>(8) * 64 * std::max(QKV, H) * sizeof(float)));
+        if (D == 128 && Hq % Hk == 0 && 128 % (Hq / Hk) == 0 && (128 / (Hq / Hk)) % 8 == 0) {
+            const int TB = 128 / (Hq / Hk);
+            h->lw_akv_rows = std::max(h->pmax, h->num_sms * TB / Hk + TB);      // n_splits x P never exceeds this (plan_attn_kv_splits)
+            h->lw_akv_o = static_cast<float*>(A(static_cast<size_t>(h->lw_akv_rows) * Hq * 128 * sizeof(float)));
+            h->lw_akv_ml = static_cast<float*>(A(static_cast<size_t>(h->lw_akv_rows) * Hq * 2 * sizeof(float)));
+        }
         // persistent decode kernel: activations of up to kDsMaxStreams lanes, state, split-KV partials, argmax candidates
         const size_t NL = kDsMaxStreams;
         auto LLA = [&](size_t words) { return static_cast<unsigned long long*>(A(words * sizeof(unsigned long long))); };   // zeroed: tag 0 never matches
@@ -2142,6 +2195,34 @@ int sm_test_attention(sm_handle* h, const void* qkv, void* out, int B, int S, in
     a.q_len = S; a.kv_len = S; a.q_pos0 = 0; a.causal = 0; a.group = 1;
     a.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
     return launch_attn(h, a, D, H, B, static_cast<cudaStream_t>(stream));
+}
+
+int sm_test_kv_attention(sm_handle* h, const void* q, int q_pitch, const void* kcache, const void* vcache, int max_ctx, void* out, int P,
+                         int pos0, int Hq, int Hk, int n_splits, void* stream) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = 128;
+    const float scale = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+    if (n_splits >= 0) {
+        if (Hk < 1 || Hq % Hk != 0 || 128 % (Hq / Hk) != 0 || (128 / (Hq / Hk)) % 8 != 0) return fail(h, "sm_test_kv_attention: unsupported head grouping %d / %d", Hq, Hk);
+        if (h->lw_akv_o == nullptr) {        // a handle without an LLM (unit tests): partial buffers on first use
+            const int TB = 128 / (Hq / Hk);
+            h->lw_akv_rows = std::max(512, h->num_sms * TB / Hk + TB);
+            h->lw_akv_o = static_cast<float*>(dalloc(h, static_cast<size_t>(h->lw_akv_rows) * Hq * 128 * sizeof(float)));
+            h->lw_akv_ml = static_cast<float*>(dalloc(h, static_cast<size_t>(h->lw_akv_rows) * Hq * 2 * sizeof(float)));
+            if (!h->lw_akv_o || !h->lw_akv_ml) return fail(h, "sm_test_kv_attention: out of device memory");
+        }
+        DISPATCH_T(h, T, return launch_attn_kv_tc_t<T>(h, q, P, q_pitch, 0, kcache, vcache, max_ctx, out, Hq * D, P, pos0, Hq, Hk, scale, n_splits, st);)
+    }
+    AttnArgs a{};
+    a.q = q; a.o = out; a.k = kcache; a.v = vcache;
+    a.q_bs = 0; a.q_ss = q_pitch;
+    a.k_bs = a.v_bs = 0; a.k_hs = a.v_hs = static_cast<long long>(max_ctx) * D; a.k_ss = a.v_ss = D;
+    a.o_bs = 0; a.o_ss = Hq * D;
+    a.q_len = P; a.kv_len = pos0 + P; a.q_pos0 = pos0; a.causal = 1; a.group = Hq / Hk;
+    a.scale_log2e = scale;
+    return launch_attn(h, a, D, Hq, 1, st);
 }
 
 int sm_debug_attention_mode(sm_handle* h, int mode) {

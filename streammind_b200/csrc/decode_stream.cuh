@@ -43,6 +43,14 @@ constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxStreams = 4;
 constexpr int kDsResidRows = 64;            // rows of the residual stream one CTA may own (hidden <= 64 x SMs)
 
+// -DSMB_DS_WAITPROBE (measurement builds only, tools/gpu/ds_probe_build.sh): producer 0 of every CTA accumulates the time it is blocked on
+// a full ring (category 3) and its whole life (5); consumer thread 0 the time it waits for a chunk to land (6 first chunk of an op, 7 later)
+#ifdef SMB_DS_WAITPROBE
+#define DS_PROBE(...) __VA_ARGS__
+#else
+#define DS_PROBE(...)
+#endif
+
 enum DsOpType : int { DS_GEMV = 0, DS_ATTN = 1, DS_FINAL = 2 };
 enum DsPro : int {
     DSP_PLAIN = 0,          // x = x0
@@ -111,9 +119,8 @@ struct DsParams {
     int H;
     unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
     unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
-    int l2_ahead;            // chunks the L2 prefetch cursor runs ahead of the ring (even; 0 = off)
     int max_inflight;        // bulk copies of this CTA that may be in flight at once (0 = as many as the ring has free slots)
-    int dbg_flags;           // measurement only: 1 skip the consumer math, 8 no L2 prefetch
+    int dbg_flags;           // measurement only: 1 skip the consumer math
     long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
 
@@ -540,7 +547,7 @@ struct DsRingState { int seq, slot, par; };   // chunk sequence number of this C
 // The weight-streaming phase of a GEMV op.
 template <typename T, int NV>
 __device__ __forceinline__ void ds_ring_phase(const DsOp& op, uint64_t* full_bar, uint64_t* empty_bar, int n_slots, int x_bytes, int xcap,
-                                          int dbg_flags, int j0, int j1, DsRingState* state) {
+                                          int dbg_flags, int j0, int j1, DsRingState* state, long long* probe) {
     extern __shared__ __align__(128) uint8_t ds_smem[];            // same carve-up as the kernel: ring | staged vectors | partial sums
     const uint8_t* ring = ds_smem;
     const T* xs = reinterpret_cast<const T*>(ds_smem + static_cast<size_t>(n_slots) * kDsSlotBytes);
@@ -579,7 +586,9 @@ __device__ __forceinline__ void ds_ring_phase(const DsOp& op, uint64_t* full_bar
         const int slot = rs.slot, par = rs.par;
         if (++rs.slot == n_slots) { rs.slot = 0; rs.par ^= 1; }
         if (kDsGroups > 1 && rs.seq % kDsGroups != grp) continue;
+        DS_PROBE(const long long tw0 = (probe != nullptr) ? ds_gtimer() : 0;)
         mbar_wait_hint(&full_bar[slot], par);
+        DS_PROBE(if (probe != nullptr) probe[j == j0 ? 0 : 1] += ds_gtimer() - tw0;)
         if (j + jr < j1 && !skip_math) {
             const uint2* wp = ring_u2 + slot * (kDsSlotBytes / 8);
             float acc[NPAIR][2][4];
@@ -658,9 +667,11 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
 
     if (warp >= kDsConsumerWarps) {
         // ================================================================== producers: the weight stream
-        // Each producer walks the chunk sequence of this CTA twice: a far cursor that asks L2 to fetch chunk seq + l2_ahead
-        // from HBM (cp.async.bulk.prefetch.L2: HBM keeps streaming while the consumers sit in an epilogue / grid barrier /
-        // prologue and the ring is full), and the ring cursor that copies chunk seq into its slot.
+        // Each producer walks the chunk sequence of this CTA (chunks seq % kDsProducerWarps == its index) and copies chunk seq into
+        // ring slot seq % n_slots as soon as the consumers have released it.  L2 prefetching of later chunks was measured and
+        // rejected twice: a cursor at a fixed distance of 8 / 16 chunks (3.65 / 5.4 ms per step vs 3.32) and a cursor that only runs
+        // while the ring is full, i.e. while the consumers sit in an exchange poll (3.17 / 3.25 / 3.87 / 4.51 ms at <= 4 / 8 / 12 / 16
+        // chunks vs 3.12): the extra requests lengthen exactly the exchange round trips the step is waiting on.
         if (lane != 0) return;
         const int pi = warp - kDsConsumerWarps;
         struct Cursor { int oi, j, j1, RJ, seq; };
@@ -677,28 +688,19 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
             c.j += c.RJ; ++c.seq;
             if (c.j >= c.j1) { ++c.oi; open_op(c); }
         };
-        auto prefetch = [&](const Cursor& c) {
-            const DsOp& op = p.ops[c.oi];
-            const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
-            const uint32_t bytes = static_cast<uint32_t>(min(c.RJ, c.j1 - c.j) * row_bytes);
-            ds_prefetch_l2(static_cast<const uint8_t*>(op.W0) + c.j * row_bytes, bytes);
-            if (op.nmat == 2) ds_prefetch_l2(static_cast<const uint8_t*>(op.W1) + c.j * row_bytes, bytes);
-        };
-        Cursor cur{0, 0, 0, 1, 0}, far{0, 0, 0, 1, 0};
+        Cursor cur{0, 0, 0, 1, 0};
         open_op(cur);
-        open_op(far);
-        const int ahead = (p.dbg_flags & 8) ? 0 : p.l2_ahead;
-        for (int i = 0; i < ahead && far.oi < p.n_ops; ++i) {
-            if (far.seq % kDsProducerWarps == pi) prefetch(far);
-            advance(far);
-        }
+        DS_PROBE(long long pb_blocked = 0; const long long pb_t0 = ds_gtimer();)
         while (cur.oi < p.n_ops) {
             if (cur.seq % kDsProducerWarps == pi) {
-                if (ahead > 0 && far.oi < p.n_ops) prefetch(far);      // far.seq == cur.seq + ahead: same producer parity when ahead is even
                 const DsOp& op = p.ops[cur.oi];
                 const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
                 const int slot = cur.seq % p.n_slots, use = cur.seq / p.n_slots;
-                if (use > 0) mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
+                if (use > 0) {
+                    DS_PROBE(const long long tb = ds_gtimer();)
+                    mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
+                    DS_PROBE(pb_blocked += ds_gtimer() - tb;)
+                }
                 if (p.max_inflight > 0 && cur.seq >= p.max_inflight) {
                     // Bound the requests queued in the memory system: every byte in flight beyond bandwidth x latency only
                     // lengthens the queue that the latency-critical accesses of the consumers (activations, barrier flags)
@@ -715,8 +717,8 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                     ds_bulk_g2s(dst + cur.RJ * row_bytes, static_cast<const uint8_t*>(op.W1) + cur.j * row_bytes, bytes, &full_bar[slot]);
             }
             advance(cur);
-            if (far.oi < p.n_ops) advance(far);
         }
+        DS_PROBE(if (p.dbg != nullptr && pi == 0) { p.dbg[8 * (cta + 1) + 3] += pb_blocked; p.dbg[8 * (cta + 1) + 5] += ds_gtimer() - pb_t0; if (cta == 0) { p.dbg[3] += pb_blocked; p.dbg[5] += ds_gtimer() - pb_t0; } })
         return;
     }
 
@@ -746,6 +748,9 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
     const uint32_t tag0 = epoch * static_cast<uint32_t>(p.n_ops + 1) + 1u;
     auto tag_of = [&](int oi) { return (tag0 + static_cast<uint32_t>(oi)) | 0x80000000u; };
     DsRingState rs{0, 0, 0};
+    long long probe_acc[2] = {0, 0};
+    long long* probe_w = nullptr;
+    DS_PROBE(if (timed) probe_w = probe_acc;)
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const DsOp& op = p.ops[oi];
         if (op.type == DS_GEMV) {
@@ -853,7 +858,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
             stamp(0);
             // ---- stream this CTA's rows through the ring
             const int P = op.P;
-            ds_ring_phase<T, NV>(op, full_bar, empty_bar, p.n_slots, p.x_bytes, p.xcap, p.dbg_flags, j0, j1, &rs);
+            ds_ring_phase<T, NV>(op, full_bar, empty_bar, p.n_slots, p.x_bytes, p.xcap, p.dbg_flags, j0, j1, &rs, probe_w);
             ds_consumer_sync();
             stamp(1);
             // ---- epilogue: one thread per output row (fixed-order sum of the parts); neighbouring lanes pair their rows into one
@@ -920,6 +925,8 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
                     p.dbg[8 * (cta + 1) + cat] += t_acc[c];
                     if (cta == 0) p.dbg[cat] += t_acc[c];
                 }
+                DS_PROBE(p.dbg[8 * (cta + 1) + 6] += probe_acc[0]; p.dbg[8 * (cta + 1) + 7] += probe_acc[1];
+                         if (cta == 0) { p.dbg[6] += probe_acc[0]; p.dbg[7] += probe_acc[1]; })
             }
             if (cta == 0 && warp == 0) {
                 int all_done = 1;

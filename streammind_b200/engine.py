@@ -378,6 +378,17 @@ class Engine:
                                           out.data_ptr(), M, N, K, epi, force_swap, force_bn, self._stream()))
         return out
 
+    def test_kv_attention(self, q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos0: int, n_splits: int = 0) -> torch.Tensor:
+        """q [P, Hq, 128] (rotated), kcache / vcache [Hk, max_ctx, 128] holding pos0 + P positions -> [P, Hq * 128].
+        n_splits: -1 mma.sync kernel, 0 tcgen05 kernel with the planned split, > 0 forced split count."""
+        P, Hq, D = q.shape
+        Hk, max_ctx, _ = kcache.shape
+        assert D == 128 and q.is_contiguous() and kcache.is_contiguous() and vcache.is_contiguous()
+        out = torch.empty(P, Hq * D, dtype=q.dtype, device=q.device)
+        self._check(self.lib.sm_test_kv_attention(self._h, q.data_ptr(), Hq * D, kcache.data_ptr(), vcache.data_ptr(), max_ctx,
+                                                  out.data_ptr(), P, pos0, Hq, Hk, n_splits, self._stream()))
+        return out
+
     def test_attention(self, qkv: torch.Tensor, B: int, S: int, H: int, D: int, mode: int = -1) -> torch.Tensor:
         """mode: -1 default kernel choice, 0 mma.sync kernel, 2 tcgen05 kernel (sm_debug_attention_mode)."""
         self._check(self.lib.sm_debug_attention_mode(self._h, mode))

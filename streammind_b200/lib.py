@@ -64,6 +64,7 @@ SYMBOLS = {
     "sm_test_gemm": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "sm_test_gemm_trace": (_I, [_VP, _VP]),
     "sm_test_attention": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "sm_test_kv_attention": (_I, [_VP, _VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     "sm_profile_enable": (_I, [_VP, _I]),
     "sm_profile_read": (_I, [_VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sm_profile_class_name": (C.c_char_p, [_I]),

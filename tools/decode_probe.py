@@ -48,11 +48,15 @@ print(f"layers {a.layers} ctx {a.ctx} streams {a.streams}: {ms_tok:.4f} ms/step,
       f"weights {gb / ms_tok * 1e3:.0f} GB/s (+KV {kv_gb / ms_tok * 1e3:.0f} GB/s), launches {eng.launch_count()}")
 if a.phases:
     torch.cuda.synchronize()
-    names = ["prologue", "ring-compute", "epilogue", "barrier", "attention", "final", "wait-first-chunk", "wait-later-chunks"]
+    # categories 3, 5, 6, 7 are only filled by a -DSMB_DS_WAITPROBE build (tools/gpu/ds_probe_build.sh, SMB_LIB_PATH)
+    names = ["prologue", "ring-compute", "epilogue", "producer-blocked", "attention", "producer-life", "wait-first-chunk", "wait-later-chunks"]
     v = buf.cpu().tolist()
     per = torch.tensor(v[8:8 + 8 * 148], dtype=torch.float64).view(148, 8) / st["steps"] / 1e3
-    for c, n in ((0, "prologue"), (1, "ring"), (2, "epilogue"), (4, "attention")):
+    for c, n in ((0, "prologue"), (1, "ring"), (2, "epilogue"), (4, "attention"), (3, "producer-blocked"), (5, "producer-life"),
+                 (6, "wait-first-chunk"), (7, "wait-later-chunks")):
         col = per[:, c]
+        if float(col.max()) == 0.0:
+            continue
         order = col.argsort()
         print(f"  per-CTA {n}: min {col.min():.0f} (cta {int(order[0])}), median {col.median():.0f}, max {col.max():.0f} (cta {int(order[-1])}); "
               f"lowest 5: {[int(x) for x in order[:5]]}, highest 5: {[int(x) for x in order[-5:]]}")
