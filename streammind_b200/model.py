@@ -353,22 +353,53 @@ class StreamMindB200ForCausalLM:
         text = tokenizer.batch_decode(torch.tensor([out_ids]), skip_special_tokens=True)[0].strip()
         return text, pred
 
+    HOST_CHECK_CHUNK = 16      # tokens decoded per device call while a stopping criterion has to be evaluated on the host
+
     def _stop_ids(self, kwargs) -> List[int]:
+        """Single-token stop ids run inside the device loop; criteria that need the host (multi-token keywords, any other
+        callable) are returned by ``_host_criteria`` and evaluated between device calls."""
         stops: List[int] = []
         for sc in kwargs.get("stopping_criteria", None) or []:
-            if getattr(sc, "needs_host_check", False):
-                raise NotImplementedError("multi-token stop keywords need a host-side check; only single-token "
-                                          "keywords (e.g. '</s>') run in the device loop")
             stops.extend(getattr(sc, "single_token_ids", []))
         eos = kwargs.get("eos_token_id", kwargs.get("pad_token_id", None))   # the demo passes pad_token_id=eos
         if eos is not None and eos not in stops:
             stops.append(int(eos))
         return stops
 
+    @staticmethod
+    def _host_criteria(kwargs) -> list:
+        return [sc for sc in (kwargs.get("stopping_criteria", None) or [])
+                if getattr(sc, "needs_host_check", not hasattr(sc, "single_token_ids"))]
+
     def _generate_from_dialogue(self, ids: Sequence[int], kwargs) -> List[int]:
         items = self._prefill_dialogue(ids)
-        out = self.engine.llm_decode(int(kwargs.get("max_new_tokens", 1024)), self._stop_ids(kwargs))
+        max_new, stops, host = int(kwargs.get("max_new_tokens", 1024)), self._stop_ids(kwargs), self._host_criteria(kwargs)
+        out = self.engine.llm_decode(max_new, stops) if not host else self._decode_with_host_check(max_new, stops, host)
         self._dialogue.commit(items, out)
+        return out
+
+    def _decode_with_host_check(self, max_new: int, stops: List[int], host: list) -> List[int]:
+        """Greedy decode with stopping criteria that only the host can evaluate (KeywordsStoppingCriteria with multi-token
+        keywords, mm_utils.py:616-647): the device decodes HOST_CHECK_CHUNK tokens per call, the host applies the criteria token
+        by token exactly as hf generate() does after every step -- on the NEW ids only, because the reference generates from
+        ``inputs_embeds`` (videollama2_mistral.py:426-431) -- and on a hit the tokens decoded past it are dropped and the cache
+        is rewound.  Between chunks the last token (never fed back by a decode call) goes through a one-position prefill,
+        whose logits start the next chunk."""
+        e = self.engine
+        out: List[int] = []
+        while len(out) < max_new:
+            kv0 = e.kv_len
+            part = e.llm_decode(min(self.HOST_CHECK_CHUNK, max_new - len(out)), stops)
+            for j, t in enumerate(part):
+                out.append(int(t))
+                if int(t) in stops or any(bool(sc(torch.tensor([out]), None)) for sc in host):
+                    e.kv_set_len(kv0 + j)          # the cache holds everything before the last kept token
+                    return out
+            if len(out) >= max_new or not part:
+                break
+            if e.kv_len + 1 >= e.cfg.llm_max_ctx:      # a full cache returns what fits
+                break
+            e.llm_prefill(e.embed_tokens(torch.tensor([out[-1]], dtype=torch.int32)))
         return out
 
     def _prefill_dialogue(self, ids: Sequence[int]) -> List[Item]:
@@ -539,6 +570,9 @@ class MultiStreamSession:
                 results[s] = (None, 0)
         max_new = int(kwargs.get("max_new_tokens", 1024))
         stops = self.streams[0]._stop_ids(kwargs)
+        if self.streams[0]._host_criteria(kwargs):
+            raise NotImplementedError("host-evaluated stopping criteria (multi-token keywords) are per stream: use "
+                                      "StreamMindB200ForCausalLM.stream_generate_demo for such a stream")
         for lo in range(0, len(firing), 4):                     # the decode kernel takes up to 4 streams per pass
             group = firing[lo:lo + 4]
             items = [self.streams[s]._prefill_dialogue(list(inputs[s])) for s in group]

@@ -66,6 +66,57 @@ def test_stream_generate_demo_vs_oracle(built_library, dt):
     model.engine.close()
 
 
+class KeywordTokenizer(IdTokenizer):
+    """a keyword string "a b c" tokenises to the ids [a, b, c] (what the reference's tokenizer(keyword).input_ids yields)"""
+
+    class _Enc:
+        def __init__(self, ids):
+            self.input_ids = ids
+
+    def __call__(self, text):
+        return self._Enc([int(t) for t in text.split()])
+
+
+def test_multi_token_stop_keyword_on_the_host(built_library):
+    """KeywordsStoppingCriteria with a multi-token keyword (reference mm_utils.py:616-647) cannot run in the device loop: the
+    model decodes in chunks, checks on the host after every token like hf generate(), cuts the output at the hit, rewinds the
+    cache, and the stream continues exactly as if the device had stopped there."""
+    from streammind_b200.mm_utils import KeywordsStoppingCriteria
+    dt = torch.bfloat16
+    cfg = engine_config(dt, max_frames=2, use_graphs=True)
+    sd = make_weights(cfg, llm=True)
+    model = StreamMindB200ForCausalLM(cfg, sd)
+    model.HOST_CHECK_CHUNK = 4                         # several chunk boundaries inside one answer
+    prompt0, turn_suffix = synth.make_prompt_ids(vocab=cfg.llm_vocab, n_sys=12, n_suffix=3)
+    frames = synth.make_frames(5, 0, 3, cfg.vit_image, dtype=dt)
+    tok = KeywordTokenizer()
+    ids = torch.tensor([list(prompt0)])
+    kw = dict(images_or_videos=frames[:1], modal_list=["video"], do_sample=False, use_cache=True, tokenizer=tok, force_pred=1)
+    free, _ = model.stream_generate_demo(ids, max_new_tokens=14, **kw)
+    free = [int(t) for t in free.split()]
+    assert len(free) == 14
+    # chunked decode without a hit reproduces the one-call decode (the chunk seams go through a one-position prefill)
+    never = KeywordsStoppingCriteria([f"{cfg.llm_vocab + 5} {cfg.llm_vocab + 6}"], tok, ids)
+    model.reset_stream()
+    chunked, _ = model.stream_generate_demo(ids, max_new_tokens=14, stopping_criteria=[never], **kw)
+    assert [int(t) for t in chunked.split()] == free
+    # a two-token keyword whose first occurrence lies beyond the first chunk
+    stop_at = next(j for j in range(5, 13) if not any(free[i:i + 2] == free[j:j + 2] for i in range(j)))
+    crit = KeywordsStoppingCriteria([f"{free[stop_at]} {free[stop_at + 1]}"], tok, ids)
+    assert crit.needs_host_check
+    model.reset_stream()
+    cut, _ = model.stream_generate_demo(ids, max_new_tokens=14, stopping_criteria=[crit], **kw)
+    cut = [int(t) for t in cut.split()]
+    assert cut == free[:stop_at + 2], (cut, free, stop_at)
+    assert model.engine.kv_len == model.last_prefill_len + len(cut) - 1       # everything but the last kept token is cached
+    # the stream goes on: next turn re-uses the cached prefix (only the suffix + the new frame token are prefilled)
+    ids2 = torch.tensor([list(prompt0) + cut + turn_suffix])
+    nxt, pred = model.stream_generate_demo(ids2, max_new_tokens=4, **{**kw, "images_or_videos": frames[1:2]})
+    assert pred == 1 and len(nxt.split()) == 4
+    assert model.last_prefill_len == 1 + len(turn_suffix)                     # last kept token + suffix (its <video> included)
+    model.engine.close()
+
+
 def test_component_hooks(built_library):
     dt = torch.float16
     cfg = engine_config(dt, max_frames=2, llm_layers=0, use_graphs=False)
