@@ -1063,7 +1063,7 @@ int launch_decode_step_t(sm_handle* h, int nv, cudaStream_t st) {
         p.dbg_flags = flags;
         p.max_inflight = inflight >= m.n_slots ? 0 : std::max(0, inflight);
     }
-    const dim3 grid(h->num_sms), block(kDsThreads);
+    const dim3 grid(h->num_sms), block(ds_threads(nv));
     {
         static bool once = false;
         if (!once && getenv("SMB_DS_POLL_NS")) { const unsigned ns = atoi(getenv("SMB_DS_POLL_NS")); cudaMemcpyToSymbol(ds_poll_ns, &ns, sizeof ns); }

@@ -35,9 +35,13 @@ constexpr int kDsGroupWarps = 8;            // warps that share one ring slot: o
 #endif
 constexpr int kDsGroups = SMB_DS_GROUPS;    // consumer groups; group g takes the chunks with seq % kDsGroups == g
 constexpr int kDsConsumerWarps = kDsGroupWarps * kDsGroups;
-constexpr int kDsProducerWarps = 2;
+// Producer warps of a launch with nv streams (one issuing thread each; a thread's bulk copies execute one at a time, so the copies
+// in flight per SM = the issuing threads).  Measured at ctx 2048 (tools/decode_probe.py): one stream 3.05 ms per step with three
+// producer warps vs 3.14 with two; two / four streams 4.32 / 6.87 vs 4.05 / 6.27 -- the third warp is worth it for one stream only
+// (how many of the warps issue matters less than the block shape: 2 .. 6 issuing threads in the 11-warp block all give 3.07-3.15).
+__host__ __device__ constexpr int ds_producer_warps(int nv) { return nv == 1 ? 3 : 2; }
+__host__ __device__ constexpr int ds_threads(int nv) { return (kDsConsumerWarps + ds_producer_warps(nv)) * 32; }
 constexpr int kDsConsumerThreads = kDsConsumerWarps * 32;
-constexpr int kDsThreads = (kDsConsumerWarps + kDsProducerWarps) * 32;
 constexpr int kDsSlotBytes = 32 * 1024;
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxStreams = 4;
@@ -644,7 +648,7 @@ __device__ __forceinline__ void ds_ring_phase(const DsOp& op, uint64_t* full_bar
 }
 
 template <typename T, int NV>
-__global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsParams p) {
+__global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const DsParams p) {
     extern __shared__ __align__(128) uint8_t ds_smem[];
     uint8_t* ring = ds_smem;                                                       // [n_slots][32 KB]
     T* xs = reinterpret_cast<T*>(ds_smem + static_cast<size_t>(p.n_slots) * kDsSlotBytes);   // [NV][xcap]; attention scratch aliases it
@@ -667,13 +671,14 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
 
     if (warp >= kDsConsumerWarps) {
         // ================================================================== producers: the weight stream
-        // Each producer walks the chunk sequence of this CTA (chunks seq % kDsProducerWarps == its index) and copies chunk seq into
+        // Each producer walks the chunk sequence of this CTA (chunks seq % (producer warps) == its index) and copies chunk seq into
         // ring slot seq % n_slots as soon as the consumers have released it.  L2 prefetching of later chunks was measured and
         // rejected twice: a cursor at a fixed distance of 8 / 16 chunks (3.65 / 5.4 ms per step vs 3.32) and a cursor that only runs
         // while the ring is full, i.e. while the consumers sit in an exchange poll (3.17 / 3.25 / 3.87 / 4.51 ms at <= 4 / 8 / 12 / 16
         // chunks vs 3.12): the extra requests lengthen exactly the exchange round trips the step is waiting on.
-        if (lane != 0) return;
+        constexpr int np = ds_producer_warps(NV);
         const int pi = warp - kDsConsumerWarps;
+        if (lane != 0) return;
         struct Cursor { int oi, j, j1, RJ, seq; };
         auto open_op = [&](Cursor& c) {            // position the cursor on the first chunk of the next GEMV op (oi = n_ops: end)
             for (; c.oi < p.n_ops; ++c.oi) {
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) decode_stream_kernel(const DsPa
         open_op(cur);
         DS_PROBE(long long pb_blocked = 0; const long long pb_t0 = ds_gtimer();)
         while (cur.oi < p.n_ops) {
-            if (cur.seq % kDsProducerWarps == pi) {
+            if (cur.seq % np == pi) {
                 const DsOp& op = p.ops[cur.oi];
                 const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
                 const int slot = cur.seq % p.n_slots, use = cur.seq / p.n_slots;

@@ -5,6 +5,7 @@
 //           per-CTA contiguous regions (pattern 0) or grid-interleaved 8 KB blocks (pattern 1)
 //   bulk  : one CTA per SM, cp.async.bulk (1-D) into an NS-stage ring of SB-byte slots, 8 consumer warps read the
 //           slot back from shared memory (LDS.128 + FADD) and release it through an mbarrier
+#include <array>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -106,7 +107,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // one CTA per SM; warp 8 = producer; warps 0..7 consume.  chunk: bytes per bulk copy (a slot is filled by SB / chunk copies)
-__global__ void __launch_bounds__(288) bulk_kernel(const uint8_t* __restrict__ src, size_t bytes, int NS, int SB, int chunk, int pattern, float* out) {
+__global__ void __launch_bounds__(288) bulk_kernel(const uint8_t* __restrict__ src, size_t bytes, int NS, int SB, int chunk, int pattern, float* out, int reps = 1) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full[16], empty[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +120,8 @@ __global__ void __launch_bounds__(288) bulk_kernel(const uint8_t* __restrict__ s
     size_t my0, mycount, stride;
     if (pattern == 0) { mycount = nslots_total / gridDim.x; my0 = mycount * blockIdx.x; stride = 1; }
     else { mycount = nslots_total / gridDim.x; my0 = blockIdx.x; stride = gridDim.x; }
+    const size_t region = mycount;          // reps > 1: the CTA walks its region reps times (L2-resident when the buffer is small)
+    mycount *= reps;
     if (warp == 8) {
         if (lane == 0) {
             for (size_t i = 0; i < mycount; ++i) {
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(288) bulk_kernel(const uint8_t* __restrict__ s
                 const uint32_t ph = static_cast<uint32_t>((i / NS) & 1);
                 if (i >= static_cast<size_t>(NS)) mbar_wait(&empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full[s], SB);
-                const uint8_t* g = src + (my0 + i * stride) * SB;
+                const uint8_t* g = src + (my0 + (i % region) * stride) * SB;
                 for (int c = 0; c < SB; c += chunk) bulk_g2s(smem + static_cast<size_t>(s) * SB + c, g + c, chunk, &full[s]);
             }
         }
@@ -203,6 +206,15 @@ int main(int argc, char** argv) {
     for (auto& c : cfgs2) {
         snprintf(nm, sizeof nm, "bulk x2/SM NS=%d SB=%d chunk=%d pattern=%d", c[0], c[1], c[2], c[3]);
         report(nm, time_ms([&] { bulk_kernel<<<sms * 2, 288, c[0] * c[1]>>>(buf, bytes, c[0], c[1], c[2], c[3], out); }, 5));
+    }
+    // L2-resident: every SM re-reads its own 192 KB / 384 KB region 256 times (28 / 57 MB in total): what a bulk-copy ring can ingest from L2
+    for (int kb : {192, 384}) {
+        const size_t small = static_cast<size_t>(sms) * kb * 1024;
+        const int reps = 256;
+        for (auto& c : {std::array<int, 3>{6, 32768, 32768}, std::array<int, 3>{3, 65536, 65536}, std::array<int, 3>{12, 16384, 16384}}) {
+            float ms = time_ms([&] { bulk_kernel<<<sms, 288, c[0] * c[1]>>>(buf, small, c[0], c[1], c[2], 0, out, reps); }, 3);
+            printf("bulk L2-resident %3d KB/SM NS=%d SB=%d      %8.3f ms  %8.1f GB/s\n", kb, c[0], c[1], ms, double(small) * reps / ms * 1e-6);
+        }
     }
     // reference: device-to-device copy (read + write bytes), as MEASURED_PEAKS.json counts it
     uint8_t* dst;
