@@ -124,7 +124,7 @@ struct DsParams {
     unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
     unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
     int max_inflight;        // bulk copies of this CTA that may be in flight at once (0 = as many as the ring has free slots)
-    int dbg_flags;           // measurement only: 1 skip the consumer math
+    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone)
     long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
 
@@ -246,7 +246,7 @@ __device__ __forceinline__ T ds_ldcg_t(const T* p) {
 // the K / V rows of the first block (64 registers) are in flight.
 template <typename T, int NV>
 __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamState* st, unsigned long long* att_part, T* xs,
-                                            uint32_t tag_in, uint32_t tag_out) {
+                                            const float (*rope_cs)[128], uint32_t tag_in, uint32_t tag_out) {
     const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     // ------------------------------------------------------------------ decode attention, split over the KV length
@@ -297,17 +297,13 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
         load_block(kb_first);
         // Poll the projection's words of this kv head and rotate them in the same thread: a job is two adjacent dims d, d + 1
         // (d < D/2) of a q head / the new k -- the word holding them and the word holding d + D/2, d + D/2 + 1 -- or one word
-        // of the new v.  cos / sin of the position (hf MistralRotaryEmbedding: fp32 angle, cos / sin cast to T) are evaluated
-        // while the first poll is in flight.
+        // of the new v.  cos / sin of the position come from the step's table (rope_cs, filled once per launch).
         for (int jb = tid; jb < (group + 1) * (D / 4) + D / 2; jb += kDsConsumerThreads) {
             if (jb < (group + 1) * (D / 4)) {
                 const int hh = jb / (D / 4), d = 2 * (jb % (D / 4));
                 const unsigned long long* wa = ql + (((hh < group ? (hk * group + hh) * D : (Hq + hk) * D) + d) >> 1);
                 unsigned long long ra = ds_ll_load(wa), rb = ds_ll_load(wa + D / 4);
-                float cs0, sn0, cs1, sn1;
-                sincosf(pos * powf(op.rope_theta, -2.0f * d / D), &sn0, &cs0);
-                sincosf(pos * powf(op.rope_theta, -2.0f * (d + 1) / D), &sn1, &cs1);
-                cs0 = rnd<T>(cs0); sn0 = rnd<T>(sn0); cs1 = rnd<T>(cs1); sn1 = rnd<T>(sn1);
+                const float cs0 = rope_cs[v][d], sn0 = rope_cs[v][D / 2 + d], cs1 = rope_cs[v][d + 1], sn1 = rope_cs[v][D / 2 + d + 1];
                 unsigned spins = 0;
                 while (!(ds_ll_ok(ra, tag_in) && ds_ll_ok(rb, tag_in))) { ds_ll_retry(spins, tag_in); ra = ds_ll_load(wa); rb = ds_ll_load(wa + D / 4); }
                 const float2 x1 = Cvt<T>::unpack2(static_cast<uint32_t>(ra)), x2 = Cvt<T>::unpack2(static_cast<uint32_t>(rb));
@@ -486,7 +482,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
             const int p0 = s * cnt, p1 = min(npair, p0 + cnt);
             const unsigned long long* pbase = att_part + (static_cast<long long>(v) * Hq + hk * group) * S * (D + 2);
-            constexpr int UM = 1;
+            constexpr int UM = 1;      // (pairs x slices) of a CTA can exceed the 256 threads by a few: both polls of a thread in flight together
             for (int i0 = tid; i0 < (p1 - p0) * S; i0 += UM * kDsConsumerThreads) {
                 unsigned long long r[UM][4];
                 const unsigned long long* q[UM];
@@ -586,6 +582,7 @@ __device__ __forceinline__ void ds_ring_phase(const DsOp& op, uint64_t* full_bar
     const uint2* ring_u2 = reinterpret_cast<const uint2*>(ring) + (static_cast<size_t>(sr) * K + c0) / 4 + lane;
     float* part_w = part + (static_cast<size_t>(m) * nloc * P + pt) * NV;           // + local row * P * NV
     const int skip_math = dbg_flags & 1;
+    if (dbg_flags & 2) return;
     for (int j = j0; j < j1; j += RJ, ++rs.seq) {
         const int slot = rs.slot, par = rs.par;
         if (++rs.slot == n_slots) { rs.slot = 0; rs.par ^= 1; }
@@ -658,6 +655,7 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
     __shared__ float cand_v[kDsConsumerWarps];
     __shared__ int cand_i[kDsConsumerWarps];
     __shared__ float resid_own[NV][kDsResidRows];      // this CTA's rows of the residual stream (values of T)
+    __shared__ float rope_cs[NV][128];                 // cos [0, 64) and sin [64, 128) of each stream's position (values of T)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -695,6 +693,7 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
         };
         Cursor cur{0, 0, 0, 1, 0};
         open_op(cur);
+        if (p.dbg_flags & 2) return;        // measurement only: no weight stream at all (the exchange chain alone)
         DS_PROBE(long long pb_blocked = 0; const long long pb_t0 = ds_gtimer();)
         while (cur.oi < p.n_ops) {
             if (cur.seq % np == pi) {
@@ -747,6 +746,19 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
         for (int i = tid; i < NV * hn; i += kDsConsumerThreads) {
             const int v = i / hn, r = i - v * hn;
             resid_own[v][r] = Cvt<T>::to_f((reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(p.st[v].tok) * p.H)[h0 + r]);
+        }
+    }
+    {   // cos / sin of every stream's position, once per step instead of once per layer (hf MistralRotaryEmbedding: fp32 angle
+        // pos * theta^(-2 d / D), cos / sin cast to T); first read after the consumer barriers of the first GEMV op
+        float theta = 0.f;
+        for (int oi = 0; oi < p.n_ops; ++oi)
+            if (p.ops[oi].type == DS_ATTN) { theta = p.ops[oi].rope_theta; break; }
+        for (int i = tid; i < NV * 64; i += kDsConsumerThreads) {
+            const int v = i >> 6, d = i & 63;
+            float sn, cs;
+            sincosf(p.st[v].pos * powf(theta, -2.0f * d / 128), &sn, &cs);
+            rope_cs[v][d] = rnd<T>(cs);
+            rope_cs[v][64 + d] = rnd<T>(sn);
         }
     }
     // tag of what op oi publishes in this step (never 0: a buffer that was never written cannot match)
@@ -919,7 +931,7 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
             }
             stamp(2);
         } else if (op.type == DS_ATTN) {
-            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, tag_of(oi - 1), tag_of(oi));
+            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, rope_cs, tag_of(oi - 1), tag_of(oi));
             stamp(4);
         } else {
             // ------------------------------------------------------------------ DS_FINAL: token selection (CTA 0)
