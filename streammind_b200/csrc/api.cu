@@ -1059,9 +1059,7 @@ int launch_decode_step_t(sm_handle* h, int nv, cudaStream_t st) {
     p.cand = h->ds_cand; p.dbg = h->ds_dbg;
     {
         static const int flags = getenv("SMB_DS_DBG") ? atoi(getenv("SMB_DS_DBG")) : 0;
-        static const int inflight = getenv("SMB_DS_INFLIGHT") ? atoi(getenv("SMB_DS_INFLIGHT")) : 0;
         p.dbg_flags = flags;
-        p.max_inflight = inflight >= m.n_slots ? 0 : std::max(0, inflight);
     }
     const dim3 grid(h->num_sms), block(ds_threads(nv));
     {

@@ -45,6 +45,7 @@ constexpr int kDsConsumerThreads = kDsConsumerWarps * 32;
 constexpr int kDsSlotBytes = 32 * 1024;
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxStreams = 4;
+constexpr int kDsKvBlock = 128;             // keys per K / V chunk of the attention op (128 rows of 256 bytes = one ring slot)
 constexpr int kDsResidRows = 64;            // rows of the residual stream one CTA may own (hidden <= 64 x SMs)
 
 // -DSMB_DS_WAITPROBE (measurement builds only, tools/gpu/ds_probe_build.sh): producer 0 of every CTA accumulates the time it is blocked on
@@ -123,7 +124,6 @@ struct DsParams {
     int H;
     unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
     unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
-    int max_inflight;        // bulk copies of this CTA that may be in flight at once (0 = as many as the ring has free slots)
     int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone)
     long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
@@ -240,21 +240,26 @@ __device__ __forceinline__ T ds_ldcg_t(const T* p) {
     return t;
 }
 
+struct DsRingState { int seq, slot, par; };   // chunk sequence number of this CTA, its ring slot and the parity of that slot's use
+
 // The attention op of the decode kernel.  Register discipline matters here: if the kernel spills anywhere, ptxas schedules the
 // WHOLE kernel for low register use and pairs every shared-memory load of the weight-streaming loop with its MMA (the loop
 // then runs at load latency: +30 % per step, measured).  So the projection's words are polled at most two at a time while
 // the K / V rows of the first block (64 registers) are in flight.
 template <typename T, int NV>
 __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamState* st, unsigned long long* att_part, T* xs,
-                                            const float (*rope_cs)[128], uint32_t tag_in, uint32_t tag_out) {
+                                            const float (*rope_cs)[128], uint32_t tag_in, uint32_t tag_out, const uint8_t* ring,
+                                            uint64_t* full_bar, uint64_t* empty_bar, int n_slots, DsRingState* state) {
     const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     // ------------------------------------------------------------------ decode attention, split over the KV length
-    // Every dependent global access costs ~2 us while the weight stream saturates HBM, so the op is arranged as few
-    // dependent rounds as possible: (1) q / new k / new v (polled from the projection's exchange words) AND this
-    // warp's K rows AND its V rows (asked into L2 one op earlier) are requested together; (2) RoPE, scores, softmax,
-    // P.V from registers / shared memory; (3) the slice's partial is published as tagged words; (4) the CTA of slice 0
-    // of a (lane, kv head) polls all slices and merges them in fixed order: no counter, no fence, no grid barrier.
+    // Every dependent global access costs ~2 us while the weight stream saturates HBM (a cache row that misses L2 waits behind
+    // ~28 MB of queued weight copies: measured ~6 us per layer when the K / V rows were loaded by the consumers), so the op is
+    // arranged as few dependent rounds as possible: (1) the K / V rows of the slice travel through the WEIGHT RING -- the
+    // producers copy them, 128 keys per chunk, K then V, between the chunks of the projection before and after this op, i.e.
+    // several chunks ahead of the consumers -- and q / new k / new v are polled from the projection's exchange words;
+    // (2) RoPE, scores, softmax, P.V from shared memory; (3) the slice's partial is published as tagged words; (4) the CTAs
+    // of a (lane, kv head) poll all slices and merge them in fixed order: no counter, no fence, no grid barrier.
     constexpr int D = 128, VPL = 4, KB = 16, GM = 4;   // GM query heads per pass (GQA groups of 8: two passes)              // KB keys per warp block: lane pair = key, lane = 4 output dims
     const int Hq = op.Hq, Hk = op.Hk, group = Hq / Hk;
     const int S = max(1, G / Hk);                        // KV slices per (lane, kv head): independent of NV, so a stream's
@@ -267,6 +272,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
     float* sm_l = sm_m + kDsGroupWarps * 8;
     float* sm_o = sm_l + kDsGroupWarps * 8;               // [8][group][D]
     float* sm_p = sm_o + kDsGroupWarps * group * D + warp * group * KB;   // this warp's [group][KB] probabilities of a key block
+    DsRingState rs = *state;
     for (int item = cta; item < NV * Hk * S; item += G) {
         const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
         const int pos = st[v].pos, kv_len = pos + 1;
@@ -277,24 +283,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
         const int per = (kv_len + S - 1) / S;
         const int kbeg = s * per, kend = min(kv_len, kbeg + per);
         const int half = lane & 1, kslot = lane >> 1;        // this lane scores dims [64 half, 64 half + 64) of key kb0 + kslot
-        // ---- round 1: everything that does not depend on anything else is requested now
-        uint4 kreg[D / 16];                                 // half a K row (64 dims) of this lane's key
-        uint2 vreg[KB];                                     // V (this lane's 4 dims) of the block's keys
-        const int kb_first = kbeg + warp * KB;
-        auto load_block = [&](int kb0) {
-            const int key = kb0 + kslot;
-            if (key < kend && key != pos) {
-                const uint4* krow = reinterpret_cast<const uint4*>(kcache + static_cast<long long>(key) * D + half * (D / 2));
-#pragma unroll
-                for (int c = 0; c < D / 16; ++c) kreg[c] = krow[c];
-            }
-#pragma unroll
-            for (int b = 0; b < KB; ++b) {
-                const int kk = kb0 + b;
-                if (kk < kend && kk != pos) vreg[b] = *reinterpret_cast<const uint2*>(vcache + static_cast<long long>(kk) * D + lane * VPL);
-            }
-        };
-        load_block(kb_first);
+        const int nblk = (max(0, kend - kbeg) + kDsKvBlock - 1) / kDsKvBlock;   // 128-key blocks of the slice = (K, V) chunk pairs in the ring, per pass
         // Poll the projection's words of this kv head and rotate them in the same thread: a job is two adjacent dims d, d + 1
         // (d < D/2) of a q head / the new k -- the word holding them and the word holding d + D/2, d + D/2 + 1 -- or one word
         // of the new v.  cos / sin of the position come from the step's table (rope_cs, filled once per launch).
@@ -325,7 +314,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             vcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_vn[tid]);
         }
         for (int gb = 0; gb < group; gb += GM) {
-        if (gb > 0) { ds_consumer_sync(); load_block(kb_first); }     // second pass of a wide GQA group re-reads K / V
+        if (gb > 0) ds_consumer_sync();      // second pass of a wide GQA group: the producers stream K / V once more
         // ---- round 2: per warp, blocks of KB keys.  Scores: a lane pair owns a key (64 dims each against the group's
         // q heads broadcast from shared memory, one shuffle per head); block-wise online softmax (one warp_max per
         // head per block); P.V: lane = 4 output dims, probabilities broadcast from shared memory.
@@ -336,8 +325,18 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
 #pragma unroll
             for (int i = 0; i < VPL; ++i) o[g][i] = 0.f;
         }
-        for (int kb0 = kb_first; kb0 < kend; kb0 += kDsConsumerWarps * KB) {
-            if (kb0 != kb_first) load_block(kb0);     // slices longer than 16 warps x 16 keys (ctx > 4.6k): next round
+        for (int blk = 0; blk < nblk; ++blk) {
+            // chunk pair of this block: K rows then V rows of keys [kbeg + 128 blk, + 128), one 256-byte row per key
+            const int slot_k = rs.slot, par_k = rs.par;
+            if (++rs.slot == n_slots) { rs.slot = 0; rs.par ^= 1; }
+            const int slot_v = rs.slot, par_v = rs.par;
+            if (++rs.slot == n_slots) { rs.slot = 0; rs.par ^= 1; }
+            rs.seq += 2;
+            const uint8_t* sk = ring + static_cast<size_t>(slot_k) * kDsSlotBytes + (warp * KB) * (D * sizeof(T));
+            const uint8_t* sv = ring + static_cast<size_t>(slot_v) * kDsSlotBytes + (warp * KB) * (D * sizeof(T));
+            const int kb0 = kbeg + blk * kDsKvBlock + warp * KB;          // this warp's 16 keys of the block
+            mbar_wait_hint(&full_bar[slot_k], par_k);
+            if (kb0 < kend) {
             const int key = kb0 + kslot;
             const bool valid = key < kend;
             float sc[GM];
@@ -346,13 +345,16 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             if (valid && key != pos) {
 #pragma unroll
                 for (int c = 0; c < D / 16; ++c) {
-                    const uint4 u = kreg[c];
+                    // 16-byte pieces of the half row in an order rotated by the key: rows are 256 bytes apart, so the lanes of a
+                    // quarter warp would otherwise all read the same banks
+                    const int cc = (c + kslot) & (D / 16 - 1);
+                    const uint4 u = *reinterpret_cast<const uint4*>(sk + kslot * (D * sizeof(T)) + half * (D / 2) * sizeof(T) + cc * 16);
                     const float2 k0 = Cvt<T>::unpack2(u.x), k1 = Cvt<T>::unpack2(u.y), k2 = Cvt<T>::unpack2(u.z), k3 = Cvt<T>::unpack2(u.w);
 #pragma unroll
                     for (int g = 0; g < GM; ++g) {
                         if (gb + g < group) {
-                            const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8);
-                            const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + c * 8 + 4);
+                            const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + cc * 8);
+                            const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + cc * 8 + 4);
                             float t = sc[g];
                             t = fmaf(qa.x, k0.x, t); t = fmaf(qa.y, k0.y, t); t = fmaf(qa.z, k1.x, t); t = fmaf(qa.w, k1.y, t);
                             t = fmaf(qb.x, k2.x, t); t = fmaf(qb.y, k2.y, t); t = fmaf(qb.z, k3.x, t); t = fmaf(qb.w, k3.y, t);
@@ -383,6 +385,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                 }
             }
             __syncwarp();
+            mbar_wait_hint(&full_bar[slot_v], par_v);
 #pragma unroll
             for (int g = 0; g < GM; ++g)
                 if (gb + g < group) {
@@ -398,7 +401,8 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
 #pragma unroll
                         for (int i = 0; i < VPL; ++i) vv[i] = sm_vn[lane * VPL + i];
                     } else {
-                        const float2 a = Cvt<T>::unpack2(vreg[b].x), bb = Cvt<T>::unpack2(vreg[b].y);
+                        const uint2 vr = *reinterpret_cast<const uint2*>(sv + b * (D * sizeof(T)) + lane * (VPL * sizeof(T)));
+                        const float2 a = Cvt<T>::unpack2(vr.x), bb = Cvt<T>::unpack2(vr.y);
                         vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
                     }
 #pragma unroll
@@ -410,7 +414,11 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                         }
                 }
             }
+            } else {
+                mbar_wait_hint(&full_bar[slot_v], par_v);      // nothing of this block for this warp: it still releases the chunks
+            }
             __syncwarp();
+            if (lane == 0) { mbar_arrive(&empty_bar[slot_k]); mbar_arrive(&empty_bar[slot_v]); }
         }
 #pragma unroll
         for (int g = 0; g < GM; ++g)
@@ -472,6 +480,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
         ds_consumer_sync();      // the scratch is rewritten by the next pass / item / op
         }   // gb
     }
+    *state = rs;
     // ---- round 4: the S CTAs of a (lane, kv head) share the merge: CTA s takes output pairs [s cnt, (s + 1) cnt) of the
     // group's heads, polls their partials of ALL slices in one round (a thread per (pair, slice)), then one thread
     // per pair folds the slices in fixed order and publishes the word
@@ -542,7 +551,6 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
     }
 }
 
-struct DsRingState { int seq, slot, par; };   // chunk sequence number of this CTA, its ring slot and the parity of that slot's use
 
 // The weight-streaming phase of a GEMV op.
 template <typename T, int NV>
@@ -670,57 +678,59 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
     if (warp >= kDsConsumerWarps) {
         // ================================================================== producers: the weight stream
         // Each producer walks the chunk sequence of this CTA (chunks seq % (producer warps) == its index) and copies chunk seq into
-        // ring slot seq % n_slots as soon as the consumers have released it.  L2 prefetching of later chunks was measured and
-        // rejected twice: a cursor at a fixed distance of 8 / 16 chunks (3.65 / 5.4 ms per step vs 3.32) and a cursor that only runs
-        // while the ring is full, i.e. while the consumers sit in an exchange poll (3.17 / 3.25 / 3.87 / 4.51 ms at <= 4 / 8 / 12 / 16
-        // chunks vs 3.12): the extra requests lengthen exactly the exchange round trips the step is waiting on.
+        // ring slot seq % n_slots as soon as the consumers have released it.  The sequence follows the op list: the row chunks
+        // of a GEMV op; for an attention op the K rows and the V rows of every 128-key block of this CTA's KV slice(s) -- the cache
+        // rows reach shared memory through the same pipelined stream as the weights, requested while the projection before the
+        // attention is still being reduced.  L2 prefetching of later chunks was measured and rejected twice: a cursor at a fixed
+        // distance of 8 / 16 chunks (3.65 / 5.4 ms per step vs 3.32) and a cursor that only runs while the ring is full, i.e. while
+        // the consumers sit in an exchange poll (3.17 / 3.25 / 3.87 / 4.51 ms at <= 4 / 8 / 12 / 16 chunks vs 3.12).
+        if (lane != 0) return;
         constexpr int np = ds_producer_warps(NV);
         const int pi = warp - kDsConsumerWarps;
-        if (lane != 0) return;
-        struct Cursor { int oi, j, j1, RJ, seq; };
-        auto open_op = [&](Cursor& c) {            // position the cursor on the first chunk of the next GEMV op (oi = n_ops: end)
-            for (; c.oi < p.n_ops; ++c.oi) {
-                const DsOp& op = p.ops[c.oi];
-                if (op.type != DS_GEMV) continue;
-                const int rpc = ds_rows_per_cta(op.N, G);
-                c.j = min(op.N, cta * rpc); c.j1 = min(op.N, c.j + rpc); c.RJ = op.R / op.nmat;
-                if (c.j < c.j1) return;
-            }
-        };
-        auto advance = [&](Cursor& c) {
-            c.j += c.RJ; ++c.seq;
-            if (c.j >= c.j1) { ++c.oi; open_op(c); }
-        };
-        Cursor cur{0, 0, 0, 1, 0};
-        open_op(cur);
-        if (p.dbg_flags & 2) return;        // measurement only: no weight stream at all (the exchange chain alone)
+        int seq = 0;
         DS_PROBE(long long pb_blocked = 0; const long long pb_t0 = ds_gtimer();)
-        while (cur.oi < p.n_ops) {
-            if (cur.seq % np == pi) {
-                const DsOp& op = p.ops[cur.oi];
-                const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
-                const int slot = cur.seq % p.n_slots, use = cur.seq / p.n_slots;
+        auto put = [&](const void* s0, const void* s1, uint32_t bytes, uint32_t off1) {       // chunk seq: one or two copies into its slot
+            if (seq % np == pi) {
+                const int slot = seq % p.n_slots, use = seq / p.n_slots;
                 if (use > 0) {
                     DS_PROBE(const long long tb = ds_gtimer();)
                     mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
                     DS_PROBE(pb_blocked += ds_gtimer() - tb;)
                 }
-                if (p.max_inflight > 0 && cur.seq >= p.max_inflight) {
-                    // Bound the requests queued in the memory system: every byte in flight beyond bandwidth x latency only
-                    // lengthens the queue that the latency-critical accesses of the consumers (activations, barrier flags)
-                    // wait in.  Chunk seq is issued once chunk seq - max_inflight has landed.
-                    const int ps = cur.seq - p.max_inflight;
-                    mbar_wait_hint(&full_bar[ps % p.n_slots], (ps / p.n_slots) & 1);
-                }
-                const int nr = min(cur.RJ, cur.j1 - cur.j);
-                const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
-                mbar_arrive_expect_tx(&full_bar[slot], bytes * op.nmat);
+                mbar_arrive_expect_tx(&full_bar[slot], s1 ? 2 * bytes : bytes);
                 uint8_t* dst = ring + static_cast<size_t>(slot) * kDsSlotBytes;
-                ds_bulk_g2s(dst, static_cast<const uint8_t*>(op.W0) + cur.j * row_bytes, bytes, &full_bar[slot]);
-                if (op.nmat == 2)
-                    ds_bulk_g2s(dst + cur.RJ * row_bytes, static_cast<const uint8_t*>(op.W1) + cur.j * row_bytes, bytes, &full_bar[slot]);
+                ds_bulk_g2s(dst, s0, bytes, &full_bar[slot]);
+                if (s1) ds_bulk_g2s(dst + off1, s1, bytes, &full_bar[slot]);
             }
-            advance(cur);
+            ++seq;
+        };
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const DsOp& op = p.ops[oi];
+            if (op.type == DS_GEMV) {
+                if (p.dbg_flags & 2) continue;          // measurement only: no weight stream (the exchange chain alone)
+                const int rpc = ds_rows_per_cta(op.N, G);
+                const int j0 = min(op.N, cta * rpc), j1 = min(op.N, j0 + rpc), RJ = op.R / op.nmat;
+                const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
+                for (int j = j0; j < j1; j += RJ) {
+                    const uint32_t bytes = static_cast<uint32_t>(min(RJ, j1 - j) * row_bytes);
+                    put(static_cast<const uint8_t*>(op.W0) + j * row_bytes,
+                        op.nmat == 2 ? static_cast<const uint8_t*>(op.W1) + j * row_bytes : nullptr, bytes, static_cast<uint32_t>(RJ * row_bytes));
+                }
+            } else if (op.type == DS_ATTN) {
+                const int Hk = op.Hk, group = op.Hq / Hk, S = max(1, G / Hk), npass = (group + 3) / 4;
+                for (int item = cta; item < NV * Hk * S; item += G) {
+                    const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
+                    const int kv_len = p.st[v].pos + 1, per = (kv_len + S - 1) / S;
+                    const int kbeg = s * per, kend = min(kv_len, kbeg + per);
+                    const long long base = p.st[v].kv_slot * op.kv_stream_stride + static_cast<long long>(hk) * op.max_ctx * 128;
+                    for (int pass = 0; pass < npass; ++pass)
+                        for (int kb = kbeg; kb < kend; kb += kDsKvBlock) {
+                            const uint32_t bytes = static_cast<uint32_t>(min(kDsKvBlock, kend - kb)) * 128u * static_cast<uint32_t>(sizeof(T));
+                            put(reinterpret_cast<const T*>(op.kc) + base + static_cast<long long>(kb) * 128, nullptr, bytes, 0u);
+                            put(reinterpret_cast<const T*>(op.vc) + base + static_cast<long long>(kb) * 128, nullptr, bytes, 0u);
+                        }
+                }
+            }
         }
         DS_PROBE(if (p.dbg != nullptr && pi == 0) { p.dbg[8 * (cta + 1) + 3] += pb_blocked; p.dbg[8 * (cta + 1) + 5] += ds_gtimer() - pb_t0; if (cta == 0) { p.dbg[3] += pb_blocked; p.dbg[5] += ds_gtimer() - pb_t0; } })
         return;
@@ -775,23 +785,6 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
             const int rpc = ds_rows_per_cta(op.N, G);
             const int j0 = min(op.N, cta * rpc), j1 = min(op.N, j0 + rpc);
             const int nloc = j1 - j0;
-            if (oi + 1 < p.n_ops && p.ops[oi + 1].type == DS_ATTN && tid == 0) {
-                // The K / V rows the attention op after this projection will read do not depend on it: ask L2 for this CTA's
-                // slices now, so that they arrive under the weight stream instead of behind it.
-                const DsOp& an = p.ops[oi + 1];
-                const int S = max(1, G / an.Hk);
-                for (int item = cta; item < NV * an.Hk * S; item += G) {
-                    const int v = item / (an.Hk * S), hk = (item / S) % an.Hk, sl = item % S;
-                    const int pos = p.st[v].pos, per = (pos + 1 + S - 1) / S;
-                    const int kbeg = sl * per, kend = min(pos, kbeg + per);          // cached keys only (position pos is appended by the op)
-                    if (kend > kbeg) {
-                        const long long off = p.st[v].kv_slot * an.kv_stream_stride + (static_cast<long long>(hk) * an.max_ctx + kbeg) * 128;
-                        const uint32_t bytes = static_cast<uint32_t>(kend - kbeg) * 128u * static_cast<uint32_t>(sizeof(T));
-                        ds_prefetch_l2(reinterpret_cast<const T*>(an.kc) + off, bytes);
-                        ds_prefetch_l2(reinterpret_cast<const T*>(an.vc) + off, bytes);
-                    }
-                }
-            }
             if (nloc == 0) continue;          // no rows of this op: nothing to read, nothing to publish (the producers skip it too)
             const uint32_t tag_in = tag_of(oi - 1), tag_out = tag_of(oi);
             // ---- prologue: stage pro(x_v) for every stream; x_v is polled word by word from the previous op's exchange buffer
@@ -931,7 +924,7 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
             }
             stamp(2);
         } else if (op.type == DS_ATTN) {
-            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, rope_cs, tag_of(oi - 1), tag_of(oi));
+            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, rope_cs, tag_of(oi - 1), tag_of(oi), ring, full_bar, empty_bar, p.n_slots, &rs);
             stamp(4);
         } else {
             // ------------------------------------------------------------------ DS_FINAL: token selection (CTA 0)
