@@ -336,13 +336,27 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             const uint8_t* sv = ring + static_cast<size_t>(slot_v) * kDsSlotBytes + (warp * KB) * (D * sizeof(T));
             const int kb0 = kbeg + blk * kDsKvBlock + warp * KB;          // this warp's 16 keys of the block
             mbar_wait_hint(&full_bar[slot_k], par_k);
+            {   // The block that holds the new position (CTA-uniform): its cache row is not written yet -- the rotated k and the v
+                // of this step are patched into the shared-memory copies of the chunks, so the loops below treat every key alike.
+                const int blk0 = kbeg + blk * kDsKvBlock;
+                if (pos >= blk0 && pos < min(kend, blk0 + kDsKvBlock)) {
+                    mbar_wait_hint(&full_bar[slot_v], par_v);
+                    if (tid < D) {
+                        const size_t row = static_cast<size_t>(pos - blk0) * D;
+                        reinterpret_cast<T*>(const_cast<uint8_t*>(ring) + static_cast<size_t>(slot_k) * kDsSlotBytes)[row + tid] = Cvt<T>::from_f(sm_kn[tid]);
+                        reinterpret_cast<T*>(const_cast<uint8_t*>(ring) + static_cast<size_t>(slot_v) * kDsSlotBytes)[row + tid] = Cvt<T>::from_f(sm_vn[tid]);
+                        fence_proxy_async_smem();      // generic-proxy writes to a slot that the next bulk copy (async proxy) overwrites
+                    }
+                    ds_consumer_sync();
+                }
+            }
             if (kb0 < kend) {
             const int key = kb0 + kslot;
             const bool valid = key < kend;
             float sc[GM];
 #pragma unroll
             for (int g = 0; g < GM; ++g) sc[g] = 0.f;
-            if (valid && key != pos) {
+            if (valid) {
 #pragma unroll
                 for (int c = 0; c < D / 16; ++c) {
                     // 16-byte pieces of the half row in an order rotated by the key: rows are 256 bytes apart, so the lanes of a
@@ -361,13 +375,6 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                             sc[g] = t;
                         }
                     }
-                }
-            } else if (valid) {                      // the new token: its k is still in shared memory
-                for (int d = half * (D / 2); d < (half + 1) * (D / 2); ++d) {
-                    const float kd = sm_kn[d];
-#pragma unroll
-                    for (int g = 0; g < GM; ++g)
-                        if (gb + g < group) sc[g] = fmaf(sm_q[(gb + g) * D + d], kd, sc[g]);
                 }
             }
             float cfac[GM];
@@ -397,14 +404,9 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                 const int kk = kb0 + b;
                 if (kk < kend) {
                     float vv[VPL];
-                    if (kk == pos) {
-#pragma unroll
-                        for (int i = 0; i < VPL; ++i) vv[i] = sm_vn[lane * VPL + i];
-                    } else {
-                        const uint2 vr = *reinterpret_cast<const uint2*>(sv + b * (D * sizeof(T)) + lane * (VPL * sizeof(T)));
-                        const float2 a = Cvt<T>::unpack2(vr.x), bb = Cvt<T>::unpack2(vr.y);
-                        vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
-                    }
+                    const uint2 vr = *reinterpret_cast<const uint2*>(sv + b * (D * sizeof(T)) + lane * (VPL * sizeof(T)));
+                    const float2 a = Cvt<T>::unpack2(vr.x), bb = Cvt<T>::unpack2(vr.y);
+                    vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
 #pragma unroll
                     for (int g = 0; g < GM; ++g)
                         if (gb + g < group) {
@@ -532,17 +534,16 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             ds_consumer_sync();
             if (tid < p1 - p0) {
                 const int pr = p0 + tid, g = pr / (D / 2), dp = pr % (D / 2);
+                // two passes (the maximum over the slices first, then independent weights 2^(m_z - M) summed in slice order): a
+                // chain of S dependent rescales would put ~1.5 us per layer on the step's critical path
                 float mm = -INFINITY, ll = 0.f, o0 = 0.f, o1 = 0.f;
+                for (int z = 0; z < S; ++z) mm = fmaxf(mm, sm_mg[tid * S + z].x);
                 for (int z = 0; z < S; ++z) {
                     const float4 t = sm_mg[tid * S + z];
-                    if (t.x != -INFINITY) {
-                        const float mn = fmaxf(mm, t.x);
-                        const float c0 = exp2f(mm - mn), c1 = exp2f(t.x - mn);     // c0 = 0 while mm = -inf
-                        ll = ll * c0 + t.y * c1;
-                        o0 = o0 * c0 + t.z * c1;
-                        o1 = o1 * c0 + t.w * c1;
-                        mm = mn;
-                    }
+                    const float c1 = t.x == -INFINITY ? 0.f : exp2f(t.x - mm);
+                    ll = fmaf(t.y, c1, ll);
+                    o0 = fmaf(t.z, c1, o0);
+                    o1 = fmaf(t.w, c1, o1);
                 }
                 ds_ll_store(op.att_ll + static_cast<long long>(v) * (Hq * D / 2) + (hk * group + g) * (D / 2) + dp, Cvt<T>::pack2(o0 / ll, o1 / ll), tag_out);
             }
