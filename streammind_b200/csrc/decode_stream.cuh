@@ -45,6 +45,9 @@ constexpr int kDsConsumerThreads = kDsConsumerWarps * 32;
 constexpr int kDsSlotBytes = 32 * 1024;
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxStreams = 4;
+#ifndef SMB_DS_WIDE_UB
+#define SMB_DS_WIDE_UB 7
+#endif
 constexpr int kDsKvBlock = 128;             // keys per K / V chunk of the attention op (128 rows of 256 bytes = one ring slot)
 constexpr int kDsResidRows = 64;            // rows of the residual stream one CTA may own (hidden <= 64 x SMs)
 
@@ -249,7 +252,10 @@ struct DsRingState { int seq, slot, par; };   // chunk sequence number of this C
 template <typename T, int NV>
 __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamState* st, unsigned long long* att_part, T* xs,
                                             const float (*rope_cs)[128], uint32_t tag_in, uint32_t tag_out, const uint8_t* ring,
-                                            uint64_t* full_bar, uint64_t* empty_bar, int n_slots, DsRingState* state) {
+                                            uint64_t* full_bar, uint64_t* empty_bar, int n_slots, DsRingState* state, long long* aprobe) {
+    // probe builds (-DSMB_DS_WAITPROBE): thread 0 of CTA 1 accumulates the time between these marks (sm_debug_decode_phases, row 149)
+    DS_PROBE(long long ap_t = (aprobe != nullptr) ? ds_gtimer() : 0;)
+#define DS_ASTAMP(i) DS_PROBE(if (aprobe != nullptr) { const long long t_ = ds_gtimer(); aprobe[i] += t_ - ap_t; ap_t = t_; })
     const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     // ------------------------------------------------------------------ decode attention, split over the KV length
@@ -309,6 +315,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             }
         }
         ds_consumer_sync();
+        DS_ASTAMP(0)      // q / k / v of the projection arrived and rotated
         if (kbeg <= pos && pos < kend && tid < D) {          // the slice holding the new position appends it
             kcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_kn[tid]);
             vcache[static_cast<long long>(pos) * D + tid] = Cvt<T>::from_f(sm_vn[tid]);
@@ -422,6 +429,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             __syncwarp();
             if (lane == 0) { mbar_arrive(&empty_bar[slot_k]); mbar_arrive(&empty_bar[slot_v]); }
         }
+        DS_ASTAMP(4)      // key blocks: scores, softmax, P V
 #pragma unroll
         for (int g = 0; g < GM; ++g)
             if (gb + g < group) l[g] = warp_sum(l[g]);
@@ -463,6 +471,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             }
         }
         ds_consumer_sync();
+        DS_ASTAMP(5)      // row sums, per-warp partials in shared memory
         unsigned long long* pbase = att_part + (static_cast<long long>(v) * Hq + hk * group) * S * (D + 2);
         const int npass = min(GM, group - gb);
         for (int idx = tid; idx < npass * D; idx += kDsConsumerThreads) {
@@ -480,6 +489,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             if (d == 0) { ds_ll_store(dst, __float_as_uint(mm), tag_out); ds_ll_store(dst + 1, __float_as_uint(ll), tag_out); }
         }
         ds_consumer_sync();      // the scratch is rewritten by the next pass / item / op
+        DS_ASTAMP(1)      // warps merged, partial published
         }   // gb
     }
     *state = rs;
@@ -532,6 +542,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                 }
             }
             ds_consumer_sync();
+            DS_ASTAMP(2)      // partials of all slices polled
             if (tid < p1 - p0) {
                 const int pr = p0 + tid, g = pr / (D / 2), dp = pr % (D / 2);
                 // two passes (the maximum over the slices first, then independent weights 2^(m_z - M) summed in slice order): a
@@ -548,8 +559,10 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                 ds_ll_store(op.att_ll + static_cast<long long>(v) * (Hq * D / 2) + (hk * group + g) * (D / 2) + dp, Cvt<T>::pack2(o0 / ll, o1 / ll), tag_out);
             }
             ds_consumer_sync();      // the scratch is rewritten by the next item / op
+            DS_ASTAMP(3)      // slices folded, output published
         }
     }
+#undef DS_ASTAMP
 }
 
 
@@ -778,7 +791,9 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
     DsRingState rs{0, 0, 0};
     long long probe_acc[2] = {0, 0};
     long long* probe_w = nullptr;
-    DS_PROBE(if (timed) probe_w = probe_acc;)
+    long long aprobe_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // attention sub-phases (probe builds)
+    long long* aprobe_w = nullptr;
+    DS_PROBE(if (timed) { probe_w = probe_acc; aprobe_w = aprobe_acc; })
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const DsOp& op = p.ops[oi];
         if (op.type == DS_GEMV) {
@@ -806,7 +821,8 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                     const unsigned long long* xl = op.xll + v * op.xll_stride;
                     uint2* xw = reinterpret_cast<uint2*>(xv);
                     const int nq = K / 4;                                               // word pairs = 4 elements
-                    constexpr int UB = 4;                                               // 16-byte polls in flight per thread
+                    auto poll_batches = [&](auto ub_tag) {
+                    constexpr int UB = decltype(ub_tag)::value;                         // 16-byte polls in flight per thread
                     for (int q0 = tid; q0 < nq; q0 += UB * kDsConsumerThreads) {
                         unsigned long long r[UB][2];
                         unsigned spins = 0;
@@ -835,6 +851,11 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                             }
                         }
                     }
+                    };
+                    // every dependent poll round costs an L2 round trip: a vector wider than 4 polls per thread (down_proj's 14 336
+                    // inputs = 14 per thread) is polled as two batches of 7 instead of four batches of 4 in a row (one batch of 14: same chain time, slower ring loop)
+                    if (nq > 4 * kDsConsumerThreads) poll_batches(std::integral_constant<int, SMB_DS_WIDE_UB>{});
+                    else poll_batches(std::integral_constant<int, 4>{});
                 }
                 if (op.pro != DSP_PLAIN) {
                     s2 = warp_sum(s2);
@@ -925,7 +946,7 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
             }
             stamp(2);
         } else if (op.type == DS_ATTN) {
-            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, rope_cs, tag_of(oi - 1), tag_of(oi), ring, full_bar, empty_bar, p.n_slots, &rs);
+            ds_attention_op<T, NV>(op, p.st, p.att_part, xs, rope_cs, tag_of(oi - 1), tag_of(oi), ring, full_bar, empty_bar, p.n_slots, &rs, aprobe_w);
             stamp(4);
         } else {
             // ------------------------------------------------------------------ DS_FINAL: token selection (CTA 0)
@@ -937,7 +958,8 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                     if (cta == 0) p.dbg[cat] += t_acc[c];
                 }
                 DS_PROBE(p.dbg[8 * (cta + 1) + 6] += probe_acc[0]; p.dbg[8 * (cta + 1) + 7] += probe_acc[1];
-                         if (cta == 0) { p.dbg[6] += probe_acc[0]; p.dbg[7] += probe_acc[1]; })
+                         if (cta == 0) { p.dbg[6] += probe_acc[0]; p.dbg[7] += probe_acc[1]; }
+                         if (cta == 1) for (int i = 0; i < 8; ++i) p.dbg[8 * 149 + i] += aprobe_acc[i];)      // attention sub-phases of CTA 1
             }
             if (cta == 0 && warp == 0) {
                 int all_done = 1;

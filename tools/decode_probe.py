@@ -35,7 +35,7 @@ for s in range(a.streams):
 sids = list(range(a.streams))
 eng.llm_decode_multi(sids, [8] * a.streams)            # warm-up
 eng.decode_stats(reset=True)
-buf = torch.zeros(8 * 160, dtype=torch.int64, device=dev)      # row 0: CTA 0, rows 1..148: every CTA, row 149: attention sub-phases of CTA 1 (probe build)
+buf = torch.zeros(8 * 160, dtype=torch.int64, device=dev)      # row 0: CTA 0, rows 1..148: every CTA, row 149: attention sub-phases of CTA 1 (probe build)      # row 0: CTA 0, rows 1..148: every CTA, row 149: attention sub-phases of CTA 1 (probe build)
 if a.phases:
     eng.lib.sm_debug_decode_phases(eng._h, C.c_void_p(buf.data_ptr()))
 eng.llm_decode_multi(sids, [a.new] * a.streams)
@@ -60,6 +60,11 @@ if a.phases:
         order = col.argsort()
         print(f"  per-CTA {n}: min {col.min():.0f} (cta {int(order[0])}), median {col.median():.0f}, max {col.max():.0f} (cta {int(order[-1])}); "
               f"lowest 5: {[int(x) for x in order[:5]]}, highest 5: {[int(x) for x in order[-5:]]}")
+    sub = v[8 * 149:8 * 149 + 6]
+    if any(sub):
+        print("CTA 1 attention sub-phases (us per step): " + ", ".join(f"{n} {x / st['steps'] / 1e3:.1f}" for n, x in zip(
+            ["wait q/k/v + rope", "merge warps + publish partial", "poll partials", "fold + publish", "key blocks (scores, softmax, P V)",
+             "row sums + warp partials to smem"], sub)))
     sub = v[8 * 149:8 * 149 + 6]
     if any(sub):
         print("CTA 1 attention sub-phases (us per step): " + ", ".join(f"{n} {x / st['steps'] / 1e3:.1f}" for n, x in zip(
