@@ -316,24 +316,49 @@ __global__ void __launch_bounds__(kAkvThreads, 1) attention_kv_tc_kernel(const _
     }
 }
 
-// Merge of the key-range splits: one CTA per (token, query head), thread = output dim; fixed order over the splits.
+// Merge of the key-range splits: one CTA per (token, query head); warp w folds the splits z = w, w + 4, ... (lane = 4 output
+// dims, 16-byte loads, the splits of a warp independent of each other), then the four warps are combined in fixed order.
 template <typename T>
 __global__ void __launch_bounds__(128) attention_kv_merge_kernel(const AttnKvArgs a) {
+    __shared__ float sm_m[4], sm_l[4];
+    __shared__ float4 sm_o[4][32];
     pdl_trigger();
     pdl_wait();
-    const int tok = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
-    float M = -INFINITY;
-    for (int z = 0; z < a.n_splits; ++z) M = fmaxf(M, a.ws_ml[((static_cast<long long>(z) * a.P + tok) * a.Hq + head) * 2]);
-    float L = 0.f, o = 0.f;
-    for (int z = 0; z < a.n_splits; ++z) {
+    const int tok = blockIdx.x, head = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = -INFINITY, l = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = warp; z < a.n_splits; z += 4) {
         const long long prow = (static_cast<long long>(z) * a.P + tok) * a.Hq + head;
-        const float m = a.ws_ml[prow * 2];
-        if (m == -INFINITY) continue;                // the split saw no visible key of this row (its O was not written)
-        const float w = atc_ex2(m - M);
-        L += w * a.ws_ml[prow * 2 + 1];
-        o += w * a.ws_o[prow * 128 + d];
+        const float2 ml = *reinterpret_cast<const float2*>(a.ws_ml + prow * 2);
+        if (ml.x == -INFINITY) continue;             // the split saw no visible key of this row (its O was not written)
+        const float4 oz = reinterpret_cast<const float4*>(a.ws_o + prow * 128)[lane];
+        const float mn = fmaxf(m, ml.x);
+        const float c0 = atc_ex2(m - mn), c1 = atc_ex2(ml.x - mn);       // c0 = 0 while m = -inf
+        l = l * c0 + ml.y * c1;
+        o.x = o.x * c0 + oz.x * c1; o.y = o.y * c0 + oz.y * c1; o.z = o.z * c0 + oz.z * c1; o.w = o.w * c0 + oz.w * c1;
+        m = mn;
     }
-    reinterpret_cast<T*>(a.o)[static_cast<long long>(tok) * a.o_ss + head * 128 + d] = Cvt<T>::from_f(L > 0.f ? o / L : 0.f);
+    if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+    sm_o[warp][lane] = o;
+    __syncthreads();
+    if (warp == 0) {
+        float M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
+        float L = 0.f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (sm_m[w] == -INFINITY) continue;
+            const float c = atc_ex2(sm_m[w] - M);
+            const float4 ow = sm_o[w][lane];
+            L += sm_l[w] * c;
+            r.x += ow.x * c; r.y += ow.y * c; r.z += ow.z * c; r.w += ow.w * c;
+        }
+        const float inv = L > 0.f ? 1.0f / L : 0.f;
+        uint2 pk;
+        pk.x = Cvt<T>::pack2(r.x * inv, r.y * inv);
+        pk.y = Cvt<T>::pack2(r.z * inv, r.w * inv);
+        *reinterpret_cast<uint2*>(reinterpret_cast<T*>(a.o) + static_cast<long long>(tok) * a.o_ss + head * 128 + lane * 4) = pk;
+    }
 }
 
 }  // namespace smb
