@@ -127,7 +127,7 @@ struct DsParams {
     int H;
     unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
     unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
-    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone)
+    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone), 16 weight chunks from L2 (every chunk re-reads the op's first rows)
     long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
 
@@ -727,8 +727,9 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                 const size_t row_bytes = static_cast<size_t>(op.K) * sizeof(T);
                 for (int j = j0; j < j1; j += RJ) {
                     const uint32_t bytes = static_cast<uint32_t>(min(RJ, j1 - j) * row_bytes);
-                    put(static_cast<const uint8_t*>(op.W0) + j * row_bytes,
-                        op.nmat == 2 ? static_cast<const uint8_t*>(op.W1) + j * row_bytes : nullptr, bytes, static_cast<uint32_t>(RJ * row_bytes));
+                    const int js = (p.dbg_flags & 16) ? j0 : j;      // measurement only: every chunk re-reads the op's first rows (L2 hits: the consumers' own speed)
+                    put(static_cast<const uint8_t*>(op.W0) + js * row_bytes,
+                        op.nmat == 2 ? static_cast<const uint8_t*>(op.W1) + js * row_bytes : nullptr, bytes, static_cast<uint32_t>(RJ * row_bytes));
                 }
             } else if (op.type == DS_ATTN) {
                 const int Hk = op.Hk, group = op.Hq / Hk, S = max(1, G / Hk), npass = (group + 3) / 4;
