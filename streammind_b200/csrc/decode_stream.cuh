@@ -270,14 +270,15 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
     const int Hq = op.Hq, Hk = op.Hk, group = Hq / Hk;
     const int S = max(1, G / Hk);                        // KV slices per (lane, kv head): independent of NV, so a stream's
                                                          // arithmetic (and ids) do not depend on what it is batched with
-    float* sm_q = reinterpret_cast<float*>(xs);           // [group][D] rotated q heads of the group (fp32 values of T)
-    float* sm_kn = sm_q + group * D;                      // [D] rotated new k
+    constexpr int QH = D / 2 + 4, QS = 2 * QH;            // q head = two halves of 64 + 4 pad floats: the two lanes of a key read different banks
+    float* sm_q = reinterpret_cast<float*>(xs);           // [group][QS] rotated q heads of the group (fp32 values of T)
+    float* sm_kn = sm_q + group * QS;                     // [D] rotated new k
     float* sm_vn = sm_kn + D;                             // [D] new v
     float* sm_cs = sm_vn + D;                             // [D/2] cos, [D/2] sin
     float* sm_m = sm_cs + D;                              // [8][8]
     float* sm_l = sm_m + kDsGroupWarps * 8;
     float* sm_o = sm_l + kDsGroupWarps * 8;               // [8][group][D]
-    float* sm_p = sm_o + kDsGroupWarps * group * D + warp * group * KB;   // this warp's [group][KB] probabilities of a key block
+    float* sm_p = sm_o + kDsGroupWarps * group * D + warp * max(group, GM) * KB;   // this warp's [KB][GM] probabilities of a key block (one pass)
     DsRingState rs = *state;
     for (int item = cta; item < NV * Hk * S; item += G) {
         const int v = item / (Hk * S), hk = (item / S) % Hk, s = item % S;
@@ -302,11 +303,12 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                 unsigned spins = 0;
                 while (!(ds_ll_ok(ra, tag_in) && ds_ll_ok(rb, tag_in))) { ds_ll_retry(spins, tag_in); ra = ds_ll_load(wa); rb = ds_ll_load(wa + D / 4); }
                 const float2 x1 = Cvt<T>::unpack2(static_cast<uint32_t>(ra)), x2 = Cvt<T>::unpack2(static_cast<uint32_t>(rb));
-                float* dst = hh < group ? sm_q + hh * D : sm_kn;
+                float* dst = hh < group ? sm_q + hh * QS : sm_kn;
+                const int h2 = hh < group ? QH : D / 2;          // offset of the second half of the row
                 dst[d] = rnd<T>(rnd<T>(x1.x * cs0) + rnd<T>(-x2.x * sn0));
                 dst[d + 1] = rnd<T>(rnd<T>(x1.y * cs1) + rnd<T>(-x2.y * sn1));
-                dst[d + D / 2] = rnd<T>(rnd<T>(x2.x * cs0) + rnd<T>(x1.x * sn0));
-                dst[d + D / 2 + 1] = rnd<T>(rnd<T>(x2.y * cs1) + rnd<T>(x1.y * sn1));
+                dst[h2 + d] = rnd<T>(rnd<T>(x2.x * cs0) + rnd<T>(x1.x * sn0));
+                dst[h2 + d + 1] = rnd<T>(rnd<T>(x2.y * cs1) + rnd<T>(x1.y * sn1));
             } else {
                 const int w = jb - (group + 1) * (D / 4);
                 const float2 f = Cvt<T>::unpack2(ds_ll_get(ql + ((Hq + Hk + hk) * D) / 2 + w, tag_in));
@@ -366,16 +368,17 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             if (valid) {
 #pragma unroll
                 for (int c = 0; c < D / 16; ++c) {
-                    // 16-byte pieces of the half row in an order rotated by the key: rows are 256 bytes apart, so the lanes of a
-                    // quarter warp would otherwise all read the same banks
-                    const int cc = (c + kslot) & (D / 16 - 1);
+                    // 16-byte pieces of the half row in an order rotated by the key (4 rotations): rows are 256 bytes apart, so the
+                    // lanes would otherwise all read the same banks; with 4 rotations and the padded q layout a K read is 8 wavefronts
+                    // and a q read 1 (8 rotations: 4 and 4 per q read, of which there are eight per K read)
+                    const int cc = (c + (kslot & 3)) & (D / 16 - 1);
                     const uint4 u = *reinterpret_cast<const uint4*>(sk + kslot * (D * sizeof(T)) + half * (D / 2) * sizeof(T) + cc * 16);
                     const float2 k0 = Cvt<T>::unpack2(u.x), k1 = Cvt<T>::unpack2(u.y), k2 = Cvt<T>::unpack2(u.z), k3 = Cvt<T>::unpack2(u.w);
 #pragma unroll
                     for (int g = 0; g < GM; ++g) {
                         if (gb + g < group) {
-                            const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + cc * 8);
-                            const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * D + half * (D / 2) + cc * 8 + 4);
+                            const float4 qa = *reinterpret_cast<const float4*>(sm_q + (gb + g) * QS + half * QH + cc * 8);
+                            const float4 qb = *reinterpret_cast<const float4*>(sm_q + (gb + g) * QS + half * QH + cc * 8 + 4);
                             float t = sc[g];
                             t = fmaf(qa.x, k0.x, t); t = fmaf(qa.y, k0.y, t); t = fmaf(qa.z, k1.x, t); t = fmaf(qa.w, k1.y, t);
                             t = fmaf(qb.x, k2.x, t); t = fmaf(qb.y, k2.y, t); t = fmaf(qb.z, k3.x, t); t = fmaf(qb.w, k3.y, t);
@@ -394,7 +397,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                     cfac[g] = exp2f(mx[g] - mn);                              // 0 for the first block (mx = -inf)
                     const float pr = valid ? rnd<T>(exp2f(sv - mn)) : 0.f;    // P is rounded to T before it multiplies V
                     l[g] = l[g] * cfac[g] + (half == 0 ? pr : 0.f);           // lane-local partial of the row sum
-                    if (half == 0) sm_p[g * KB + kslot] = pr;
+                    if (half == 0) sm_p[kslot * GM + g] = pr;
                     mx[g] = mn;
                 }
             }
@@ -414,12 +417,13 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                     const uint2 vr = *reinterpret_cast<const uint2*>(sv + b * (D * sizeof(T)) + lane * (VPL * sizeof(T)));
                     const float2 a = Cvt<T>::unpack2(vr.x), bb = Cvt<T>::unpack2(vr.y);
                     vv[0] = a.x; vv[1] = a.y; vv[2] = bb.x; vv[3] = bb.y;
+                    const float4 p4 = *reinterpret_cast<const float4*>(sm_p + b * GM);      // the key's probabilities for the pass's heads
+                    const float prs[GM] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
                     for (int g = 0; g < GM; ++g)
                         if (gb + g < group) {
-                            const float pr = sm_p[g * KB + b];
 #pragma unroll
-                            for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(pr, vv[i], o[g][i]);
+                            for (int i = 0; i < VPL; ++i) o[g][i] = fmaf(prs[g], vv[i], o[g][i]);
                         }
                 }
             }
@@ -1050,8 +1054,8 @@ __global__ void __launch_bounds__(1024) ds_first_token_kernel(const float* __res
 
 // bytes of the attention scratch that aliases the vector staging region (GQA group g)
 inline size_t decode_stream_attn_scratch_bytes(int group) {
-    return (static_cast<size_t>(group) * 128 + 3 * 128 + 2 * kDsGroupWarps * 8 + static_cast<size_t>(kDsGroupWarps) * group * 128 +
-            static_cast<size_t>(kDsConsumerWarps) * group * 16) * sizeof(float);
+    return (static_cast<size_t>(group) * 136 + 3 * 128 + 2 * kDsGroupWarps * 8 + static_cast<size_t>(kDsGroupWarps) * group * 128 +
+            static_cast<size_t>(kDsConsumerWarps) * (group > 4 ? group : 4) * 16) * sizeof(float);
 }
 inline size_t decode_stream_smem_bytes(int n_slots, int x_bytes, int part_cap) {
     return static_cast<size_t>(n_slots) * kDsSlotBytes + static_cast<size_t>(x_bytes) + static_cast<size_t>(part_cap) * sizeof(float);
