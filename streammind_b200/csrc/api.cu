@@ -618,10 +618,10 @@ int init_kernel_attrs_t(sm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem_bytes()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
     CUDA_OK(h, cudaFuncSetAttribute(attention_kv_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_kv_smem_bytes()));
-    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 1) * 1024));   // static: <= 1 KB per stream
-    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 2) * 1024));   // static: <= 1 KB per stream
-    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 3) * 1024));   // static: <= 1 KB per stream
-    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 4) * 1024));   // static: <= 1 KB per stream
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 1) * 1024 - (kDsGroups > 1 ? 2048 : 0)));   // static: <= 1 KB per stream
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 2) * 1024 - (kDsGroups > 1 ? 2048 : 0)));   // static: <= 1 KB per stream
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 3) * 1024 - (kDsGroups > 1 ? 2048 : 0)));   // static: <= 1 KB per stream
+    CUDA_OK(h, cudaFuncSetAttribute(decode_stream_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 4) * 1024 - (kDsGroups > 1 ? 2048 : 0)));   // static: <= 1 KB per stream
     return 0;
 }
 
@@ -1041,7 +1041,7 @@ DsSmem ds_smem_plan(const sm_handle* h, int nv) {
     m.x_bytes = static_cast<int>(std::max<size_t>(static_cast<size_t>(nv) * h->ds_xcap * 2, decode_stream_attn_scratch_bytes(group)));
     m.x_bytes = (m.x_bytes + 127) & ~127;
     m.part_cap = (h->ds_part_rows * nv + 31) & ~31;
-    const long long budget = (227 - nv) * 1024 /* static shared memory of the kernel: <= 1 KB per stream */ - m.x_bytes - static_cast<long long>(m.part_cap) * 4;
+    const long long budget = (227 - nv) * 1024 - (kDsGroups > 1 ? 2048 : 0) /* static shared memory of the kernel: <= 1 KB per stream */ - m.x_bytes - static_cast<long long>(m.part_cap) * 4;
     static const int env_slots = getenv("SMB_DS_SLOTS") ? atoi(getenv("SMB_DS_SLOTS")) : kDsMaxSlots;
     m.n_slots = static_cast<int>(std::max<long long>(0, std::min<long long>(std::min(env_slots, kDsMaxSlots), budget / kDsSlotBytes)));
     m.total = decode_stream_smem_bytes(m.n_slots, m.x_bytes, m.part_cap);

@@ -39,7 +39,7 @@ constexpr int kDsConsumerWarps = kDsGroupWarps * kDsGroups;
 // in flight per SM = the issuing threads).  Measured at ctx 2048 (tools/decode_probe.py): one stream 3.05 ms per step with three
 // producer warps vs 3.14 with two; two / four streams 4.32 / 6.87 vs 4.05 / 6.27 -- the third warp is worth it for one stream only
 // (how many of the warps issue matters less than the block shape: 2 .. 6 issuing threads in the 11-warp block all give 3.07-3.15).
-__host__ __device__ constexpr int ds_producer_warps(int nv) { return nv == 1 ? 3 : 2; }
+__host__ __device__ constexpr int ds_producer_warps(int nv) { return (nv == 1 && kDsGroups == 1) ? 3 : 2; }
 __host__ __device__ constexpr int ds_threads(int nv) { return (kDsConsumerWarps + ds_producer_warps(nv)) * 32; }
 constexpr int kDsConsumerThreads = kDsConsumerWarps * 32;
 constexpr int kDsSlotBytes = 32 * 1024;
@@ -127,7 +127,7 @@ struct DsParams {
     int H;
     unsigned long long* att_part;   // [NV][Hq][S][D + 2] tagged words: split-KV partials (m, l, o[D]) as fp32 bits
     unsigned long long* cand;       // [NV][gridDim.x][2] tagged words: per-CTA argmax candidates (value bits, index)
-    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone), 16 weight chunks from L2 (every chunk re-reads the op's first rows)
+    int dbg_flags;           // measurement only: 1 skip the consumer math, 2 no weight stream (exchange chain alone), 16 weight chunks from L2 (every chunk re-reads the op's first rows), 32 no copies after the first lap of the ring (the consumers alone)
     long long* dbg;          // optional: CTA 0 accumulates ns per phase (0 prologue incl. waiting for the input, 1 ring compute, 2 epilogue, 4 attention)
 };
 
@@ -344,11 +344,12 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
             const uint8_t* sk = ring + static_cast<size_t>(slot_k) * kDsSlotBytes + (warp * KB) * (D * sizeof(T));
             const uint8_t* sv = ring + static_cast<size_t>(slot_v) * kDsSlotBytes + (warp * KB) * (D * sizeof(T));
             const int kb0 = kbeg + blk * kDsKvBlock + warp * KB;          // this warp's 16 keys of the block
-            mbar_wait_hint(&full_bar[slot_k], par_k);
+            if (kDsGroups == 1 || warp < kDsGroupWarps) mbar_wait_hint(&full_bar[slot_k], par_k);
             {   // The block that holds the new position (CTA-uniform): its cache row is not written yet -- the rotated k and the v
                 // of this step are patched into the shared-memory copies of the chunks, so the loops below treat every key alike.
                 const int blk0 = kbeg + blk * kDsKvBlock;
                 if (pos >= blk0 && pos < min(kend, blk0 + kDsKvBlock)) {
+                    if (kDsGroups > 1 && warp >= kDsGroupWarps) mbar_wait_hint(&full_bar[slot_k], par_k);
                     mbar_wait_hint(&full_bar[slot_v], par_v);
                     if (tid < D) {
                         const size_t row = static_cast<size_t>(pos - blk0) * D;
@@ -359,6 +360,7 @@ __device__ __forceinline__ void ds_attention_op(const DsOp& op, const DsStreamSt
                     ds_consumer_sync();
                 }
             }
+            if (kDsGroups > 1 && warp >= kDsGroupWarps) continue;      // a second consumer group (experiment builds) has no part in the key blocks
             if (kb0 < kend) {
             const int key = kb0 + kslot;
             const bool valid = key < kend;
@@ -715,10 +717,14 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                     mbar_wait_hint(&empty_bar[slot], (use - 1) & 1);
                     DS_PROBE(pb_blocked += ds_gtimer() - tb;)
                 }
-                mbar_arrive_expect_tx(&full_bar[slot], s1 ? 2 * bytes : bytes);
-                uint8_t* dst = ring + static_cast<size_t>(slot) * kDsSlotBytes;
-                ds_bulk_g2s(dst, s0, bytes, &full_bar[slot]);
-                if (s1) ds_bulk_g2s(dst + off1, s1, bytes, &full_bar[slot]);
+                if ((p.dbg_flags & 32) && use > 0) {      // measurement only: no copy after the first lap, the slot is declared full as it is
+                    mbar_arrive(&full_bar[slot]);
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[slot], s1 ? 2 * bytes : bytes);
+                    uint8_t* dst = ring + static_cast<size_t>(slot) * kDsSlotBytes;
+                    ds_bulk_g2s(dst, s0, bytes, &full_bar[slot]);
+                    if (s1) ds_bulk_g2s(dst + off1, s1, bytes, &full_bar[slot]);
+                }
             }
             ++seq;
         };
