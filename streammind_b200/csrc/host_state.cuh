@@ -266,3 +266,5 @@ struct ProfScope {
     ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
+
+}  // namespace
