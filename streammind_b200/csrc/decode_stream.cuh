@@ -814,6 +814,17 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
             const int nloc = j1 - j0;
             if (nloc == 0) continue;          // no rows of this op: nothing to read, nothing to publish (the producers skip it too)
             const uint32_t tag_in = tag_of(oi - 1), tag_out = tag_of(oi);
+            // the RMSNorm weights of this thread's elements are requested BEFORE the input is polled: loaded in the second pass they put an
+            // L2 round trip on the chain of every normalising op (64 per step)
+            uint4 nw_pre[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+            const bool nw_fit = op.pro != DSP_PLAIN && K <= 2 * kDsConsumerThreads * 8;
+            if (nw_fit) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int k = (tid + i * kDsConsumerThreads) * 8;
+                    if (k < K) nw_pre[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(op.nw) + k);
+                }
+            }
             // ---- prologue: stage pro(x_v) for every stream; x_v is polled word by word from the previous op's exchange buffer
 #pragma unroll 1
             for (int v = 0; v < NV; ++v) {
@@ -883,9 +894,10 @@ __global__ void __launch_bounds__(ds_threads(NV), 1) decode_stream_kernel(const 
                     const float r = rsqrtf(t2 / static_cast<float>(K) + op.eps);
                     T* xv = xs + static_cast<size_t>(v) * p.xcap;
                     const T* nw = reinterpret_cast<const T*>(op.nw);
-                    for (int k = tid * 8; k < K; k += kDsConsumerThreads * 8) {
+#pragma unroll 2
+                    for (int k = tid * 8, i = 0; k < K; k += kDsConsumerThreads * 8, ++i) {
                         const uint4 u = *reinterpret_cast<const uint4*>(xv + k);
-                        const uint4 g = *reinterpret_cast<const uint4*>(nw + k);
+                        const uint4 g = nw_fit ? (i == 0 ? nw_pre[0] : nw_pre[1]) : *reinterpret_cast<const uint4*>(nw + k);
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {g.x, g.y, g.z, g.w};
                         uint32_t o[4];
 #pragma unroll
