@@ -219,10 +219,9 @@ int run_gate_gemm(sm_handle* h, const void* toks, float* logits_out, int n, cuda
     h->gemm_class = KC_GATE_GEMM;
     if (!kon(h, KC_GATE_GEMM)) return 0;
     CUDA_OK(h, cudaMemcpyAsync(h->gg_h, toks, static_cast<size_t>(n) * H * h->esz, cudaMemcpyDeviceToDevice, st));
-    const int nb = (n + 7) / 8;
     auto rms = [&](const void* nw) -> int {
         DISPATCH_T(h, T, {
-            CUDA_OK(h, launch_pdl(h, rmsnorm_rows_kernel<T>, dim3(nb), dim3(256), 0, st, (const T*)h->gg_h, (const T*)nw, (T*)h->gg_hn, n, H, c.gate_eps));
+            CUDA_OK(h, launch_pdl(h, rmsnorm_rows_kernel<T>, dim3(n), dim3(kRmsRowsThreads), 0, st, (const T*)h->gg_h, (const T*)nw, (T*)h->gg_hn, n, H, c.gate_eps));
             count_launch(h);
         })
         return 0;
@@ -283,7 +282,6 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     const int H = c.llm_hidden, Hq = c.llm_heads, Hk = c.llm_kv_heads, D = c.llm_head_dim, F = c.llm_ffn;
     const int QKV = (Hq + 2 * Hk) * D;
     CUDA_OK(h, cudaMemcpyAsync(h->lw_x, embeds, static_cast<size_t>(P) * H * h->esz, cudaMemcpyDeviceToDevice, st));
-    const int nb = (P + 7) / 8;
     // short dialogue suffixes (a fire prefills 11-74 new tokens): the narrow projections are split along K
     static const bool few_on = getenv("SMB_PREFILL_SPLITK") ? atoi(getenv("SMB_PREFILL_SPLITK")) != 0 : true;
     const bool few = few_on && P <= 64 && h->lw_part2 != nullptr;
@@ -292,7 +290,7 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             if (kon(h, KC_RMSNORM_ROWS)) {
-            rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
             }
             count_launch(h);
         })
@@ -322,7 +320,7 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             if (kon(h, KC_RMSNORM_ROWS)) {
-            rmsnorm_rows_kernel<T><<<nb, 256, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
             }
             count_launch(h);
         })
