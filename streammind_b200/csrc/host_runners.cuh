@@ -187,8 +187,11 @@ int run_gate(sm_handle* h, const void* tok, float* logits_out, int nv, cudaStrea
 // N / 128 CTAs alone cannot pull HBM bandwidth for narrow outputs (32-48 tiles for the 4096 / 6144-wide projections), so
 // K is split until about one CTA per SM streams weights; the fp32 partials are summed in fixed order by
 // splitk_rows_kernel (T(resid + T(sum)) for the in-place residual stream).  part: [8][n][N] floats.
+// deferred != nullptr: when K is split, the partials are left for the caller's next kernel to fold (rmsnorm_rows_kernel does it for the
+// residual stream) and *deferred = the number of splits; 0 when the GEMM wrote `out` itself.
 int gemm_few_rows(sm_handle* h, const void* x, int n, const void* W, int N, int K, void* out, bool residual, float* part,
-                  cudaStream_t st) {
+                  cudaStream_t st, int* deferred = nullptr) {
+    if (deferred) *deferred = 0;
     const int tiles = (N + 127) / 128, kb = (K + 63) / 64;
     const int bn = std::max(16, (n + 15) / 16 * 16);
     int split = std::min({8, std::max(1, h->num_sms / tiles), std::max(1, kb / 8)});
@@ -196,6 +199,7 @@ int gemm_few_rows(sm_handle* h, const void* x, int n, const void* W, int N, int 
     if (split < 2 || part == nullptr)
         return launch_gemm(h, x, n, W, N, K, nullptr, out, N, residual ? EPI_RESIDUAL : EPI_STORE, st, 1, bn);
     if (launch_gemm(h, x, n, W, N, K, nullptr, part, N, EPI_STORE_F32, st, 1, bn, false, split)) return 1;
+    if (deferred) { *deferred = split; return 0; }
     DISPATCH_T(h, T, {
         const long long tot = static_cast<long long>(n) * N;
         if (kon(h, h->gemm_class)) {
@@ -221,7 +225,7 @@ int run_gate_gemm(sm_handle* h, const void* toks, float* logits_out, int n, cuda
     CUDA_OK(h, cudaMemcpyAsync(h->gg_h, toks, static_cast<size_t>(n) * H * h->esz, cudaMemcpyDeviceToDevice, st));
     auto rms = [&](const void* nw) -> int {
         DISPATCH_T(h, T, {
-            CUDA_OK(h, launch_pdl(h, rmsnorm_rows_kernel<T>, dim3(n), dim3(kRmsRowsThreads), 0, st, (const T*)h->gg_h, (const T*)nw, (T*)h->gg_hn, n, H, c.gate_eps));
+            CUDA_OK(h, launch_pdl(h, rmsnorm_rows_kernel<T>, dim3(n), dim3(kRmsRowsThreads), 0, st, (const T*)h->gg_h, (const T*)nw, (T*)h->gg_hn, n, H, c.gate_eps, (const float*)nullptr, 0, 0LL, (T*)nullptr));
             count_launch(h);
         })
         return 0;
@@ -285,15 +289,22 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
     // short dialogue suffixes (a fire prefills 11-74 new tokens): the narrow projections are split along K
     static const bool few_on = getenv("SMB_PREFILL_SPLITK") ? atoi(getenv("SMB_PREFILL_SPLITK")) != 0 : true;
     const bool few = few_on && P <= 64 && h->lw_part2 != nullptr;
+    // split-K partials of a residual projection (o_proj, down_proj) are folded into the residual stream by the RMSNorm kernel that
+    // reads it next, not by a kernel of their own; `pending` = splits of the partials in lw_part2 that lw_x is still waiting for
+    int pending = 0;
+    const long long part_stride = static_cast<long long>(P) * H;
+    int* const defer = H <= 8 * kRmsRowsThreads * 8 ? &pending : nullptr;      // the norm kernel folds partials for rows it holds in registers
     for (int l = 0; l < c.llm_layers; ++l) {
         const MistralLayer& L = h->llm[l];
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             if (kon(h, KC_RMSNORM_ROWS)) {
-            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.in_ln, (T*)h->lw_hn, P, H, c.llm_eps,
+                                                                 (const float*)h->lw_part2, pending, part_stride, (T*)h->lw_x);
             }
             count_launch(h);
         })
+        pending = 0;
         if (few) { if (gemm_few_rows(h, h->lw_hn, P, L.wqkv, QKV, H, h->lw_qkv, false, h->lw_part2, st)) return 1; }
         else if (launch_gemm(h, h->lw_hn, P, L.wqkv, QKV, H, nullptr, h->lw_qkv, QKV, EPI_STORE, st)) return 1;
         DISPATCH_T(h, T, {
@@ -315,15 +326,17 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
             DISPATCH_T(h, T, { if (launch_attn_kv_tc_t<T>(h, h->lw_qkv, h->pmax, QKV, 0, a.k, a.v, c.llm_max_ctx, h->lw_att, Hq * D, P, pos0, Hq, Hk,
                                                           a.scale_log2e, 0, st)) return 1; })
         } else if (launch_attn(h, a, D, Hq, 1, st)) return 1;
-        if (few) { if (gemm_few_rows(h, h->lw_att, P, L.wo, H, Hq * D, h->lw_x, true, h->lw_part2, st)) return 1; }
+        if (few) { if (gemm_few_rows(h, h->lw_att, P, L.wo, H, Hq * D, h->lw_x, true, h->lw_part2, st, defer)) return 1; }
         else if (launch_gemm(h, h->lw_att, P, L.wo, H, Hq * D, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
         DISPATCH_T(h, T, {
             ProfScope ps_kc_rmsnorm_rows(h, KC_RMSNORM_ROWS, st);
             if (kon(h, KC_RMSNORM_ROWS)) {
-            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps);
+            rmsnorm_rows_kernel<T><<<P, kRmsRowsThreads, 0, st>>>((const T*)h->lw_x, (const T*)L.post_ln, (T*)h->lw_hn, P, H, c.llm_eps,
+                                                                 (const float*)h->lw_part2, pending, part_stride, (T*)h->lw_x);
             }
             count_launch(h);
         })
+        pending = 0;
         if (launch_gemm(h, h->lw_hn, P, L.wgu, 2 * F, H, nullptr, h->lw_gu, 2 * F, EPI_STORE, st)) return 1;
         DISPATCH_T(h, T, {
             const long long tot = static_cast<long long>(P) * F;
@@ -334,8 +347,15 @@ int run_prefill_chunk(sm_handle* h, const void* embeds, int P, int pos0, cudaStr
             }
             count_launch(h);
         })
-        if (few) { if (gemm_few_rows(h, h->lw_m, P, L.wd, H, F, h->lw_x, true, h->lw_part2, st)) return 1; }
+        if (few) { if (gemm_few_rows(h, h->lw_m, P, L.wd, H, F, h->lw_x, true, h->lw_part2, st, defer)) return 1; }
         else if (launch_gemm(h, h->lw_m, P, L.wd, H, F, nullptr, h->lw_x, H, EPI_RESIDUAL, st)) return 1;
+    }
+    if (pending > 0) {        // the last down_proj: nothing normalises the residual stream after it inside this chunk
+        DISPATCH_T(h, T, {
+            CUDA_OK(h, launch_pdl(h, splitk_rows_kernel<T>, dim3(static_cast<int>(std::min<long long>((part_stride + 255) / 256, 1024))), dim3(256), 0, st,
+                                  (const float*)h->lw_part2, pending, part_stride, (const T*)h->lw_x, (T*)h->lw_x, part_stride));
+            count_launch(h);
+        })
     }
     CUDA_OK(h, cudaGetLastError());
     return 0;

@@ -369,8 +369,12 @@ __global__ void gather_rows_kernel(const T* __restrict__ table, const int* __res
 // per 512 bytes: 12 us per launch for 11 rows of 4096), the row is normalised from registers.  Rows wider than 8192 fall back to a loop.
 constexpr int kRmsRowsThreads = 128;
 template <typename T>
-__global__ void __launch_bounds__(kRmsRowsThreads) rmsnorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ nw, T* __restrict__ h, int rows,
-                                                                       int C, float eps) {
+// nsplit > 0: the row is still waiting for the split-K partials of the projection that feeds the residual stream -- part[z][row][c] fp32,
+// z < nsplit, split_stride apart -- and this kernel folds them first (x = T(x + T(sum_z part)), fixed order, written back to x_io),
+// instead of a reduce kernel of its own between the GEMM and the norm.
+__global__ void __launch_bounds__(kRmsRowsThreads) rmsnorm_rows_kernel(const T* x, const T* __restrict__ nw, T* __restrict__ h, int rows,
+                                                                       int C, float eps, const float* __restrict__ part, int nsplit,
+                                                                       long long split_stride, T* x_io) {
     constexpr int MAXI = 8;                       // 16-byte pieces per thread held in registers
     __shared__ float red[kRmsRowsThreads / 32];
     pdl_trigger();
@@ -387,6 +391,30 @@ __global__ void __launch_bounds__(kRmsRowsThreads) rmsnorm_rows_kernel(const T* 
         for (int i = 0; i < MAXI; ++i) {
             const int c = (tid + i * kRmsRowsThreads) * 8;
             if (c < C) { u[i] = *reinterpret_cast<const uint4*>(xr + c); g[i] = *reinterpret_cast<const uint4*>(nw + c); }
+        }
+        if (nsplit > 0) {
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i) {
+                const int c = (tid + i * kRmsRowsThreads) * 8;
+                if (c < C) {
+                    const float* pr = part + static_cast<long long>(row) * C + c;
+                    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                    for (int z = 0; z < nsplit; ++z) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(pr + z * split_stride), p1 = *reinterpret_cast<const float4*>(pr + z * split_stride + 4);
+                        a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w; a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
+                    }
+                    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = Cvt<T>::unpack2(w[j]);
+                        o[j] = Cvt<T>::pack2(f.x + rnd<T>(a[2 * j]), f.y + rnd<T>(a[2 * j + 1]));
+                    }
+                    u[i] = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(x_io + static_cast<long long>(row) * C + c) = u[i];
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < MAXI; ++i) {
