@@ -6,22 +6,24 @@
 // vector), a pipeline fill and a tail, during which HBM idles: 0.64 of the HBM roofline at ctx 4k (round 1).  Here
 // one CTA per SM walks a device-resident op list (GEMV, attention, final argmax); activations travel between the CTAs as
 // tagged 8-byte words that the consumer polls (no grid barrier anywhere in the step, see "activation exchange" below),
-// and the WEIGHT stream never stops: producer warps run ahead of the consumers through a shared-memory ring
-// (kDsSlots x 32 KB, filled by cp.async.bulk, one mbarrier pair per slot) across op boundaries -- weights do not
-// depend on activations -- so epilogue + grid barrier + next prologue (~2-3 us) hide under up to 192 KB / SM of
-// weights already in flight (tools/hbm_read_bench.cu, profiles/r02_hbm_read_bench.txt: bulk copies of >= 32 KB from
-// two issuing threads per SM reach 7.1 TB/s, 16-byte LDG streams 7.3; small copies are issue-bound).
+// and the WEIGHT stream runs ahead: producer warps copy chunks into a shared-memory ring (kDsSlots x 32 KB, cp.async.bulk,
+// one mbarrier pair per slot) across op boundaries -- weights do not depend on activations -- so an op starts with up to
+// 192 KB / SM already on chip (tools/hbm_read_bench.cu, profiles/r02_hbm_read_bench*.txt: bulk copies of >= 32 KB from
+// two issuing threads per SM reach 7.1 TB/s, 16-byte LDG streams 7.3; a thread's bulk copies execute one at a time).
+// What bounds a step is measured in profiles/r02_ncu_decode_kernel.md: the weights at the HBM read rate (2.0 ms) plus the
+// serial exchange chain (0.7 ms), which the ring does not hide because the consumers are no faster than HBM.
 //
 // Work split of a GEMV op  y[n] = epi(sum_k W[n, k] * pro(x)[k]):  CTA c owns rows [c * rpc, (c+1) * rpc) of every
 // matrix of the op; a ring slot holds R = 8 / P consecutive rows (two matrices: R/2 rows of each, the gate and up rows of
 // the same outputs); consumer warp w reduces part w % P (K / P columns) of slot row w / P against the NV staged
-// vectors: fp32 FMA chains, one butterfly per (row, part, vector), partials summed in FIXED order by the epilogue thread
-// of the row (deterministic: greedy decode is reproducible run to run).
+// vectors on mma.sync in a diagonal arrangement (see ds_ring_phase), one butterfly per (row, part, vector), partials
+// summed in FIXED order by the epilogue thread of the row (deterministic: greedy decode is reproducible run to run).
 //
-// Attention op (one query per stream): CTA (stream, kv head, KV slice) applies RoPE to the group's q heads and to the
-// new k, appends k / v to the cache, runs online softmax over its slice (all query heads of the GQA group share each
-// K / V read), publishes an un-normalised partial; the CTA of slice 0 of a (stream, kv head) merges the slices in
-// fixed order (split-KV combine folded in: no extra launch, no counter, no barrier).
+// Attention op (one query per stream): CTA (stream, kv head, KV slice).  The slice's K / V rows arrive through the same ring
+// as the weights (128-key chunks copied by the producers); the CTA applies RoPE (cos / sin from a per-launch table) to the
+// group's q heads and to the new k, appends k / v to the cache and patches them into the chunk copies, runs online softmax
+// over its slice (all query heads of the GQA group share each K / V read), publishes an un-normalised partial; the CTAs
+// of a (stream, kv head) share the merge of the slices, in fixed order (no extra launch, no counter, no barrier).
 // Rounding points are those of the reference (oracle/restate.py mistral_forward): RMSNorm output, every projection
 // output, RoPE products, softmax probabilities before P.V, silu and its product, residual sums, logits.
 #pragma once
